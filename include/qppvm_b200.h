@@ -1,0 +1,161 @@
+/*
+ * qppvm_b200.h — C-ABI of the B200-native whole-body QP hot path.
+ *
+ * This is the drop-in boundary under the two XBotCore RT plugins of the
+ * reference.  One call to qppvm_solve_batch() does, for every record of a
+ * batch, what one tick of the reference does between "model is updated" and
+ * "torques are written":
+ *
+ *   ForceAcc kind  (QPPVM_KIND_FORCEACC)
+ *     replaces  _autostack->update()            ref:src/ForceAcc.cpp:184
+ *               _solver->solve(_x)              ref:src/ForceAcc.cpp:188-193
+ *               qddot/wrench getValue           ref:src/ForceAcc.cpp:196-201
+ *               tau = ID(qddot) - sum J^T w     ref:src/ForceAcc.cpp:206-219
+ *     problem structure (variables, tasks, bounds, eps=1e4)
+ *                                               ref:src/ForceAcc.cpp:58-137
+ *
+ *   Torque kind  (QPPVM_KIND_TORQUE)
+ *     replaces  torque-limit shift by h         ref:src/QPPVMPlugin.cpp:203-205
+ *               _autostack->update(_q)          ref:src/QPPVMPlugin.cpp:226
+ *               _solver->solve(_tau_d)          ref:src/QPPVMPlugin.cpp:246-249
+ *               _tau_d += _h                    ref:src/QPPVMPlugin.cpp:256
+ *     problem structure (tasks, gains, eps=1.0) ref:src/QPPVMPlugin.cpp:112-188
+ *
+ * Plain C: POD structs, raw pointers and sizes.  No C++/torch types cross it.
+ * One handle per calling thread (the reference's single-RT-thread contract).
+ * Every entry point returns 0 on success (== reference's solve()==true for the
+ * call as a whole; per-problem solver status is in the output trailer).
+ */
+#ifndef QPPVM_B200_H_
+#define QPPVM_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- problem kinds -------------------------------------------------------- */
+#define QPPVM_KIND_TORQUE    0  /* x = tau            (ref:src/QPPVMPlugin.cpp)   */
+#define QPPVM_KIND_FORCEACC  1  /* x = [qddot ; f_c]  (ref:src/ForceAcc.cpp:63-70) */
+
+/* ---- optional constraint families (north_star; OpenSoT definitions) ------- */
+#define QPPVM_FLAG_FRICTION_CONES  1  /* 5-row linearised pyramid per contact    */
+#define QPPVM_FLAG_TORQUE_LIMITS   2  /* tau_min <= M_a qdd + h_a - J^T f <= max  */
+
+/* ---- per-problem solver status (reference: bool from solve()) ------------- */
+#define QPPVM_STATUS_OK          0
+#define QPPVM_STATUS_MAX_ITER    1  /* nWSR exhausted                            */
+#define QPPVM_STATUS_INFEASIBLE  2
+#define QPPVM_STATUS_NUMERIC     3  /* active-set overflow / non-finite data     */
+
+/* ---- API return codes ------------------------------------------------------ */
+#define QPPVM_OK                 0
+#define QPPVM_ERR_ARG            1
+#define QPPVM_ERR_UNSUPPORTED    2  /* no kernel instantiated for these dims     */
+#define QPPVM_ERR_CUDA           3
+#define QPPVM_ERR_NO_DEVICE      4
+
+#define QPPVM_QPOASES_EPS        2.221e-16         /* qpOASES EPS                */
+#define QPPVM_QPOASES_EPS_REG    (1.0e3 * QPPVM_QPOASES_EPS) /* default epsRegularisation */
+#define QPPVM_INFTY              1.0e20            /* qpOASES INFTY              */
+#define QPPVM_M0                 6                 /* rows of the level-0 task   */
+
+typedef struct qppvm_desc {
+    int32_t kind;               /* QPPVM_KIND_*                                          */
+    int32_t n_a;                /* actuated joints                                       */
+    int32_t n_contacts;         /* FORCEACC: contacts c; TORQUE: must be 2 (two hands)   */
+    int32_t flags;              /* QPPVM_FLAG_*  (FORCEACC only)                         */
+    double  eps_regularisation; /* QPOases_sot ctor arg: 1e4 (ForceAcc.cpp:137) / 1.0    */
+    int32_t n_reg_steps;        /* qpOASES numRegularisationSteps (MPC option set: 1)    */
+    int32_t max_iter;           /* working-set changes allowed per level (nWSR): 132     */
+    int32_t device;             /* CUDA ordinal                                          */
+    int32_t reserved;
+} qppvm_desc;
+
+/*
+ * Record layout (one problem), all FP64, offsets in doubles, problem-major
+ * contiguous; record stride is padded to an even number of doubles (16 B).
+ *
+ * FORCEACC  (n_v = n_a + 6, n_x = n_v + 3c):
+ *   J_waist  6 x n_v row-major          level-0 Cartesian task Jacobian   (ForceAcc.cpp:118-122)
+ *   J_c      c x 6 x n_v                contact-link Jacobians            (ForceAcc.cpp:83-89, 208)
+ *   M        packed lower, row-major    n_v(n_v+1)/2                      (DynamicFeasibility, ID)
+ *   h        n_v                        nonlinear term
+ *   Jdqd     6(1+c)                     Jdot*qdot, waist first
+ *   rhs      6(1+c) + n_v               a_ref + l2*edot + l*e per Cartesian task, then postural
+ *   tau_min, tau_max   2 n_a            only with QPPVM_FLAG_TORQUE_LIMITS
+ *   cone     c x (R 3x3 row-major, mu)  only with QPPVM_FLAG_FRICTION_CONES
+ *   f_lb,f_ub  c x (lb3, ub3)           force box                          (ForceAcc.cpp:74-76)
+ *
+ * TORQUE  (n_v = n_x = n_a):
+ *   J_ee     2 x 6 x n  (right hand first: stack order ee_right + ee_left, QPPVMPlugin.cpp:177)
+ *   M        packed lower n(n+1)/2
+ *   h        n
+ *   F_ee     2 x 6      K e + D edot per hand (spring+damper wrench)
+ *   tau_j    n          K (q_ref - q) + D (-qdot)                          (QPPVMPlugin.cpp:105-118)
+ *   tau_min_const, tau_max_const  2 n  (before the -h shift of QPPVMPlugin.cpp:203-204)
+ */
+typedef struct qppvm_layout {
+    int32_t n_a, n_v, n_c, n_x;
+    int32_t n_rows;        /* constraint rows incl. level-1 optimality rows (mask width)   */
+    int32_t row_dyn;       /* first dyn-feas row (6 rows)          ; -1 if absent          */
+    int32_t row_box;       /* first force-box row (6 per contact) / simple bounds (TORQUE) */
+    int32_t row_cone;      /* first friction row (5 per contact)   ; -1 if absent          */
+    int32_t row_tau;       /* first torque-limit row (n_a rows)    ; -1 if absent          */
+    int32_t row_opt;       /* first level-1 optimality row (QPPVM_M0 rows)                 */
+    int32_t off_jwaist, off_jc, off_M, off_h, off_jdqd, off_rhs;
+    int32_t off_taulim, off_cone, off_fbox;          /* -1 if absent                        */
+    int32_t off_fee, off_tauj;                       /* TORQUE kind only, else -1          */
+    int32_t rec_doubles;   /* record stride in doubles (even)                               */
+    int32_t out_bytes;     /* output stride: 8 (n_x + n_a) + 32                             */
+    int32_t diag_doubles;  /* diagnostic stride: n_x (x0) + 2 n_rows (y0,y1) + QPPVM_M0     */
+} qppvm_layout;
+
+/* Output trailer that follows x[n_x], tau[n_a] in every output record (32 B). */
+typedef struct qppvm_trailer {
+    int32_t  status;       /* QPPVM_STATUS_*                                   */
+    int32_t  iters;        /* working-set changes: level 0 | (level 1 << 16)   */
+    uint32_t active[4];    /* bit r set <=> constraint row r active at level 1 */
+    float    kkt[2];       /* scaled KKT residual per level      */
+} qppvm_trailer;
+
+typedef struct qppvm_handle qppvm_handle;
+
+/* Pure host arithmetic; usable without a GPU.  Returns QPPVM_ERR_ARG on bad dims. */
+int qppvm_get_layout(const qppvm_desc* desc, qppvm_layout* out);
+
+/* Creates the solver for one problem shape.  Fails (no CPU fallback) when there is
+ * no CUDA device or no kernel instantiated for the shape. */
+int qppvm_create(const qppvm_desc* desc, qppvm_handle** out);
+int qppvm_destroy(qppvm_handle* h);
+/* Message of the last failure on this handle (NULL handle: last create failure). */
+const char* qppvm_last_error(const qppvm_handle* h);
+
+/* Batched solve, device pointers, asynchronous on `cuda_stream` (cudaStream_t or NULL).
+ * records: B * rec_doubles doubles.  out: B * out_bytes bytes. */
+int qppvm_solve_batch(qppvm_handle* h, const double* records_dev, void* out_dev,
+                      int64_t batch, void* cuda_stream);
+/* Same plus the diagnostic block (level-0 solution and the multipliers of both levels). */
+int qppvm_solve_batch_diag(qppvm_handle* h, const double* records_dev, void* out_dev,
+                           double* diag_dev, int64_t batch, void* cuda_stream);
+/* Batched solve with HOST buffers: chunked H2D / solve / D2H overlapped on internal
+ * streams; returns after the outputs are in `out_host`. */
+int qppvm_solve_batch_host(qppvm_handle* h, const double* records_host, void* out_host,
+                           int64_t batch);
+/* Latency mode: one record, host in / host out, synchronous (one control tick). */
+int qppvm_solve_one(qppvm_handle* h, const double* record_host, void* out_host);
+
+/* Number of kernel launches issued through this handle so far. */
+int64_t qppvm_kernel_launches(const qppvm_handle* h);
+/* Measures the FP64 FMA peak of the device (TFLOP/s) with a register-resident DFMA
+ * kernel; the compute-roofline denominator (not in MEASURED_PEAKS.json). */
+int qppvm_fp64_peak(qppvm_handle* h, double* tflops);
+/* Shapes compiled into this library: writes up to `cap` (n_a, c, flags) triples, returns count. */
+int qppvm_supported_shapes(int32_t* triples, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QPPVM_B200_H_ */

@@ -1,0 +1,320 @@
+"""Deterministic synthetic humanoid states -> QP records (SURVEY.md 8(d) "Synthetic inputs").
+
+The reference gets J, Jdot*qdot, M, h from XBot::ModelInterface after
+``_model->update()`` (ref:src/ForceAcc.cpp:256-282, ref:src/QPPVMPlugin.cpp:344-353) and
+builds the task right-hand sides inside OpenSoT.  That producer is not
+part of the hot path; this module stands in for it: a fixed kinematic tree (floating
+pelvis, legs 2x6, waist 3, arms 2x7 [+ neck 2 + hands 2]) evaluated in FP64 with batched
+numpy, written straight into the record layout of ``include/qppvm_b200.h``.
+
+Determinism / sharding: problem ``i`` draws its DRAWS uniforms from Philox(key=seed) advanced
+to ``i*DRAWS/4`` so any rank can regenerate exactly its slice ``[start, start+count)``.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.special import ndtri
+
+from .layout import (Desc, Layout, layout, KIND_FORCEACC, KIND_TORQUE, FLAG_FRICTION_CONES,
+                     FLAG_TORQUE_LIMITS)
+
+DRAWS = 256            # uniforms reserved per problem (multiple of 4: Philox yields 4 per step)
+BASE_SEED = 20260118   # seed = 20260118 + 1000 * config_index
+GRAVITY = 9.81
+
+_AX = {"x": (1.0, 0.0, 0.0), "y": (0.0, 1.0, 0.0), "z": (0.0, 0.0, 1.0)}
+
+
+class Robot:
+    """Fixed kinematic tree.  Body 0 = pelvis (floating base); body k>=1 moves with joint k-1."""
+
+    def __init__(self, n_a: int):
+        # (name, parent body, axis, offset from parent frame [m], mass [kg], com [m], tau_max [Nm])
+        J = []
+
+        def chain(prefix, parent, specs):
+            p = parent
+            for (nm, ax, off, m, com, tmax) in specs:
+                J.append((prefix + nm, p, ax, off, m, com, tmax))
+                p = len(J)          # body index of the link just added
+            return p
+
+        heavy = n_a >= 33           # WALK-MAN-like (~120 kg) vs COMAN-like (~30 kg)
+        s = 4.0 if heavy else 1.0   # mass scale
+        ln = 1.25 if heavy else 1.0  # length scale
+        legs = lambda sy: [
+            ("hip_pitch", "y", (0.0, sy * 0.07 * ln, -0.05 * ln), 1.2 * s, (0, 0, -0.02), 120 * s),
+            ("hip_roll", "x", (0.0, 0.0, 0.0), 0.8 * s, (0, 0, -0.03), 100 * s),
+            ("hip_yaw", "z", (0.0, 0.0, -0.05 * ln), 2.2 * s, (0, 0, -0.10 * ln), 60 * s),
+            ("knee", "y", (0.0, 0.0, -0.22 * ln), 1.6 * s, (0, 0, -0.10 * ln), 120 * s),
+            ("ank_pitch", "y", (0.0, 0.0, -0.22 * ln), 0.5 * s, (0, 0, -0.01), 80 * s),
+            ("ank_roll", "x", (0.0, 0.0, 0.0), 0.7 * s, (0.02, 0, -0.04 * ln), 60 * s),
+        ]
+        arms = lambda sy: [
+            ("sh_pitch", "y", (0.0, sy * 0.15 * ln, 0.20 * ln), 0.9 * s, (0, sy * 0.02, 0), 60 * s),
+            ("sh_roll", "x", (0.0, 0.0, 0.0), 0.6 * s, (0, 0, -0.03), 60 * s),
+            ("sh_yaw", "z", (0.0, 0.0, -0.04 * ln), 1.0 * s, (0, 0, -0.08 * ln), 40 * s),
+            ("elbow", "y", (0.0, 0.0, -0.18 * ln), 0.7 * s, (0, 0, -0.06 * ln), 40 * s),
+            ("fore_yaw", "z", (0.0, 0.0, -0.05 * ln), 0.5 * s, (0, 0, -0.05 * ln), 20 * s),
+            ("wr_pitch", "y", (0.0, 0.0, -0.12 * ln), 0.3 * s, (0, 0, -0.01), 15 * s),
+            ("wr_roll", "x", (0.0, 0.0, 0.0), 0.4 * s, (0, 0, -0.04 * ln), 15 * s),
+        ]
+        self.foot = [chain("l_", 0, legs(+1.0)), chain("r_", 0, legs(-1.0))]
+        torso = chain("waist_", 0, [
+            ("roll", "x", (0.0, 0.0, 0.08 * ln), 0.8 * s, (0, 0, 0.02), 80 * s),
+            ("pitch", "y", (0.0, 0.0, 0.0), 0.8 * s, (0, 0, 0.03), 120 * s),
+            ("yaw", "z", (0.0, 0.0, 0.05 * ln), 7.0 * s, (0, 0, 0.12 * ln), 80 * s),
+        ])
+        self.hand = [chain("l_", torso, arms(+1.0)), chain("r_", torso, arms(-1.0))]
+        if n_a == 33:
+            chain("neck_", torso, [
+                ("yaw", "z", (0.0, 0.0, 0.28 * ln), 0.3 * s, (0, 0, 0.02), 10 * s),
+                ("pitch", "y", (0.0, 0.0, 0.03), 1.0 * s, (0, 0, 0.06), 10 * s),
+            ])
+            for k, sy in enumerate((+1.0, -1.0)):
+                chain("lr"[k] + "_hand_", self.hand[k], [
+                    ("grasp", "y", (0.0, 0.0, -0.06 * ln), 0.3 * s, (0, 0, -0.03), 8 * s)])
+        elif n_a != 29:
+            # generic limb padding for other shapes: extra single-joint links on the torso
+            while len(J) < n_a:
+                chain("aux%d_" % len(J), torso, [
+                    ("j", "xyz"[len(J) % 3], (0.05, 0.0, 0.1), 0.4 * s, (0, 0, 0.03), 20 * s)])
+        if len(J) != n_a:
+            J = J[:n_a]
+            self.foot = [min(f, n_a) for f in self.foot]
+            self.hand = [min(h, n_a) for h in self.hand]
+        self.n_a = n_a
+        self.n_v = n_a + 6
+        self.n_b = n_a + 1
+        self.names = ["pelvis"] + [j[0] for j in J]
+        self.parent = np.array([-1] + [j[1] for j in J])
+        self.axis = np.array([(0.0, 0.0, 0.0)] + [_AX[j[2]] for j in J])
+        self.offset = np.array([(0.0, 0.0, 0.0)] + [j[3] for j in J], dtype=np.float64)
+        self.mass = np.array([(6.0 * s)] + [j[4] for j in J])
+        self.com = np.array([(0.0, 0.0, 0.03)] + [j[5] for j in J], dtype=np.float64)
+        # box-like inertia about the COM: I = m * r^2 * (1, 1, 0.5), r ~ 6 cm * length scale
+        r2 = (0.06 * ln) ** 2
+        self.inertia = np.stack([self.mass * r2, self.mass * r2, 0.5 * self.mass * r2], axis=1)
+        self.tau_max = np.array([j[6] for j in J], dtype=np.float64)
+        # "home": slightly bent knees / elbows
+        qh = np.zeros(n_a)
+        for i, j in enumerate(J):
+            nm = j[0]
+            if nm.endswith("hip_pitch"): qh[i] = -0.35
+            elif nm.endswith("knee"): qh[i] = 0.70
+            elif nm.endswith("ank_pitch"): qh[i] = -0.35
+            elif nm.endswith("sh_pitch"): qh[i] = 0.35
+            elif nm.endswith("sh_roll"): qh[i] = 0.15 if nm.startswith("l_") else -0.15
+            elif nm.endswith("elbow"): qh[i] = -0.9
+        self.q_home = qh
+        # ancestors mask: anc[i, k] = 1 if joint k (body k+1) is on the path pelvis -> body i
+        anc = np.zeros((self.n_b, n_a), dtype=bool)
+        for i in range(1, self.n_b):
+            b = i
+            while b > 0:
+                anc[i, b - 1] = True
+                b = self.parent[b]
+        self.anc = anc
+
+    # ---- batched kinematics / dynamics ------------------------------------------------
+    @staticmethod
+    def _rot(axis, ang):
+        """Rodrigues, axis (3,) unit, ang (B,) -> (B,3,3)."""
+        K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+        s, c = np.sin(ang)[:, None, None], np.cos(ang)[:, None, None]
+        return np.eye(3)[None] + s * K[None] + (1 - c) * (K @ K)[None]
+
+    def dynamics(self, q, qd, R0, p0, v0, w0, links):
+        """q, qd (B,n_a); base rotation R0 (B,3,3), position p0, linear/angular velocity v0, w0 (B,3)
+        (world frame).  Generalised velocity = [v0, w0, qd] (world-aligned 'mixed' convention).
+        Returns dict with M (B,nv,nv), h (B,nv) and per requested link: J (B,6,nv), Jdqd (B,6), R (B,3,3).
+        """
+        B, nb, nv, na = q.shape[0], self.n_b, self.n_v, self.n_a
+        R = np.empty((B, nb, 3, 3)); p = np.empty((B, nb, 3)); z = np.zeros((B, nb, 3))
+        w = np.empty((B, nb, 3)); al = np.zeros((B, nb, 3)); a = np.zeros((B, nb, 3))
+        R[:, 0], p[:, 0], w[:, 0] = R0, p0, w0
+        for i in range(1, nb):
+            pa = self.parent[i]
+            r = np.einsum("bij,j->bi", R[:, pa], self.offset[i])
+            p[:, i] = p[:, pa] + r
+            z[:, i] = np.einsum("bij,j->bi", R[:, pa], self.axis[i])
+            R[:, i] = R[:, pa] @ self._rot(self.axis[i], q[:, i - 1])
+            zq = z[:, i] * qd[:, i - 1:i]
+            w[:, i] = w[:, pa] + zq
+            al[:, i] = al[:, pa] + np.cross(w[:, pa], zq)
+            a[:, i] = a[:, pa] + np.cross(al[:, pa], r) + np.cross(w[:, pa], np.cross(w[:, pa], r))
+
+        def jac(body, point):
+            """Jacobian of world point `point` (B,3) rigidly attached to `body`: (B,6,nv)."""
+            Jm = np.zeros((B, 6, nv))
+            Jm[:, 0, 0] = Jm[:, 1, 1] = Jm[:, 2, 2] = 1.0
+            Jm[:, 3, 3] = Jm[:, 4, 4] = Jm[:, 5, 5] = 1.0
+            d = point - p[:, 0]
+            Jm[:, 0, 4], Jm[:, 0, 5] = d[:, 2], -d[:, 1]          # -[d]x
+            Jm[:, 1, 3], Jm[:, 1, 5] = -d[:, 2], d[:, 0]
+            Jm[:, 2, 3], Jm[:, 2, 4] = d[:, 1], -d[:, 0]
+            ks = np.nonzero(self.anc[body])[0]
+            zz = z[:, ks + 1]                                      # (B,k,3)
+            rr = point[:, None, :] - p[:, ks + 1]
+            Jm[:, 0:3, 6 + ks] = np.cross(zz, rr).transpose(0, 2, 1)
+            Jm[:, 3:6, 6 + ks] = zz.transpose(0, 2, 1)
+            return Jm
+
+        M = np.zeros((B, nv, nv)); h = np.zeros((B, nv))
+        gvec = np.array([0.0, 0.0, GRAVITY])
+        for i in range(nb):
+            c = np.einsum("bij,j->bi", R[:, i], self.com[i])
+            Jc = jac(i, p[:, i] + c)
+            Jv, Jw = Jc[:, 0:3], Jc[:, 3:6]
+            Iw = np.einsum("bij,j,bkj->bik", R[:, i], self.inertia[i], R[:, i])
+            M += self.mass[i] * np.einsum("bki,bkj->bij", Jv, Jv)
+            M += np.einsum("bki,bkl,blj->bij", Jw, Iw, Jw)
+            ac = a[:, i] + np.cross(al[:, i], c) + np.cross(w[:, i], np.cross(w[:, i], c))
+            # the base itself translates: its classical acceleration bias is zero (v0 is world-frame)
+            h += np.einsum("bki,bk->bi", Jv, self.mass[i] * (ac + gvec))
+            Iww = np.einsum("bij,bj->bi", Iw, w[:, i])
+            h += np.einsum("bki,bk->bi", Jw, np.einsum("bij,bj->bi", Iw, al[:, i]) + np.cross(w[:, i], Iww))
+        out = {"M": 0.5 * (M + M.transpose(0, 2, 1)), "h": h, "links": {}}
+        for b in links:
+            out["links"][b] = dict(J=jac(b, p[:, b]), Jdqd=np.concatenate([a[:, b], al[:, b]], axis=1),
+                                   R=R[:, b].copy(), p=p[:, b].copy())
+        return out
+
+
+_ROBOTS: dict[int, Robot] = {}
+
+
+def robot_for(n_a: int) -> Robot:
+    if n_a not in _ROBOTS:
+        _ROBOTS[n_a] = Robot(n_a)
+    return _ROBOTS[n_a]
+
+
+def _uniforms(seed: int, start: int, count: int) -> np.ndarray:
+    bg = np.random.Philox(key=seed)
+    bg.advance(start * (DRAWS // 4))
+    return np.random.Generator(bg).random((count, DRAWS))
+
+
+def _rpy(r, p, y):
+    cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+    R = np.empty(r.shape + (3, 3))
+    R[:, 0, 0], R[:, 0, 1], R[:, 0, 2] = cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr
+    R[:, 1, 0], R[:, 1, 1], R[:, 1, 2] = sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr
+    R[:, 2, 0], R[:, 2, 1], R[:, 2, 2] = -sp, cp * sr, cp * cr
+    return R
+
+
+def pack_lower(M: np.ndarray) -> np.ndarray:
+    n = M.shape[-1]
+    i, j = np.tril_indices(n)
+    return M[..., i, j]
+
+
+def unpack_lower(Mp: np.ndarray, n: int) -> np.ndarray:
+    M = np.zeros(Mp.shape[:-1] + (n, n))
+    i, j = np.tril_indices(n)
+    M[..., i, j] = Mp
+    M[..., j, i] = Mp
+    return M
+
+
+def generate(desc: Desc, count: int, seed: int = BASE_SEED, start: int = 0,
+             chunk: int = 2048) -> np.ndarray:
+    """Records for problems [start, start+count): float64 array (count, rec_doubles)."""
+    L = layout(desc)
+    out = np.zeros((count, L.rec_doubles))
+    for c0 in range(0, count, chunk):
+        n = min(chunk, count - c0)
+        out[c0:c0 + n] = _generate_chunk(desc, L, seed, start + c0, n)
+    return out
+
+
+def _generate_chunk(desc: Desc, L: Layout, seed: int, start: int, n: int) -> np.ndarray:
+    rob = robot_for(desc.n_a)
+    na, nv, c = L.n_a, desc.n_a + 6, L.n_c
+    U = _uniforms(seed, start, n)
+    k = 0
+
+    def take(m):
+        nonlocal k
+        v = U[:, k:k + m]
+        k += m
+        return v
+
+    def normal(m, sigma):
+        return sigma * ndtri(np.clip(take(m), 1e-12, 1 - 1e-12))
+
+    q = rob.q_home[None] + (take(na) * 0.6 - 0.3)             # q_home + U(-0.3, 0.3)
+    qd = normal(na, 0.5)                                      # N(0, 0.5^2) rad/s
+    rpy = take(3) * np.array([0.4, 0.4, 2 * np.pi]) - np.array([0.2, 0.2, np.pi])
+    R0 = _rpy(rpy[:, 0], rpy[:, 1], rpy[:, 2])
+    p0 = np.concatenate([take(2) * 2 - 1, 0.55 + 0.1 * take(1)], axis=1)
+    tw = normal(6, 0.2)
+    gains = 0.8 + 0.4 * take(4)                               # "perturbed gains" x U(0.8, 1.2)
+    ori_err = take(3) * 0.1 - 0.05
+    foot_err = normal(24, 1e-3)
+    mu = 0.4 + 0.5 * take(4)
+    tau_scale = 0.5 + 0.5 * take(na)
+    assert k <= DRAWS
+
+    rec = np.zeros((n, L.rec_doubles))
+    if desc.kind == KIND_FORCEACC:
+        contact_bodies = (rob.foot + rob.hand)[:c]
+        dyn = rob.dynamics(q, qd, R0, p0, tw[:, 0:3], tw[:, 3:6], [0] + contact_bodies)
+        v = np.concatenate([tw, qd], axis=1)
+        lam_w, lam2_w = 100.0 * gains[:, 0:1], 20.0 * gains[:, 1:2]
+        lam_p, lam2_p = 100.0 * gains[:, 2:3], 20.0 * gains[:, 3:4]
+        Jw = dyn["links"][0]["J"]
+        rec[:, L.off_jwaist:L.off_jwaist + 6 * nv] = Jw.reshape(n, -1)
+        rec[:, L.off_M:L.off_M + nv * (nv + 1) // 2] = pack_lower(dyn["M"])
+        rec[:, L.off_h:L.off_h + nv] = dyn["h"]
+        rec[:, L.off_jdqd:L.off_jdqd + 6] = dyn["links"][0]["Jdqd"]
+        # waist: position reference = current - 0.1 z (ref:src/ForceAcc.cpp:181), velocity ref 0
+        e_w = np.concatenate([np.tile([0.0, 0.0, -0.1], (n, 1)), ori_err], axis=1)
+        rec[:, L.off_rhs:L.off_rhs + 6] = lam_w * e_w - lam2_w * np.einsum("bij,bj->bi", Jw, v)
+        for ci, b in enumerate(contact_bodies):
+            Jc = dyn["links"][b]["J"]
+            o = L.off_jc + ci * 6 * nv
+            rec[:, o:o + 6 * nv] = Jc.reshape(n, -1)
+            rec[:, L.off_jdqd + 6 * (1 + ci):L.off_jdqd + 6 * (2 + ci)] = dyn["links"][b]["Jdqd"]
+            e_c = foot_err[:, 6 * ci:6 * ci + 6]
+            rec[:, L.off_rhs + 6 * (1 + ci):L.off_rhs + 6 * (2 + ci)] = (
+                lam_p * e_c - lam2_p * np.einsum("bij,bj->bi", Jc, v))
+            if desc.flags & FLAG_FRICTION_CONES:
+                o = L.off_cone + 10 * ci
+                rec[:, o:o + 9] = dyn["links"][b]["R"].reshape(n, 9)
+                rec[:, o + 9] = mu[:, ci]
+            o = L.off_fbox + 6 * ci
+            rec[:, o:o + 6] = np.array([-1000.0, -1000.0, 10.0, 1000.0, 1000.0, 1000.0])  # ForceAcc.cpp:75-76
+        # postural: qddot = l2 (0 - qdot) + l (q_home - q); base rows carry the damping term only
+        e_p = np.concatenate([np.zeros((n, 6)), rob.q_home[None] - q], axis=1)
+        o = L.off_rhs + 6 * (1 + c)
+        rec[:, o:o + nv] = lam_p * e_p - lam2_p * v
+        if desc.flags & FLAG_TORQUE_LIMITS:
+            tmax = rob.tau_max[None] * tau_scale
+            rec[:, L.off_taulim:L.off_taulim + na] = -tmax
+            rec[:, L.off_taulim + na:L.off_taulim + 2 * na] = tmax
+    elif desc.kind == KIND_TORQUE:
+        # fixed base: drop the 6 base columns/rows of the floating-base quantities
+        Z3 = np.zeros((n, 3))
+        dyn = rob.dynamics(q, qd, np.tile(np.eye(3), (n, 1, 1)), Z3, Z3, Z3, rob.hand[::-1])
+        Mj = dyn["M"][:, 6:, 6:]
+        rec[:, L.off_M:L.off_M + na * (na + 1) // 2] = pack_lower(Mj)
+        rec[:, L.off_h:L.off_h + na] = dyn["h"][:, 6:]
+        for ti, b in enumerate(rob.hand[::-1]):                # right first (QPPVMPlugin.cpp:177)
+            Jh = dyn["links"][b]["J"][:, :, 6:]
+            rec[:, L.off_jc + ti * 6 * na:L.off_jc + (ti + 1) * 6 * na] = Jh.reshape(n, -1)
+            e = np.concatenate([foot_err[:, 6 * ti:6 * ti + 3] * 30.0, ori_err * (1 - 2 * ti)], axis=1)
+            F = 700.0 * gains[:, 0:1] * e - 70.0 * gains[:, 1:2] * np.einsum("bij,bj->bi", Jh, qd)
+            rec[:, L.off_fee + 6 * ti:L.off_fee + 6 * ti + 6] = F     # K=700, D=70: QPPVMPlugin.cpp:136-137
+        rec[:, L.off_tauj:L.off_tauj + na] = (5.0 * gains[:, 2:3] * (rob.q_home[None] - q)
+                                              - 2.0 * gains[:, 3:4] * qd)  # K=5, D=2: QPPVMPlugin.cpp:105-106
+        tmax = rob.tau_max[None] * tau_scale
+        rec[:, L.off_taulim:L.off_taulim + na] = -tmax
+        rec[:, L.off_taulim + na:L.off_taulim + 2 * na] = tmax
+    return rec
+
+
+def config_seed(config_index: int) -> int:
+    return BASE_SEED + 1000 * config_index
