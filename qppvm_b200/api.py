@@ -1,0 +1,171 @@
+"""Host-side front end of the C-ABI (``include/qppvm_b200.h``) via ctypes.
+
+PyTorch is used only as plumbing (device memory, streams, torch.distributed); the solve is the
+hand-written sm_100a kernel in ``libqppvm_b200.so``.  There is no CPU path: constructing a
+:class:`Solver` without the built library or without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .layout import Desc, Layout, layout
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqppvm_b200.so")
+
+
+class CDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_a", C.c_int32), ("n_contacts", C.c_int32), ("flags", C.c_int32),
+                ("eps_regularisation", C.c_double), ("n_reg_steps", C.c_int32), ("max_iter", C.c_int32),
+                ("device", C.c_int32), ("reserved", C.c_int32)]
+
+
+class CLayout(C.Structure):
+    _fields_ = [(f, C.c_int32) for f in Layout.FIELDS]
+
+
+EXPORTS = ("qppvm_get_layout", "qppvm_create", "qppvm_destroy", "qppvm_last_error", "qppvm_solve_batch",
+           "qppvm_solve_batch_diag", "qppvm_solve_batch_host", "qppvm_solve_one", "qppvm_kernel_launches",
+           "qppvm_fp64_peak", "qppvm_supported_shapes")
+
+_lib = None
+
+
+def load_library():
+    """Loads the in-tree native library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("native library missing: %s (run `python -m qppvm_b200.build`); "
+                               "qppvm_b200 has no CPU fallback" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        P = C.c_void_p
+        lib.qppvm_get_layout.argtypes = [C.POINTER(CDesc), C.POINTER(CLayout)]
+        lib.qppvm_create.argtypes = [C.POINTER(CDesc), C.POINTER(P)]
+        lib.qppvm_destroy.argtypes = [P]
+        lib.qppvm_last_error.argtypes = [P]
+        lib.qppvm_last_error.restype = C.c_char_p
+        lib.qppvm_solve_batch.argtypes = [P, P, P, C.c_int64, P]
+        lib.qppvm_solve_batch_diag.argtypes = [P, P, P, P, C.c_int64, P]
+        lib.qppvm_solve_batch_host.argtypes = [P, P, P, C.c_int64]
+        lib.qppvm_solve_one.argtypes = [P, P, P]
+        lib.qppvm_kernel_launches.argtypes = [P]
+        lib.qppvm_kernel_launches.restype = C.c_int64
+        lib.qppvm_fp64_peak.argtypes = [P, C.POINTER(C.c_double)]
+        lib.qppvm_supported_shapes.argtypes = [C.POINTER(C.c_int32), C.c_int]
+        _lib = lib
+    return _lib
+
+
+def cdesc(desc: Desc) -> CDesc:
+    return CDesc(desc.kind, desc.n_a, desc.n_contacts, desc.flags, desc.eps_regularisation,
+                 desc.n_reg_steps, desc.max_iter, desc.device, 0)
+
+
+def c_layout(desc: Desc) -> dict:
+    L = CLayout()
+    if load_library().qppvm_get_layout(C.byref(cdesc(desc)), C.byref(L)):
+        raise ValueError("qppvm_get_layout rejected the description")
+    return {f: getattr(L, f) for f in Layout.FIELDS}
+
+
+def supported_shapes():
+    buf = (C.c_int32 * 64)()
+    n = load_library().qppvm_supported_shapes(buf, 16)
+    return [tuple(buf[4 * i:4 * i + 4]) for i in range(min(n, 16))]
+
+
+class QPError(RuntimeError):
+    pass
+
+
+class Solver:
+    """One ``qppvm_handle``: batched / single-tick whole-body QP solves for one problem shape."""
+
+    def __init__(self, desc: Desc):
+        self.desc = desc
+        self.layout = layout(desc)
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.qppvm_create(C.byref(cdesc(desc)), C.byref(self._h))
+        if rc:
+            raise QPError("qppvm_create failed (%d): %s" % (rc, self._lib.qppvm_last_error(None).decode()))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.qppvm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc:
+            raise QPError("qppvm call failed (%d): %s" % (rc, self._lib.qppvm_last_error(self._h).decode()))
+
+    # ---- device path (torch tensors are only the memory/stream plumbing) -------------------
+    def solve_batch(self, records, out=None, diag=None, stream=None):
+        """records: CUDA float64 tensor (B, rec_doubles).  Returns (out, diag): out is a CUDA float64
+        tensor (B, out_bytes/8) (trailer bit-packed in the last 4 doubles); asynchronous on `stream`."""
+        import torch
+        L = self.layout
+        assert records.is_cuda and records.dtype == torch.float64 and records.is_contiguous()
+        assert records.shape[1] == L.rec_doubles
+        B = records.shape[0]
+        if out is None:
+            out = torch.empty((B, L.out_doubles), dtype=torch.float64, device=records.device)
+        if diag is True:
+            diag = torch.empty((B, L.diag_doubles), dtype=torch.float64, device=records.device)
+        st = torch.cuda.current_stream(records.device) if stream is None else stream
+        self._check(self._lib.qppvm_solve_batch_diag(
+            self._h, records.data_ptr(), out.data_ptr(), diag.data_ptr() if diag is not None else None,
+            B, st.cuda_stream))
+        return out, diag
+
+    # ---- host path: the reference-facing call (host buffers in, host buffers out) ----------
+    def solve_batch_host(self, records: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        L = self.layout
+        assert records.dtype == np.float64 and records.flags.c_contiguous and records.shape[1] == L.rec_doubles
+        B = records.shape[0]
+        if out is None:
+            out = np.empty((B, L.out_doubles))
+        self._check(self._lib.qppvm_solve_batch_host(self._h, records.ctypes.data, out.ctypes.data, B))
+        return out
+
+    def solve_batch_host_ptr(self, rec_ptr: int, out_ptr: int, batch: int):
+        self._check(self._lib.qppvm_solve_batch_host(self._h, rec_ptr, out_ptr, batch))
+
+    def solve_one(self, record: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        L = self.layout
+        assert record.dtype == np.float64 and record.flags.c_contiguous and record.size == L.rec_doubles
+        if out is None:
+            out = np.empty(L.out_doubles)
+        self._check(self._lib.qppvm_solve_one(self._h, record.ctypes.data, out.ctypes.data))
+        return out
+
+    @property
+    def kernel_launches(self) -> int:
+        return self._lib.qppvm_kernel_launches(self._h)
+
+    def fp64_peak_tflops(self) -> float:
+        v = C.c_double(0)
+        self._check(self._lib.qppvm_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
+
+def split_out(L: Layout, out: np.ndarray) -> dict:
+    """out (B, out_doubles) float64 -> x, tau, status, iters0, iters1, active (B,4) u32, kkt (B,2) f32."""
+    n, na = L.n_x, L.n_a
+    out = np.ascontiguousarray(out)
+    tr = out[:, n + na:n + na + 4].copy().view(np.uint8).reshape(out.shape[0], 32)
+    i32 = tr[:, 0:8].copy().view(np.int32)
+    return dict(x=out[:, :n], tau=out[:, n:n + na], status=i32[:, 0], iters0=i32[:, 1] & 0xffff,
+                iters1=(i32[:, 1] >> 16) & 0xffff, active=tr[:, 8:24].copy().view(np.uint32),
+                kkt=tr[:, 24:32].copy().view(np.float32))
+
+
+def split_diag(L: Layout, diag: np.ndarray) -> dict:
+    n, nr = L.n_x, L.n_rows
+    return dict(x0=diag[:, :n], y0=diag[:, n:n + nr], y1=diag[:, n + nr:n + 2 * nr], eopt=diag[:, n + 2 * nr:])

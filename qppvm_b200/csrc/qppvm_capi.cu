@@ -1,0 +1,317 @@
+// qppvm_capi.cu — C-ABI (include/qppvm_b200.h) over the sm_100a kernels.  Plain CUDA runtime;
+// no torch, no CPU fallback: every solve entry point fails when there is no device.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+#include "qp_kernel.cuh"
+
+using namespace qppvm;
+
+namespace {
+
+char g_create_error[512] = "";
+
+struct ShapeEntry {
+    int kind, n_a, n_c, flags;
+    const void* kernel;
+    int slab_bytes;
+};
+
+// Instantiated problem shapes (BASELINE.json configs).
+template <class P>
+constexpr ShapeEntry entry()
+{
+    return ShapeEntry{P::KIND, P::NA, P::NC, P::FLAGS, (const void*)&qp_solve_kernel<P, 1>, Slab<P>::BYTES};
+}
+constexpr int F_ALL = QPPVM_FLAG_FRICTION_CONES | QPPVM_FLAG_TORQUE_LIMITS;
+const ShapeEntry g_shapes[] = {
+    entry<ForceAcc<29, 2, 0>>(),       // config [1]: literal ForceAcc structure, COMAN-like, 2 contacts
+    entry<ForceAcc<29, 2, F_ALL>>(),   // configs [0], [4]: + cones + torque limits
+    entry<ForceAcc<33, 4, F_ALL>>(),   // configs [2], [3]: WALK-MAN-like, 4 contacts
+    entry<ForceAcc<33, 4, 0>>(),
+};
+constexpr int N_SHAPES = sizeof(g_shapes) / sizeof(g_shapes[0]);
+
+constexpr int HOST_STREAMS = 3;
+
+}  // namespace
+
+struct qppvm_handle {
+    qppvm_desc desc;
+    qppvm_layout L;
+    const ShapeEntry* shape;
+    int sm_count, ctas_per_sm;
+    unsigned long long* counters;          // HOST_STREAMS + 2 device counters
+    cudaStream_t streams[HOST_STREAMS];
+    double* d_rec[HOST_STREAMS];
+    unsigned char* d_out[HOST_STREAMS];
+    int64_t chunk;                         // records per host-path chunk
+    double* d_one_rec; unsigned char* d_one_out;
+    double* h_one_rec; unsigned char* h_one_out;   // pinned staging for latency mode
+    cudaStream_t one_stream;
+    int64_t launches;
+    char err[512];
+};
+
+namespace {
+
+int fail(qppvm_handle* h, int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h ? h->err : g_create_error, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(h, call)                                                                        \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return fail(h, QPPVM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t batch,
+           cudaStream_t st, unsigned long long* counter)
+{
+    if (batch <= 0) return QPPVM_OK;
+    CU(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    long long want = batch;                                   // one warp (= one CTA) per problem in flight
+    long long cap = (long long)h->sm_count * h->ctas_per_sm;
+    int grid = (int)(want < cap ? want : cap);
+    Params prm{h->desc.eps_regularisation * QPPVM_QPOASES_EPS_REG, h->desc.n_reg_steps, h->desc.max_iter};
+    long long b = batch;
+    void* args[] = {(void*)&rec, (void*)&out, (void*)&diag, (void*)&b, (void*)&prm, (void*)&counter};
+    CU(h, cudaLaunchKernel(h->shape->kernel, dim3(grid), dim3(32), args, (size_t)h->shape->slab_bytes, st));
+    h->launches += 1;
+    return QPPVM_OK;
+}
+
+__global__ void fp64_peak_kernel(double* out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qppvm_get_layout(const qppvm_desc* d, qppvm_layout* L)
+{
+    if (!d || !L) return QPPVM_ERR_ARG;
+    memset(L, 0, sizeof(*L));
+    if (d->n_a < 1 || d->n_a > 58) return QPPVM_ERR_ARG;
+    int off = 0, row = 0;
+    if (d->kind == QPPVM_KIND_FORCEACC) {
+        const int c = d->n_contacts;
+        if (c < 1 || c > 4) return QPPVM_ERR_ARG;
+        const bool cones = d->flags & QPPVM_FLAG_FRICTION_CONES, tl = d->flags & QPPVM_FLAG_TORQUE_LIMITS;
+        const int nv = d->n_a + 6;
+        L->n_a = d->n_a; L->n_v = nv; L->n_c = c; L->n_x = nv + 3 * c;
+        if (L->n_x > 64) return QPPVM_ERR_ARG;
+        L->row_dyn = row; row += 6;
+        L->row_box = row; row += 6 * c;
+        L->row_cone = cones ? row : -1; if (cones) row += 5 * c;
+        L->row_tau = tl ? row : -1; if (tl) row += d->n_a;
+        L->row_opt = row; row += QPPVM_M0;
+        L->off_jwaist = off; off += 6 * nv;
+        L->off_jc = off; off += c * 6 * nv;
+        L->off_M = off; off += nv * (nv + 1) / 2;
+        L->off_h = off; off += nv;
+        L->off_jdqd = off; off += 6 * (1 + c);
+        L->off_rhs = off; off += 6 * (1 + c) + nv;
+        L->off_taulim = tl ? off : -1; if (tl) off += 2 * d->n_a;
+        L->off_cone = cones ? off : -1; if (cones) off += 10 * c;
+        L->off_fbox = off; off += 6 * c;
+        L->off_fee = L->off_tauj = -1;
+    } else if (d->kind == QPPVM_KIND_TORQUE) {
+        if (d->n_contacts != 2 || d->flags != 0) return QPPVM_ERR_ARG;
+        const int n = d->n_a;
+        L->n_a = L->n_v = L->n_x = n; L->n_c = 2;
+        L->row_dyn = L->row_cone = L->row_tau = -1;
+        L->row_box = 0; L->row_opt = n; row = n + QPPVM_M0;
+        L->off_jwaist = -1;
+        L->off_jc = off; off += 12 * n;
+        L->off_M = off; off += n * (n + 1) / 2;
+        L->off_h = off; off += n;
+        L->off_jdqd = L->off_rhs = -1;
+        L->off_fee = off; off += 12;
+        L->off_tauj = off; off += n;
+        L->off_taulim = off; off += 2 * n;
+        L->off_cone = L->off_fbox = -1;
+    } else return QPPVM_ERR_ARG;
+    if (row > 128) return QPPVM_ERR_ARG;
+    L->n_rows = row;
+    L->rec_doubles = off + (off & 1);
+    L->out_bytes = 8 * (L->n_x + L->n_a) + 32;
+    L->diag_doubles = L->n_x + 2 * row + QPPVM_M0;
+    return QPPVM_OK;
+}
+
+int qppvm_supported_shapes(int32_t* t, int cap)
+{
+    for (int i = 0; i < N_SHAPES && i < cap; ++i) {
+        t[4 * i] = g_shapes[i].kind; t[4 * i + 1] = g_shapes[i].n_a; t[4 * i + 2] = g_shapes[i].n_c; t[4 * i + 3] = g_shapes[i].flags;
+    }
+    return N_SHAPES;
+}
+
+int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
+{
+    if (!d || !out) return fail(nullptr, QPPVM_ERR_ARG, "null argument");
+    *out = nullptr;
+    qppvm_layout L;
+    if (qppvm_get_layout(d, &L)) return fail(nullptr, QPPVM_ERR_ARG, "invalid problem description");
+    if (d->max_iter < 1 || d->n_reg_steps < 0 || !(d->eps_regularisation >= 0.0))
+        return fail(nullptr, QPPVM_ERR_ARG, "invalid solver options");
+    const ShapeEntry* sh = nullptr;
+    for (int i = 0; i < N_SHAPES; ++i)
+        if (g_shapes[i].kind == d->kind && g_shapes[i].n_a == d->n_a && g_shapes[i].n_c == d->n_contacts && g_shapes[i].flags == d->flags)
+            sh = &g_shapes[i];
+    if (!sh) return fail(nullptr, QPPVM_ERR_UNSUPPORTED, "no sm_100a kernel instantiated for kind=%d n_a=%d contacts=%d flags=%d",
+                         d->kind, d->n_a, d->n_contacts, d->flags);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= d->device)
+        return fail(nullptr, QPPVM_ERR_NO_DEVICE, "no CUDA device %d (this library has no CPU path)", d->device);
+    qppvm_handle* h = new (std::nothrow) qppvm_handle();
+    if (!h) return fail(nullptr, QPPVM_ERR_ARG, "out of memory");
+    memset(h, 0, sizeof(*h));
+    h->desc = *d; h->L = L; h->shape = sh;
+#define CUC(call)                                                                                 \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            fail(nullptr, QPPVM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));        \
+            delete h;                                                                             \
+            return QPPVM_ERR_CUDA;                                                                \
+        }                                                                                         \
+    } while (0)
+    CUC(cudaSetDevice(d->device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, d->device));
+    h->sm_count = prop.multiProcessorCount;
+    CUC(cudaFuncSetAttribute(sh->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh->slab_bytes));
+    CUC(cudaFuncSetAttribute(sh->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int occ = 0;
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh->kernel, 32, (size_t)sh->slab_bytes));
+    if (occ < 1) { fail(nullptr, QPPVM_ERR_CUDA, "kernel does not fit on an SM (%d B smem)", sh->slab_bytes); delete h; return QPPVM_ERR_CUDA; }
+    h->ctas_per_sm = occ;
+    CUC(cudaMalloc(&h->counters, sizeof(unsigned long long) * (HOST_STREAMS + 2)));
+    h->chunk = 2048;
+    for (int i = 0; i < HOST_STREAMS; ++i) {
+        CUC(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+        CUC(cudaMalloc(&h->d_rec[i], sizeof(double) * L.rec_doubles * h->chunk));
+        CUC(cudaMalloc(&h->d_out[i], (size_t)L.out_bytes * h->chunk));
+    }
+    CUC(cudaStreamCreateWithFlags(&h->one_stream, cudaStreamNonBlocking));
+    CUC(cudaMalloc(&h->d_one_rec, sizeof(double) * L.rec_doubles));
+    CUC(cudaMalloc(&h->d_one_out, L.out_bytes));
+    CUC(cudaMallocHost(&h->h_one_rec, sizeof(double) * L.rec_doubles));
+    CUC(cudaMallocHost(&h->h_one_out, L.out_bytes));
+#undef CUC
+    *out = h;
+    return QPPVM_OK;
+}
+
+int qppvm_destroy(qppvm_handle* h)
+{
+    if (!h) return QPPVM_ERR_ARG;
+    cudaSetDevice(h->desc.device);
+    for (int i = 0; i < HOST_STREAMS; ++i) {
+        if (h->streams[i]) { cudaStreamSynchronize(h->streams[i]); cudaStreamDestroy(h->streams[i]); }
+        cudaFree(h->d_rec[i]); cudaFree(h->d_out[i]);
+    }
+    if (h->one_stream) cudaStreamDestroy(h->one_stream);
+    cudaFree(h->d_one_rec); cudaFree(h->d_one_out);
+    cudaFreeHost(h->h_one_rec); cudaFreeHost(h->h_one_out);
+    cudaFree(h->counters);
+    delete h;
+    return QPPVM_OK;
+}
+
+const char* qppvm_last_error(const qppvm_handle* h) { return h ? h->err : g_create_error; }
+
+int qppvm_solve_batch_diag(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t batch, void* stream)
+{
+    if (!h) return QPPVM_ERR_ARG;
+    if (batch < 0 || (batch > 0 && (!rec || !out))) return fail(h, QPPVM_ERR_ARG, "bad batch arguments");
+    CU(h, cudaSetDevice(h->desc.device));
+    return launch(h, rec, out, diag, batch, (cudaStream_t)stream, h->counters + HOST_STREAMS);
+}
+
+int qppvm_solve_batch(qppvm_handle* h, const double* rec, void* out, int64_t batch, void* stream)
+{
+    return qppvm_solve_batch_diag(h, rec, out, nullptr, batch, stream);
+}
+
+int qppvm_solve_batch_host(qppvm_handle* h, const double* rec, void* out, int64_t batch)
+{
+    if (!h) return QPPVM_ERR_ARG;
+    if (batch < 0 || (batch > 0 && (!rec || !out))) return fail(h, QPPVM_ERR_ARG, "bad batch arguments");
+    CU(h, cudaSetDevice(h->desc.device));
+    const size_t rb = sizeof(double) * h->L.rec_doubles, ob = (size_t)h->L.out_bytes;
+    int s = 0;
+    for (int64_t c0 = 0; c0 < batch; c0 += h->chunk, s = (s + 1) % HOST_STREAMS) {
+        const int64_t n = batch - c0 < h->chunk ? batch - c0 : h->chunk;
+        cudaStream_t st = h->streams[s];
+        CU(h, cudaMemcpyAsync(h->d_rec[s], (const char*)rec + c0 * rb, n * rb, cudaMemcpyHostToDevice, st));
+        int rc = launch(h, h->d_rec[s], h->d_out[s], nullptr, n, st, h->counters + s);
+        if (rc) return rc;
+        CU(h, cudaMemcpyAsync((char*)out + c0 * ob, h->d_out[s], n * ob, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < HOST_STREAMS; ++i) CU(h, cudaStreamSynchronize(h->streams[i]));
+    return QPPVM_OK;
+}
+
+int qppvm_solve_one(qppvm_handle* h, const double* rec, void* out)
+{
+    if (!h || !rec || !out) return h ? fail(h, QPPVM_ERR_ARG, "null argument") : QPPVM_ERR_ARG;
+    CU(h, cudaSetDevice(h->desc.device));
+    const size_t rb = sizeof(double) * h->L.rec_doubles, ob = (size_t)h->L.out_bytes;
+    memcpy(h->h_one_rec, rec, rb);
+    CU(h, cudaMemcpyAsync(h->d_one_rec, h->h_one_rec, rb, cudaMemcpyHostToDevice, h->one_stream));
+    int rc = launch(h, h->d_one_rec, h->d_one_out, nullptr, 1, h->one_stream, h->counters + HOST_STREAMS + 1);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(h->h_one_out, h->d_one_out, ob, cudaMemcpyDeviceToHost, h->one_stream));
+    CU(h, cudaStreamSynchronize(h->one_stream));
+    memcpy(out, h->h_one_out, ob);
+    return QPPVM_OK;
+}
+
+int64_t qppvm_kernel_launches(const qppvm_handle* h) { return h ? h->launches : 0; }
+
+int qppvm_fp64_peak(qppvm_handle* h, double* tflops)
+{
+    if (!h || !tflops) return QPPVM_ERR_ARG;
+    CU(h, cudaSetDevice(h->desc.device));
+    const int blocks = h->sm_count * 8, threads = 256, iters = 1 << 16;
+    double* buf = nullptr;
+    CU(h, cudaMalloc(&buf, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CU(h, cudaEventCreate(&e0)); CU(h, cudaEventCreate(&e1));
+    fp64_peak_kernel<<<blocks, threads>>>(buf, 1024);           // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CU(h, cudaEventRecord(e0));
+        fp64_peak_kernel<<<blocks, threads>>>(buf, iters);
+        CU(h, cudaEventRecord(e1));
+        CU(h, cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(h, cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    h->launches += 4;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+    return QPPVM_OK;
+}
+
+}  // extern "C"
