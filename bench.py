@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py — whole-body QP solves/sec on N B200s (one process per GPU), next to the CPU path.
+
+A step = one pass of the hot path (2-level cascade + output recovery, what one control_loop tick
+does: ref:src/ForceAcc.cpp:184-219) over one batch of BASELINE.json configs[1]:
+"ForceAcc batched QP, 4096 synthetic states, 2 foot contacts" per GPU (weak scaling: every rank owns
+its own, differently seeded, batches; the path shards with no data-path collective).
+
+    python bench.py --gpus 1 --steps 1000 --warmup 10
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the CPU restatement (oracle) on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "whole-body QP solves/sec (2-level cascade, KKT<=1e-6)"
+N_BUF = 4     # distinct input batches rotated so the inputs (4 x 45 MB at config 1) exceed the 126 MB L2
+# SURVEY.md 8(d) minimum-work FP64 model (FLOP per solve)
+F_ALG = {(29, 2): 182e3, (33, 4): 335e3}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=1, help="BASELINE.json config index (default 1 = the metric's config)")
+    ap.add_argument("--batch", type=int, default=0, help="override records per step per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                     "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80, "applications_clocks_setting": 0x2}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.02)
+        except Exception as e:  # NVML unavailable: report that rather than invent clocks
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def result(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference(desc, recs, target_s, mode):
+    """Times the oracle (restated active-set path, not the qpOASES binary) on a bounded sample."""
+    from oracle import oracle
+    threads = oracle.num_threads()
+    t0 = time.perf_counter(); oracle.solve_batch(desc, recs[:512], mode=mode); rate = 512 / (time.perf_counter() - t0)
+    n = int(min(max(rate * target_s, 512), 4 * len(recs)))
+    reps = (n + len(recs) - 1) // len(recs)
+    done, t0 = 0, time.perf_counter()
+    for r in range(reps):
+        m = min(len(recs), n - done)
+        oracle.solve_batch(desc, recs[:m], mode=mode)
+        done += m
+    dt = time.perf_counter() - t0
+    return done / dt, threads, done, dt
+
+
+def config_dict(args, cfg_name, desc, L, batch, world):
+    return {"workload": cfg_name, "records_per_step_per_gpu": batch, "n_a": desc.n_a,
+            "contacts": desc.n_contacts, "flags": desc.flags,
+            "l2": "inputs rotate over %d distinct batches per GPU (%.0f MB > 126 MB L2)" % (N_BUF, N_BUF * batch * L.rec_doubles * 8 / 1e6),
+            "parallelism": "batch sharded over %d GPU(s), no data-path collective" % world}
+
+
+def run_reference(args, desc, L, cfg_name, batch):
+    """--impl reference: the reference's own CPU path cannot be built here (OpenSoT/qpOASES/XBotCore absent),
+    so this arm times the oracle port with the reference's numerics (formed H + Cholesky) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from qppvm_b200 import gen
+    from oracle import oracle
+    recs = gen.generate(desc, batch, gen.config_seed(args.config))
+    threads = oracle.num_threads()
+    t0 = time.perf_counter(); oracle.solve_batch(desc, recs[:256], mode=oracle.FACTOR_CHOLESKY)
+    rate = 256 / (time.perf_counter() - t0)
+    budget = 120.0 / max(1, args.steps + args.warmup)            # whole run ~<= 2 min
+    sample = int(max(32, min(batch, rate * budget)))
+    for _ in range(args.warmup):
+        oracle.solve_batch(desc, recs[:sample], mode=oracle.FACTOR_CHOLESKY)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out, _ = oracle.solve_batch(desc, recs[:sample], mode=oracle.FACTOR_CHOLESKY)
+    dt = time.perf_counter() - t0
+    o = oracle.split_out(desc, out)
+    good = float(((o["status"] == 0) & (o["kkt"].max(axis=1) <= 1e-6)).mean())
+    val = args.steps * sample * good / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "solves/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, cfg_name, desc, L, batch, args.gpus),
+            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": threads, "kind": "port",
+                             "sample": "%d records/step of the %d-record batch, restated active-set path "
+                                       "(qpOASES semantics, formed H + Cholesky), not the qpOASES binary" % (sample, batch)},
+            "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    from qppvm_b200.layout import CONFIGS, layout
+    cfg = CONFIGS[args.config]
+    desc = cfg["desc"]
+    L = layout(desc)
+    batch = args.batch or min(cfg["batch"], 65536)
+    cfg_name = "configs[%d]: %s" % (args.config, cfg["name"])
+    if args.impl == "reference":
+        return run_reference(args, desc, L, cfg_name, batch)
+
+    import torch
+    import torch.distributed as dist
+    from qppvm_b200 import api, gen
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import dataclasses
+    desc = dataclasses.replace(desc, device=local)
+    solver = api.Solver(desc)
+    dev = torch.device("cuda", local)
+
+    # ---- synthetic inputs: N_BUF distinct batches per rank, resident in HBM and mirrored in pinned host memory
+    host_recs = gen.generate(desc, N_BUF * batch, gen.config_seed(args.config), start=rank * N_BUF * batch)
+    pinned = torch.from_numpy(host_recs).pin_memory()
+    d_recs = [pinned[i * batch:(i + 1) * batch].to(dev, non_blocking=False).contiguous() for i in range(N_BUF)]
+    d_out = [torch.empty((batch, L.out_doubles), dtype=torch.float64, device=dev) for _ in range(N_BUF)]
+    h_out = torch.empty((batch, L.out_doubles), dtype=torch.float64).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ("value") ------------------------------------------------------
+    for i in range(args.warmup):
+        solver.solve_batch(d_recs[i % N_BUF], out=d_out[i % N_BUF])
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    l0 = solver.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        solver.solve_batch(d_recs[i % N_BUF], out=d_out[i % N_BUF])
+    e1.record(stream)
+    barrier()
+    sampler.stop_flag = True; sampler.join()
+    launches = solver.kernel_launches - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    # every counted solve must have converged with KKT <= 1e-6 (in-kernel certificate)
+    good, total, kkt_max = 0, 0, 0.0
+    for i in range(min(N_BUF, args.steps)):
+        g = api.split_out(L, d_out[i].cpu().numpy())
+        ok = (g["status"] == 0) & (g["kkt"].max(axis=1) <= 1e-6)
+        good += int(ok.sum()); total += len(ok)
+        kkt_max = max(kkt_max, float(g["kkt"][g["status"] == 0].max()) if (g["status"] == 0).any() else 0.0)
+    frac = torch.tensor([good / max(1, total)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(frac, op=dist.ReduceOp.MIN)
+    t_s = ms.item() * 1e-3
+    value = world * args.steps * batch * frac.item() / t_s
+
+    # ---- end to end through the reference-facing C-ABI call with HOST buffers ("e2e") ----------------
+    e2e_steps = max(3, min(args.steps, 200))
+    rec_ptr = [pinned[i * batch:(i + 1) * batch].data_ptr() for i in range(N_BUF)]
+    for i in range(3):
+        solver.solve_batch_host_ptr(rec_ptr[i % N_BUF], h_out.data_ptr(), batch)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        solver.solve_batch_host_ptr(rec_ptr[i % N_BUF], h_out.data_ptr(), batch)   # H2D + solve + D2H, synchronous
+    torch.cuda.synchronize(dev)
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    ge = api.split_out(L, h_out.numpy())
+    e2e_ok = float(((ge["status"] == 0) & (ge["kkt"].max(axis=1) <= 1e-6)).mean())
+    e2e_val = world * e2e_steps * batch * e2e_ok / t_e2e.item()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant (only) kernel -----------------------------------------------------
+    peaks, peak_src = measured_peaks()
+    launch_s = t_s / max(1, args.steps)                    # one launch per step; events bracket the K launches
+    alg_bytes = L.algorithmic_bytes() * batch
+    fp64_peak = solver.fp64_peak_tflops()
+    f_alg = F_ALG.get((desc.n_a, desc.n_contacts))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_config%d.json" % args.config)
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": alg_bytes / launch_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": alg_bytes / launch_s / 1e9 / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                "kernel": "qp_solve_kernel<ForceAcc<%d,%d,%d>>" % (desc.n_a, desc.n_contacts, desc.flags),
+                "note": "path is FP64-pipe/latency bound (SURVEY 8(d)); see roofline_fp64 for the binding roof"}
+    roofline_fp64 = None
+    if f_alg:
+        ach = f_alg * batch / launch_s / 1e12
+        roofline_fp64 = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                         "peak_source": "measured in this run (register-resident DFMA kernel)",
+                         "flop_per_solve": f_alg}
+
+    line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_s / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, cfg_name, desc, L, batch, world),
+            "clocks": sampler.result(),
+            "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": batch * L.rec_doubles * 8,
+                    "d2h_bytes_per_step": batch * L.out_bytes, "steps": e2e_steps,
+                    "api": "qppvm_solve_batch_host (pinned host buffers in/out)"},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "roofline_fp64": roofline_fp64,
+            "converged_frac": frac.item(), "kkt_max": kkt_max}
+
+    if world == 1 and not args.no_latency:
+        # single-tick latency (the metric's second half): config [4] shape, host in / host out per tick
+        d4 = dataclasses.replace(CONFIGS[4]["desc"], device=local)
+        s4 = api.Solver(d4)
+        r4 = gen.generate(d4, 256, gen.config_seed(4))
+        o4 = np.empty(layout(d4).out_doubles)
+        for i in range(200):
+            s4.solve_one(r4[i % 256], o4)
+        lat = np.empty(3000)
+        for i in range(3000):
+            t0 = time.perf_counter(); s4.solve_one(r4[i % 256], o4); lat[i] = time.perf_counter() - t0
+        line["single_tick"] = {"p50_us": float(np.percentile(lat, 50) * 1e6), "p99_us": float(np.percentile(lat, 99) * 1e6),
+                               "max_us": float(lat.max() * 1e6), "ticks": 3000,
+                               "workload": "configs[4]: one QP per tick through qppvm_solve_one (host in/out)"}
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        v, threads, n_done, dt = cpu_reference(desc, host_recs, 12.0, oracle.FACTOR_CHOLESKY)
+        line["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": threads, "kind": "port",
+                                "sample": "%d records of the same workload in %.1f s; restated active-set path "
+                                          "(qpOASES semantics), not the qpOASES binary" % (n_done, dt)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

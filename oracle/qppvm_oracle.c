@@ -608,6 +608,7 @@ static int solve_level(const level_qp* q, int mode, int n_reg_steps, int max_ite
         status = gi_solve(n, s->J, s->xu, q->nc, q->C, q->lA, q->uA, max_iter, y, &it, s->giwk, s->iwk);
         total += it;
         memcpy(x, s->xu, sizeof(double) * n);
+        for (int j = 0; j < n && status == QPPVM_STATUS_OK; ++j) if (!isfinite(x[j])) status = QPPVM_STATUS_NUMERIC;
         if (status != QPPVM_STATUS_OK) break;
     }
     *iters = total;

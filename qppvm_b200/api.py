@@ -95,11 +95,15 @@ class Solver:
             raise QPError("qppvm_create failed (%d): %s" % (rc, self._lib.qppvm_last_error(None).decode()))
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h:
-            self._lib.qppvm_destroy(self._h)
-            self._h = C.c_void_p()
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.qppvm_destroy(h)
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _check(self, rc):
         if rc:

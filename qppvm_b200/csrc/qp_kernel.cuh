@@ -596,6 +596,11 @@ struct Solver {
             for (int i = lane; i < N; i += 32) u[i] += w2[i];
             __syncwarp();
         }
+        if (status == QPPVM_STATUS_OK) {                       // non-finite data must not reach the command
+            bool bad = false;
+            for (int i = lane; i < N; i += 32) bad |= !isfinite(x[i]);
+            if (__any_sync(0xffffffffu, bad)) status = QPPVM_STATUS_NUMERIC;
+        }
         if (status != QPPVM_STATUS_OK) { kkt_out = __int_as_float(0x7f800000); return status; }
         kkt_out = (float)kkt(level, md, eps, ydiag);
         return status;

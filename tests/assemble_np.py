@@ -1,0 +1,70 @@
+"""Independent numpy restatement of the OpenSoT stack assembly used to pin the
+oracle's C assembly; written from the reference call sites, shares no code with oracle/ or csrc/."""
+from __future__ import annotations
+
+import numpy as np
+
+from qppvm_b200.gen import unpack_lower
+from qppvm_b200.layout import Desc, KIND_FORCEACC, layout, QPOASES_EPS_REG, INFTY
+
+
+def level_matrices(desc: Desc, rec: np.ndarray, level: int, x0=None):
+    """(A, b, C, lA, uA, eps) of priority level `level` for one record."""
+    L = layout(desc)
+    n, nv, c, na = L.n_x, L.n_v, L.n_c, L.n_a
+    if desc.kind == KIND_FORCEACC:
+        Jw = rec[L.off_jwaist:L.off_jwaist + 6 * nv].reshape(6, nv)
+        Jc = rec[L.off_jc:L.off_jc + c * 6 * nv].reshape(c, 6, nv)
+        M = unpack_lower(rec[L.off_M:L.off_M + nv * (nv + 1) // 2], nv)
+        h = rec[L.off_h:L.off_h + nv]
+        jdqd = rec[L.off_jdqd:L.off_jdqd + 6 * (1 + c)]
+        rhs = rec[L.off_rhs:L.off_rhs + 6 * (1 + c) + nv]
+        Z = np.zeros
+        if level == 0:   # _waist_task (ForceAcc.cpp:118-122)
+            A = np.hstack([Jw, Z((6, 3 * c))]); b = rhs[:6] - jdqd[:6]
+        else:            # _postural_task + feet_cart_aggr (ForceAcc.cpp:131)
+            A = np.vstack([np.hstack([np.eye(nv), Z((nv, 3 * c))])] +
+                          [np.hstack([Jc[i], Z((6, 3 * c))]) for i in range(c)])
+            b = np.concatenate([rhs[6 * (1 + c):]] + [rhs[6 * (1 + i):6 * (2 + i)] - jdqd[6 * (1 + i):6 * (2 + i)] for i in range(c)])
+        rows, lo, hi = [], [], []
+        # DynamicFeasibility: (M qdd + h - sum J_i^T [f_i; 0])[0:6] = 0
+        D = np.hstack([M[:6]] + [-Jc[i][:3, :6].T for i in range(c)])
+        rows.append(D); lo.append(-h[:6]); hi.append(-h[:6])
+        for i in range(c):   # wrench_i = force_i / Zero(3)  in [lb, ub]  (ForceAcc.cpp:74-76, 81, 91-95)
+            W = Z((6, n)); W[:3, nv + 3 * i:nv + 3 * i + 3] = np.eye(3)
+            fb = rec[L.off_fbox + 6 * i:L.off_fbox + 6 * i + 6]
+            rows.append(W); lo.append(np.concatenate([fb[:3], -np.ones(3)])); hi.append(np.concatenate([fb[3:], np.ones(3)]))
+        if L.row_cone >= 0:
+            for i in range(c):
+                blk = rec[L.off_cone + 10 * i:L.off_cone + 10 * i + 10]
+                R, mu = blk[:9].reshape(3, 3), blk[9] / np.sqrt(2.0)
+                Ci = np.array([[1, 0, -mu], [-1, 0, -mu], [0, 1, -mu], [0, -1, -mu], [0, 0, -1.0]])
+                F = Z((5, n)); F[:, nv + 3 * i:nv + 3 * i + 3] = Ci @ R.T
+                rows.append(F); lo.append(np.full(5, -INFTY)); hi.append(np.zeros(5))
+        if L.row_tau >= 0:
+            T = np.hstack([M[6:]] + [-Jc[i][:3, 6:].T for i in range(c)])
+            tl = rec[L.off_taulim:L.off_taulim + 2 * na]
+            rows.append(T); lo.append(tl[:na] - h[6:]); hi.append(tl[na:] - h[6:])
+        if level == 1:
+            A0 = np.hstack([Jw, Z((6, 3 * c))])
+            rows.append(A0); lo.append(A0 @ x0); hi.append(A0 @ x0)
+        eps = desc.eps_regularisation * QPOASES_EPS_REG
+    else:
+        nn = n
+        J = rec[L.off_jc:L.off_jc + 12 * nn].reshape(2, 6, nn)
+        M = unpack_lower(rec[L.off_M:L.off_M + nn * (nn + 1) // 2], nn)
+        h = rec[L.off_h:L.off_h + nn]
+        F = rec[L.off_fee:L.off_fee + 12].reshape(2, 6)
+        Minv = np.linalg.inv(M)
+        A0 = np.vstack([(J[t] @ Minv)[:3] for t in range(2)])          # CartesianImpedanceCtrl rows 0..2
+        if level == 0:
+            A = A0; b = np.concatenate([(J[t] @ Minv)[:3] @ (J[t].T @ F[t]) for t in range(2)])
+            eps = desc.eps_regularisation * QPOASES_EPS_REG
+        else:
+            A = Minv; b = Minv @ rec[L.off_tauj:L.off_tauj + nn]        # JointImpedanceCtrl
+            eps = 0.0
+        tl = rec[L.off_taulim:L.off_taulim + 2 * nn]
+        rows, lo, hi = [np.eye(nn)], [tl[:nn] - h], [tl[nn:] - h]      # TorqueLimits (QPPVMPlugin.cpp:203-205)
+        if level == 1:
+            rows.append(A0); lo.append(A0 @ x0); hi.append(A0 @ x0)
+    return A, b, np.vstack(rows), np.concatenate(lo), np.concatenate(hi), eps

@@ -1,0 +1,156 @@
+"""T3: the CUDA path (through the C-ABI) against the oracle on the same seeded records, for every
+BASELINE.json config shape; plus the edge cases of the batch interface and size-independent
+properties at the full BASELINE sizes.  Tolerances are north_star's: primal <= 1e-6 relative,
+KKT <= 1e-6 at both levels, identical active set at convergence."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from qppvm_b200 import gen
+from qppvm_b200.layout import CONFIGS, layout
+from tests.helpers import PRIMAL_TOL, KKT_TOL, compare, rel_inf
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _solve_gpu(torch, desc, recs, diag=True):
+    from qppvm_b200 import api
+    L = layout(desc)
+    s = api.Solver(desc)
+    out, dg = s.solve_batch(torch.from_numpy(recs).cuda(), diag=diag)
+    torch.cuda.synchronize()
+    assert s.kernel_launches >= 1
+    return api.split_out(L, out.cpu().numpy()), (api.split_diag(L, dg.cpu().numpy()) if diag else None)
+
+
+@pytest.mark.parametrize("ci,batch", [(1, 1024), (0, 768), (2, 512)])
+def test_parity_vs_oracle(torch_mod, oracle_mod, ci, batch):
+    from qppvm_b200 import api
+    desc = CONFIGS[ci]["desc"]
+    L = layout(desc)
+    recs = gen.generate(desc, batch, gen.config_seed(ci))
+    oo, od = oracle_mod.solve_batch(desc, recs, diag=True)
+    o, odg = oracle_mod.split_out(desc, oo), api.split_diag(L, od)
+    g, gdg = _solve_gpu(torch_mod, desc, recs)
+    r = compare(L, g, o, gdg, odg)
+    assert r["status_equal"] and r["both_ok"] == batch
+    assert r["primal"] <= PRIMAL_TOL and r["tau"] <= PRIMAL_TOL
+    assert r["kkt_gpu"] <= KKT_TOL and r["kkt_oracle"] <= KKT_TOL
+    assert r["mask_equal"] == 1.0 and r["strong_active_equal"] == 1.0 and r["strong_sign_equal"] == 1.0
+    assert r["eopt"] <= PRIMAL_TOL
+    assert rel_inf(gdg["x0"], odg["x0"]).max() <= 1e-4      # level-0 point: eps-defined directions
+
+
+def test_empty_single_and_ragged_batches(torch_mod, oracle_mod):
+    from qppvm_b200 import api
+    torch = torch_mod
+    desc = CONFIGS[1]["desc"]
+    L = layout(desc)
+    s = api.Solver(desc)
+    recs = gen.generate(desc, 301, 99)
+    ref = oracle_mod.split_out(desc, oracle_mod.solve_batch(desc, recs)[0])
+    empty = torch.empty((0, L.rec_doubles), dtype=torch.float64, device="cuda")
+    out, _ = s.solve_batch(empty)
+    assert out.shape == (0, L.out_doubles)
+    for b in (1, 31, 33, 149, 301):                        # below / above a warp, an SM count, ragged
+        out, _ = s.solve_batch(torch.from_numpy(recs[:b]).cuda())
+        torch.cuda.synchronize()
+        g = api.split_out(L, out.cpu().numpy())
+        assert (g["status"] == 0).all() and rel_inf(g["x"], ref["x"][:b]).max() <= PRIMAL_TOL
+
+
+def test_host_and_single_tick_entry_points_match_device_path(torch_mod):
+    from qppvm_b200 import api
+    torch = torch_mod
+    desc = CONFIGS[0]["desc"]
+    L = layout(desc)
+    s = api.Solver(desc)
+    recs = gen.generate(desc, 5000, 7)                     # > 2 host chunks, ragged tail
+    dev, _ = s.solve_batch(torch.from_numpy(recs).cuda())
+    torch.cuda.synchronize()
+    dev = dev.cpu().numpy()
+    host = s.solve_batch_host(recs)
+    assert np.array_equal(host, dev)                       # bitwise: problems are independent
+    for i in (0, 17, 4999):
+        assert np.array_equal(s.solve_one(recs[i]), dev[i])
+
+
+def test_shard_invariance(torch_mod):
+    """T5: any partition of the batch gives bitwise-identical per-problem results."""
+    from qppvm_b200 import api
+    torch = torch_mod
+    desc = CONFIGS[2]["desc"]
+    s = api.Solver(desc)
+    recs = torch.from_numpy(gen.generate(desc, 1000, 3)).cuda()
+    whole, _ = s.solve_batch(recs)
+    parts = [s.solve_batch(recs[a:b].contiguous())[0] for a, b in ((0, 137), (137, 512), (512, 1000))]
+    torch.cuda.synchronize()
+    assert torch.equal(whole, torch.cat(parts))
+
+
+def test_infeasible_and_iteration_limit_status(torch_mod, oracle_mod):
+    from qppvm_b200 import api
+    torch = torch_mod
+    desc = CONFIGS[1]["desc"]
+    L = layout(desc)
+    recs = gen.generate(desc, 64, 11)
+    bad = recs.copy()
+    bad[::2, L.off_fbox + 2] = 50.0; bad[::2, L.off_fbox + 5] = 20.0      # f_z in [50, 20]: empty box
+    g, _ = _solve_gpu(torch, desc, bad, diag=False)
+    o = oracle_mod.split_out(desc, oracle_mod.solve_batch(desc, bad)[0])
+    assert (g["status"][::2] == 2).all() and (g["status"][1::2] == 0).all()
+    assert np.array_equal(g["status"], o["status"])
+    assert (g["x"][::2] == 0).all() and (g["tau"][::2] == 0).all()       # nothing commanded (ForceAcc.cpp:189-193)
+    lim = dataclasses.replace(desc, max_iter=7)
+    g2, _ = _solve_gpu(torch, lim, recs, diag=False)
+    o2 = oracle_mod.split_out(lim, oracle_mod.solve_batch(lim, recs)[0])
+    assert (g2["status"] == 1).any() and np.array_equal(g2["status"] == 0, o2["status"] == 0)
+
+
+def test_non_finite_record_is_flagged_not_propagated(torch_mod):
+    from qppvm_b200 import api
+    desc = CONFIGS[1]["desc"]
+    L = layout(desc)
+    recs = gen.generate(desc, 8, 5)
+    recs[3, L.off_M + 10] = np.nan
+    g, _ = _solve_gpu(torch_mod, desc, recs, diag=False)
+    assert g["status"][3] != 0 and (np.delete(g["status"], 3) == 0).all()
+    assert np.isfinite(g["x"]).all() and np.isfinite(g["tau"]).all()
+
+
+@pytest.mark.parametrize("ci", (1, 2))
+def test_full_size_properties(torch_mod, oracle_mod, ci):
+    """At BASELINE.json's full batch: every solve converges with KKT <= 1e-6 (in-kernel certificate),
+    dyn-feas holds, forces respect their box, level 1 keeps the level-0 task value; a random sample is
+    compared with the oracle."""
+    from qppvm_b200 import api
+    desc, batch = CONFIGS[ci]["desc"], CONFIGS[ci]["batch"]
+    L = layout(desc)
+    recs = gen.generate(desc, batch, gen.config_seed(ci))
+    g, gd = _solve_gpu(torch_mod, desc, recs)
+    assert (g["status"] == 0).all()
+    assert g["kkt"].max() <= KKT_TOL
+    nv, c = L.n_v, L.n_c
+    f = g["x"][:, nv:].reshape(batch, c, 3)
+    fb = recs[:, L.off_fbox:L.off_fbox + 6 * c].reshape(batch, c, 6)
+    assert (f >= fb[:, :, :3] - 1e-6).all() and (f <= fb[:, :, 3:] + 1e-6).all()
+    M = gen.unpack_lower(recs[:, L.off_M:L.off_M + nv * (nv + 1) // 2], nv)
+    Jc = recs[:, L.off_jc:L.off_jc + c * 6 * nv].reshape(batch, c, 6, nv)
+    wrench = np.einsum("bckj,bck->bj", Jc[:, :, :3, :], f)
+    res = np.einsum("bij,bj->bi", M, g["x"][:, :nv]) + recs[:, L.off_h:L.off_h + nv] - wrench
+    assert np.abs(res[:, :6]).max() <= 1e-6 * max(1.0, np.abs(recs[:, L.off_h:L.off_h + nv]).max())
+    np.testing.assert_allclose(g["tau"], res[:, 6:], rtol=0, atol=1e-7 * max(1.0, np.abs(res).max()))
+    Jw = recs[:, L.off_jwaist:L.off_jwaist + 6 * nv].reshape(batch, 6, nv)
+    assert rel_inf(np.einsum("bij,bj->bi", Jw, g["x"][:, :nv]), gd["eopt"]).max() <= 1e-8
+    idx = np.random.default_rng(0).choice(batch, 256, replace=False)
+    o = oracle_mod.split_out(desc, oracle_mod.solve_batch(desc, recs[idx])[0])
+    assert rel_inf(g["x"][idx], o["x"]).max() <= PRIMAL_TOL
+    assert np.array_equal(g["active"][idx], o["active"])

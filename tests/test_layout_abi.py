@@ -1,0 +1,93 @@
+"""Host logic without a GPU: layouts agree across Python / C-ABI / oracle, the shared library loads
+and exports every symbol include/qppvm_b200.h declares, algorithmic bytes match SURVEY.md 8(d)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from qppvm_b200 import api, build
+from qppvm_b200.layout import (CONFIGS, Desc, KIND_TORQUE, layout, FLAG_FRICTION_CONES, FLAG_TORQUE_LIMITS)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return api.load_library()
+
+
+DESCS = [c["desc"] for c in CONFIGS.values()] + [
+    Desc(n_a=33, n_contacts=4, flags=0), Desc(n_a=39, n_contacts=4, flags=0),
+    Desc(n_a=12, n_contacts=1, flags=FLAG_FRICTION_CONES), Desc(n_a=20, n_contacts=3, flags=FLAG_TORQUE_LIMITS),
+    Desc(kind=KIND_TORQUE, n_a=39, n_contacts=2, flags=0, eps_regularisation=1.0),
+]
+
+
+@pytest.mark.parametrize("desc", DESCS)
+def test_layouts_agree(lib, oracle_mod, desc):
+    L = layout(desc)
+    py = {f: getattr(L, f) for f in L.FIELDS}
+    assert py == api.c_layout(desc)
+    assert py == oracle_mod.c_layout(desc)
+    assert L.rec_doubles % 2 == 0 and L.out_bytes % 8 == 0 and L.n_rows <= 128
+
+
+def test_algorithmic_bytes_match_survey():
+    # cfg[1] 11 616 B; cfg[0],[4] 12 240 B; cfg[2],[3] 18 448 B
+    assert layout(CONFIGS[1]["desc"]).algorithmic_bytes() == 11616
+    assert layout(CONFIGS[0]["desc"]).algorithmic_bytes() == 12240
+    assert layout(CONFIGS[4]["desc"]).algorithmic_bytes() == 12240
+    assert layout(CONFIGS[2]["desc"]).algorithmic_bytes() == 18448
+    assert layout(CONFIGS[3]["desc"]).algorithmic_bytes() == 18448
+
+
+def test_survey_dimensions():
+    # SURVEY.md 8(a) per-config table: n_x, n_C(L0)/n_C(L1)
+    for ci, nx, nc1 in ((1, 41, 24), (0, 41, 63), (2, 51, 89)):
+        L = layout(CONFIGS[ci]["desc"])
+        assert (L.n_x, L.n_rows) == (nx, nc1) and L.row_opt == nc1 - 6
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "qppvm_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(qppvm_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(api.EXPORTS), declared ^ set(api.EXPORTS)
+    raw = ctypes.CDLL(api.LIB_PATH)
+    for name in declared:
+        assert getattr(raw, name) is not None
+
+
+def test_bad_descriptions_rejected(lib):
+    for bad in (Desc(n_a=0), Desc(n_a=59), Desc(n_contacts=0), Desc(n_contacts=5), Desc(n_a=58, n_contacts=4)):
+        with pytest.raises(ValueError):
+            layout(bad)
+        with pytest.raises(ValueError):
+            api.c_layout(bad)
+
+
+def test_shapes_cover_baseline_configs(lib):
+    shapes = set(api.supported_shapes())
+    for c in CONFIGS.values():
+        d = c["desc"]
+        assert (d.kind, d.n_a, d.n_contacts, d.flags) in shapes
+
+
+def test_no_cpu_fallback_in_product(lib):
+    """Without a CUDA device the product must fail loudly (there is no CPU path)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(api.QPError):
+        api.Solver(CONFIGS[1]["desc"])
+
+
+def test_product_does_not_reference_oracle():
+    pkg = os.path.join(ROOT, "qppvm_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                src = open(os.path.join(dp, fn)).read()
+                assert "oracle" not in src.lower() or fn == "__init__.py" and False, os.path.join(dp, fn)
