@@ -92,7 +92,7 @@ def cpu_reference(desc, recs, target_s, mode):
     from oracle import oracle
     threads = oracle.num_threads()
     t0 = time.perf_counter(); oracle.solve_batch(desc, recs[:512], mode=mode); rate = 512 / (time.perf_counter() - t0)
-    n = int(min(max(rate * target_s, 512), 4 * len(recs)))
+    n = int(max(rate * target_s, 512))
     reps = (n + len(recs) - 1) // len(recs)
     done, t0 = 0, time.perf_counter()
     for r in range(reps):

@@ -120,6 +120,8 @@ class Solver:
         B = records.shape[0]
         if out is None:
             out = torch.empty((B, L.out_doubles), dtype=torch.float64, device=records.device)
+        if diag is False:
+            diag = None
         if diag is True:
             diag = torch.empty((B, L.diag_doubles), dtype=torch.float64, device=records.device)
         st = torch.cuda.current_stream(records.device) if stream is None else stream

@@ -1,4 +1,4 @@
-// qp_kernel.cuh — batched hierarchical whole-body QP, one warp per problem, sm_100a.
+// qp_kernel.cuh — batched hierarchical whole-body QP, one thread team per problem, sm_100a.
 //
 // Replaces, per record, what one tick of the reference does between "model updated" and
 // "torques written":
@@ -6,17 +6,20 @@
 //   ref:src/ForceAcc.cpp:184-219, ref:src/QPPVMPlugin.cpp:203-256  (SURVEY.md 8(a) a3-a16).
 //
 // B200 design (not the reference's: qpOASES is a sequential null-space homotopy method):
-//   * one warp owns one QP; all state of the solve lives in that warp's shared-memory slab
-//     (no H, C or KKT matrix ever touches HBM); the record is streamed once from HBM with
-//     coalesced row reads; outputs are written once.
+//   * one team (TEAM = 32 or 64 threads = one CTA) owns one QP; the whole solve lives in the
+//     CTA's shared-memory slab: no H, C or KKT matrix ever touches HBM.  The record is pulled
+//     from HBM once by a single TMA bulk copy (cp.async.bulk + mbarrier) and every later read
+//     of J / M / bounds hits shared memory; outputs are written once, coalesced.
 //   * whitening instead of normal equations: R from a Householder QR of the stacked task
-//     matrix [sqrt(D+eps) ; A_dense] (never forms A^T A, so the eps-regularised directions
-//     keep full relative accuracy), J = R^-1 explicit upper-triangular => every later
-//     "solve" is a lane-parallel triangular mat-vec with no dependent chain across lanes.
+//     matrix [sqrt(D+eps) ; A_dense] (never forms A^T A, so the eps-regularised directions keep
+//     full relative accuracy); only the leading NB x NB block that has dense task columns is
+//     factorised, the cost-free force columns stay diagonal.  J = R^-1 is made explicit so
+//     every later "solve" is a thread-parallel triangular mat-vec, no dependent chain across
+//     threads.
 //   * dual active set (Goldfarb-Idnani) in whitened coordinates u = R x, where the QP is a
 //     least-distance problem; the active normals are kept as an orthonormal basis Q1 (CGS2)
-//     plus a small triangular RN, so adding a constraint is two tall-skinny products, never
-//     an n x n rotation sweep.  Equalities (dyn-feas, level-0 optimality rows) enter first.
+//     plus a small triangular RN, so adding a constraint is two tall-skinny products, never an
+//     n x n rotation sweep.  Equalities (dyn-feas, level-0 optimality rows) enter first.
 //   * both priority levels, the qpOASES proximal regularisation re-solve, the KKT certificate
 //     and tau = M qdd + h - J^T f run in the same kernel.
 #pragma once
@@ -36,6 +39,9 @@ struct Params {
     int max_iter;
 };
 
+// ------------------------------------------------------------------------------------------
+// Team primitives (TEAM threads = the whole CTA)
+// ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -48,19 +54,109 @@ __device__ __forceinline__ double warp_max(double v)
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-// argmin over lanes of (v, idx); ties -> smaller idx.  Result uniform across the warp.
+// argmin of (v, idx); ties -> smaller idx.  Result uniform across the warp.
 __device__ __forceinline__ void warp_argmin(double& v, int& idx)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        double ov = __shfl_xor_sync(0xffffffffu, v, o);
-        int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
         if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
     }
 }
 
+extern __shared__ __align__(16) unsigned char g_smem[];   // the CTA's slab; all addresses are compile-time offsets
+
+template <int TEAM>
+struct Team {
+    static constexpr int WARPS = TEAM / 32;
+    __device__ static __forceinline__ void sync()
+    {
+        if (TEAM == 32) __syncwarp(); else __syncthreads();
+    }
+    // cross-warp exchange (TEAM > 32 only): red = 2 x WARPS doubles
+    __device__ static __forceinline__ double sum(double v, double* red)
+    {
+        v = warp_sum(v);
+        if (TEAM > 32) {
+            const int tid = threadIdx.x;
+            if ((tid & 31) == 0) red[tid >> 5] = v;
+            __syncthreads();
+            v = red[0];
+#pragma unroll
+            for (int w = 1; w < WARPS; ++w) v += red[w];
+            __syncthreads();
+        }
+        return v;
+    }
+    __device__ static __forceinline__ double max(double v, double* red)
+    {
+        v = warp_max(v);
+        if (TEAM > 32) {
+            const int tid = threadIdx.x;
+            if ((tid & 31) == 0) red[tid >> 5] = v;
+            __syncthreads();
+            v = red[0];
+#pragma unroll
+            for (int w = 1; w < WARPS; ++w) v = fmax(v, red[w]);
+            __syncthreads();
+        }
+        return v;
+    }
+    __device__ static __forceinline__ void argmin(double& v, int& idx, double* red)
+    {
+        warp_argmin(v, idx);
+        if (TEAM > 32) {
+            const int tid = threadIdx.x;
+            if ((tid & 31) == 0) { red[tid >> 5] = v; red[WARPS + (tid >> 5)] = (double)idx; }
+            __syncthreads();
+            v = red[0]; idx = (int)red[WARPS];
+#pragma unroll
+            for (int w = 1; w < WARPS; ++w) {
+                const double ov = red[w]; const int oi = (int)red[WARPS + w];
+                if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+            }
+            __syncthreads();
+        }
+    }
+    __device__ static __forceinline__ bool any(bool p)
+    {
+        if (TEAM == 32) return __any_sync(0xffffffffu, p);
+        return __syncthreads_or(p) != 0;
+    }
+};
+
+// ---- TMA bulk copy global -> shared with mbarrier completion (UBLKCP in SASS) ---------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    // order the previous problem's generic-proxy reads of the slab before the async-proxy overwrite
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(b), "r"(parity) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // Problem policy: ForceAcc stack  x = [qddot ; f]   (ref:src/ForceAcc.cpp:58-137)
+// `rec` points at the record staged in shared memory.
 // ------------------------------------------------------------------------------------------
 template <int NA_, int NC_, int FLAGS_>
 struct ForceAcc {
@@ -69,6 +165,7 @@ struct ForceAcc {
     static constexpr bool CONES = (FLAGS & QPPVM_FLAG_FRICTION_CONES) != 0;
     static constexpr bool TLIM = (FLAGS & QPPVM_FLAG_TORQUE_LIMITS) != 0;
     static constexpr int NV = NA + 6, N = NV + 3 * NC;
+    static constexpr int NB = NV;                            // columns with dense task entries (both levels)
     static constexpr int MD_MAX = 6 * NC > 6 ? 6 * NC : 6;   // dense task rows per level
     // reference row ids
     static constexpr int ROW_DYN = 0, ROW_BOX = 6, ROW_CONE = ROW_BOX + 6 * NC;
@@ -87,140 +184,151 @@ struct ForceAcc {
     static constexpr int REC_UNPADDED = OFF_FBOX + 6 * NC;
     static constexpr int REC = REC_UNPADDED + (REC_UNPADDED & 1);
 
-    __device__ static __forceinline__ double M(const double* __restrict__ rec, int i, int j)
+    __device__ static __forceinline__ double M(const double* rec, int i, int j)
     {
-        return i >= j ? __ldg(rec + OFF_M + i * (i + 1) / 2 + j) : __ldg(rec + OFF_M + j * (j + 1) / 2 + i);
+        return i >= j ? rec[OFF_M + i * (i + 1) / 2 + j] : rec[OFF_M + j * (j + 1) / 2 + i];
     }
     __device__ static __forceinline__ int n_eq(int level) { return level == 0 ? 6 : 12; }
     __device__ static __forceinline__ int eq_row(int level, int e) { return e < 6 ? ROW_DYN + e : ROW_OPT + (e - 6); }
     __device__ static __forceinline__ bool regularised(int) { return true; }   // Cartesian/postural: HST_SEMIDEF
 
-    // Dense task rows of a level into Ad (row-major, ld = N+1, last column = b); diagonal task
+    // Dense task rows of a level into Ad (row-major, ld = NB+1, last column = b); diagonal task
     // weights / targets into dg, db (postural rows are unit rows -> kept as a diagonal).
     // Level 0: waist Cartesian (ForceAcc.cpp:118-122).  Level 1: postural + contact Cartesian (:131).
-    __device__ static int load_tasks(const double* __restrict__ rec, int level, double* Ad, double* dg, double* db, int lane)
+    template <int TEAM>
+    __device__ static int load_tasks(const double* rec, int level, double* Ad, double* dg, double* db, int tid)
     {
-        constexpr int LDA = N + 1;
+        constexpr int LDA = NB + 1;
         const int md = level == 0 ? 6 : 6 * NC;
-        for (int r = 0; r < md; ++r) {
-            const double* Jr = level == 0 ? rec + OFF_JW + r * NV : rec + OFF_JC + r * NV;
-            for (int j = lane; j < N; j += 32) Ad[r * LDA + j] = j < NV ? __ldg(Jr + j) : 0.0;
-        }
-        for (int r = lane; r < md; r += 32) {
+        const double* Jr = level == 0 ? rec + OFF_JW : rec + OFF_JC;
+        for (int e = tid; e < md * NV; e += TEAM) { const int r = e / NV, j = e - r * NV; Ad[r * LDA + j] = Jr[e]; }
+        for (int r = tid; r < md; r += TEAM) {
             const int t = level == 0 ? r : 6 + r;            // task-row index into rhs / Jdqd
-            Ad[r * LDA + N] = __ldg(rec + OFF_RHS + t) - __ldg(rec + OFF_JDQD + t);
+            Ad[r * LDA + NB] = rec[OFF_RHS + t] - rec[OFF_JDQD + t];
         }
-        for (int j = lane; j < N; j += 32) {
+        for (int j = tid; j < N; j += TEAM) {
             const bool post = level == 1 && j < NV;
             dg[j] = post ? 1.0 : 0.0;
-            db[j] = post ? __ldg(rec + OFF_RHS + 6 * (1 + NC) + j) : 0.0;
+            db[j] = post ? rec[OFF_RHS + 6 * (1 + NC) + j] : 0.0;
         }
         return md;
     }
 
     // Coefficients of constraint row `row` as a dense n-vector (smem av) + its two-sided bounds.
     // eopt: A0 x0* (level-1 optimality right-hand sides).
-    __device__ static void build_row(const double* __restrict__ rec, int row, const double* eopt,
-                                     double* av, double& lo, double& hi, int lane)
+    template <int TEAM>
+    __device__ static void build_row(const double* rec, int row, const double* eopt,
+                                     double* av, double& lo, double& hi, int tid)
     {
         if (row < ROW_BOX) {                                   // DynamicFeasibility (base rows of M qdd + h - J^T w)
             const int r = row - ROW_DYN;
-            for (int j = lane; j < N; j += 32) {
+            for (int j = tid; j < N; j += TEAM) {
                 double v;
                 if (j < NV) v = M(rec, r, j);
-                else { const int ci = (j - NV) / 3, k = (j - NV) % 3; v = -__ldg(rec + OFF_JC + (ci * 6 + k) * NV + r); }
+                else { const int ci = (j - NV) / 3, k = (j - NV) % 3; v = -rec[OFF_JC + (ci * 6 + k) * NV + r]; }
                 av[j] = v;
             }
-            lo = hi = -__ldg(rec + OFF_H + r);
+            lo = hi = -rec[OFF_H + r];
         } else if (row < ROW_CONE) {                           // wrench box (GenericConstraint)
             const int ci = (row - ROW_BOX) / 6, k = (row - ROW_BOX) % 6;
-            for (int j = lane; j < N; j += 32) av[j] = (k < 3 && j == NV + 3 * ci + k) ? 1.0 : 0.0;
-            if (k < 3) { lo = __ldg(rec + OFF_FBOX + 6 * ci + k); hi = __ldg(rec + OFF_FBOX + 6 * ci + 3 + k); }
+            for (int j = tid; j < N; j += TEAM) av[j] = (k < 3 && j == NV + 3 * ci + k) ? 1.0 : 0.0;
+            if (k < 3) { lo = rec[OFF_FBOX + 6 * ci + k]; hi = rec[OFF_FBOX + 6 * ci + 3 + k]; }
             else { lo = -1.0; hi = 1.0; }
         } else if (CONES && row < ROW_TAU) {                   // friction pyramid on R^T f
             const int ci = (row - ROW_CONE) / 5, jr = (row - ROW_CONE) % 5;
             const double* R = rec + OFF_CONE + 10 * ci;
-            const double mu = __ldg(R + 9) * 0.70710678118654752440;
+            const double mu = R[9] * 0.70710678118654752440;
             const double c0 = jr == 0 ? 1.0 : (jr == 1 ? -1.0 : 0.0);
             const double c1 = jr == 2 ? 1.0 : (jr == 3 ? -1.0 : 0.0);
             const double c2 = jr == 4 ? -1.0 : -mu;
-            for (int j = lane; j < N; j += 32) {
+            for (int j = tid; j < N; j += TEAM) {
                 double v = 0.0;
                 const int k = j - (NV + 3 * ci);
-                if (k >= 0 && k < 3) v = c0 * __ldg(R + 3 * k) + c1 * __ldg(R + 3 * k + 1) + c2 * __ldg(R + 3 * k + 2);
+                if (k >= 0 && k < 3) v = c0 * R[3 * k] + c1 * R[3 * k + 1] + c2 * R[3 * k + 2];
                 av[j] = v;
             }
             lo = -QPPVM_INFTY; hi = 0.0;
         } else if (TLIM && row < ROW_OPT) {                    // torque limits on M_a qdd + h_a - J_a^T f
             const int a = row - ROW_TAU;
-            for (int j = lane; j < N; j += 32) {
+            for (int j = tid; j < N; j += TEAM) {
                 double v;
                 if (j < NV) v = M(rec, 6 + a, j);
-                else { const int ci = (j - NV) / 3, k = (j - NV) % 3; v = -__ldg(rec + OFF_JC + (ci * 6 + k) * NV + 6 + a); }
+                else { const int ci = (j - NV) / 3, k = (j - NV) % 3; v = -rec[OFF_JC + (ci * 6 + k) * NV + 6 + a]; }
                 av[j] = v;
             }
-            const double ha = __ldg(rec + OFF_H + 6 + a);
-            lo = __ldg(rec + OFF_TAULIM + a) - ha; hi = __ldg(rec + OFF_TAULIM + NA + a) - ha;
+            const double ha = rec[OFF_H + 6 + a];
+            lo = rec[OFF_TAULIM + a] - ha; hi = rec[OFF_TAULIM + NA + a] - ha;
         } else {                                               // optimality rows of level 0: J_waist x = J_waist x0*
             const int r = row - ROW_OPT;
-            for (int j = lane; j < N; j += 32) av[j] = j < NV ? __ldg(rec + OFF_JW + r * NV + j) : 0.0;
+            for (int j = tid; j < N; j += TEAM) av[j] = j < NV ? rec[OFF_JW + r * NV + j] : 0.0;
             lo = hi = eopt[r];
         }
     }
 
-    // Inequality slot q -> (row id, value a.x, lo, hi).  One slot per lane.
-    __device__ static void eval_slot(const double* __restrict__ rec, int q, const double* x,
+    // Inequality slot q -> (row id, value a.x, lo, hi).  One slot per thread.
+    __device__ static void eval_slot(const double* rec, int q, const double* x,
                                      int& row, double& val, double& lo, double& hi)
     {
         if (q < NI_BOX) {
             const int ci = q / 3, k = q % 3;
             row = ROW_BOX + 6 * ci + k;
             val = x[NV + q];
-            lo = __ldg(rec + OFF_FBOX + 6 * ci + k); hi = __ldg(rec + OFF_FBOX + 6 * ci + 3 + k);
+            lo = rec[OFF_FBOX + 6 * ci + k]; hi = rec[OFF_FBOX + 6 * ci + 3 + k];
         } else if (CONES && q < NI_BOX + NI_CONE) {
             const int qq = q - NI_BOX, ci = qq / 5, jr = qq % 5;
             row = ROW_CONE + qq;
             const double* R = rec + OFF_CONE + 10 * ci;
-            const double mu = __ldg(R + 9) * 0.70710678118654752440;
+            const double mu = R[9] * 0.70710678118654752440;
             const double c0 = jr == 0 ? 1.0 : (jr == 1 ? -1.0 : 0.0);
             const double c1 = jr == 2 ? 1.0 : (jr == 3 ? -1.0 : 0.0);
             const double c2 = jr == 4 ? -1.0 : -mu;
             double v = 0.0;
 #pragma unroll
             for (int k = 0; k < 3; ++k)
-                v += (c0 * __ldg(R + 3 * k) + c1 * __ldg(R + 3 * k + 1) + c2 * __ldg(R + 3 * k + 2)) * x[NV + 3 * ci + k];
+                v += (c0 * R[3 * k] + c1 * R[3 * k + 1] + c2 * R[3 * k + 2]) * x[NV + 3 * ci + k];
             val = v; lo = -QPPVM_INFTY; hi = 0.0;
         } else {
             const int a = q - NI_BOX - NI_CONE;
             row = ROW_TAU + a;
-            double v = 0.0;
-            for (int j = 0; j < NV; ++j) v += M(rec, 6 + a, j) * x[j];
-            for (int j = 0; j < 3 * NC; ++j) v -= __ldg(rec + OFF_JC + ((j / 3) * 6 + (j % 3)) * NV + 6 + a) * x[NV + j];
-            const double ha = __ldg(rec + OFF_H + 6 + a);
-            val = v; lo = __ldg(rec + OFF_TAULIM + a) - ha; hi = __ldg(rec + OFF_TAULIM + NA + a) - ha;
+            double v0 = 0.0, v1 = 0.0;
+            const int i = 6 + a;
+            const double* Mi = rec + OFF_M + i * (i + 1) / 2;
+#pragma unroll 2
+            for (int j = 0; j <= i; ++j) v0 = fma(Mi[j], x[j], v0);
+#pragma unroll 2
+            for (int j = i + 1; j < NV; ++j) v1 = fma(rec[OFF_M + j * (j + 1) / 2 + i], x[j], v1);
+#pragma unroll 1
+            for (int j = 0; j < 3 * NC; ++j) v0 = fma(-rec[OFF_JC + ((j / 3) * 6 + (j % 3)) * NV + i], x[NV + j], v0);
+            const double ha = rec[OFF_H + i];
+            val = v0 + v1; lo = rec[OFF_TAULIM + a] - ha; hi = rec[OFF_TAULIM + NA + a] - ha;
         }
     }
 
     // Level-0 task value A0 x0* (6 numbers) -> eopt.
-    __device__ static void task0_value(const double* __restrict__ rec, const double* x, double* eopt, int lane)
+    template <int TEAM>
+    __device__ static void task0_value(const double* rec, const double* x, double* eopt, int tid)
     {
-        for (int r = 0; r < QPPVM_M0; ++r) {
-            double s = 0.0;
-            for (int j = lane; j < NV; j += 32) s += __ldg(rec + OFF_JW + r * NV + j) * x[j];
-            s = warp_sum(s);
-            if (lane == 0) eopt[r] = s;
+        if (tid < QPPVM_M0) {
+            double s0 = 0.0, s1 = 0.0;
+            const double* Jr = rec + OFF_JW + tid * NV;
+            int j = 0;
+            for (; j + 1 < NV; j += 2) { s0 = fma(Jr[j], x[j], s0); s1 = fma(Jr[j + 1], x[j + 1], s1); }
+            if (j < NV) s0 = fma(Jr[j], x[j], s0);
+            eopt[tid] = s0 + s1;
         }
     }
 
     // tau = (M qdd + h - sum J_c^T [f;0]) actuated rows  (ref:src/ForceAcc.cpp:206-219)
-    __device__ static void recover(const double* __restrict__ rec, const double* x, double* tau_out, bool ok, int lane)
+    template <int TEAM>
+    __device__ static void recover(const double* rec, const double* x, double* tau_out, bool ok, int tid)
     {
-        for (int a = lane; a < NA; a += 32) {
+        for (int a = tid; a < NA; a += TEAM) {
             double v = 0.0;
             if (ok) {
-                v = __ldg(rec + OFF_H + 6 + a);
-                for (int j = 0; j < NV; ++j) v += M(rec, 6 + a, j) * x[j];
-                for (int j = 0; j < 3 * NC; ++j) v -= __ldg(rec + OFF_JC + ((j / 3) * 6 + (j % 3)) * NV + 6 + a) * x[NV + j];
+                const int i = 6 + a;
+                v = rec[OFF_H + i];
+                for (int j = 0; j < NV; ++j) v = fma(M(rec, i, j), x[j], v);
+                for (int j = 0; j < 3 * NC; ++j) v = fma(-rec[OFF_JC + ((j / 3) * 6 + (j % 3)) * NV + i], x[NV + j], v);
             }
             tau_out[a] = v;     // failure: nothing is commanded (ForceAcc.cpp:189-193) -> zeros
         }
@@ -228,524 +336,633 @@ struct ForceAcc {
 };
 
 // ------------------------------------------------------------------------------------------
-// Per-warp shared-memory slab
+// Shared-memory slab of one team
 // ------------------------------------------------------------------------------------------
 template <class P>
 struct Slab {
-    static constexpr int N = P::N;
-    static constexpr int LDJ = N | 1;                 // odd column stride
-    static constexpr int LDA = N + 1;
+    static constexpr int N = P::N, NB = P::NB;
+    static constexpr int LDJ = NB | 1;                // odd column stride
+    static constexpr int LDA = NB + 1;
     static constexpr int VEC = (N + 3) & ~3;
-    static constexpr int SZ_J = N * LDJ;
-    static constexpr int SZ_Q = (N * LDQ > P::MD_MAX * LDA) ? N * LDQ : P::MD_MAX * LDA;   // Q1, aliased by Ad
-    static constexpr int SZ_R = KMAX * LDR;
-    static constexpr int NVEC = 9;                    // u0 u x w w2 av dg db xp
-    static constexpr int SZ_SMALL = 4 * KMAX + 8;     // d1 r lam | eopt
-    static constexpr int DOUBLES = SZ_J + SZ_Q + SZ_R + NVEC * VEC + SZ_SMALL;
-    static constexpr int INTS = 2 * KMAX + ((P::NROWS + 3) & ~3);   // act_row, act_sgn, cstate(bytes as ints/4)
-    static constexpr int BYTES = DOUBLES * 8 + (2 * KMAX) * 4 + ((P::NROWS + 15) & ~15);
+    // offsets in doubles from the slab base
+    static constexpr int O_REC = 0;                   // staged record (16-B aligned: first in the slab)
+    static constexpr int O_J = O_REC + P::REC;
+    static constexpr int SZ_J = NB * LDJ + (NB * LDJ & 1);
+    static constexpr int O_Q = O_J + SZ_J;            // Q1, aliased by Ad during the factorisation
+    static constexpr int SZ_Q = (N * LDQ > P::MD_MAX * LDA) ? N * LDQ : P::MD_MAX * LDA;
+    static constexpr int O_R = O_Q + SZ_Q;
+    static constexpr int O_VEC = O_R + KMAX * LDR;    // u0 u x w w2 av dg db xp jd
+    static constexpr int O_SMALL = O_VEC + 10 * VEC;  // d1 rr lam (KMAX each) | eopt 8 | red 16
+    static constexpr int O_MBAR = O_SMALL + 3 * KMAX + 8 + 16;
+    static constexpr int O_STATE = O_MBAR + 1;        // ints: k, n_act_ineq, iters, - | act_row[KMAX] | act_sgn[KMAX]
+    static constexpr int O_CSTATE = O_STATE + 2 + KMAX;   // bytes
+    static constexpr int DOUBLES = O_CSTATE + ((P::NROWS + 15) & ~15) / 8;
+    static constexpr int BYTES = DOUBLES * 8;
 };
 
 // ------------------------------------------------------------------------------------------
 // The solver
 // ------------------------------------------------------------------------------------------
-template <class P>
+template <class P, int TEAM>
 struct Solver {
     using S = Slab<P>;
-    static constexpr int N = P::N, LDJ = S::LDJ, LDA = S::LDA;
+    static constexpr int N = P::N, NB = P::NB, LDJ = S::LDJ, LDA = S::LDA;
 
-    double *Jm, *Q1, *Ad, *RN, *u0, *u, *x, *w, *w2, *av, *dg, *db, *xp, *d1, *rr, *lam, *eopt;
-    int *act_row, *act_sgn;
-    unsigned char* cstate;
-    int lane, k, n_act_ineq, iters;
-    const double* rec;
+#define QP_SM(name, off) __device__ static __forceinline__ double* name##_() { return reinterpret_cast<double*>(g_smem) + (off); }
+    QP_SM(rec, S::O_REC) QP_SM(Jm, S::O_J) QP_SM(Q1, S::O_Q) QP_SM(Ad, S::O_Q) QP_SM(RN, S::O_R)
+    QP_SM(u0, S::O_VEC) QP_SM(u, S::O_VEC + S::VEC) QP_SM(x, S::O_VEC + 2 * S::VEC) QP_SM(w, S::O_VEC + 3 * S::VEC)
+    QP_SM(w2, S::O_VEC + 4 * S::VEC) QP_SM(av, S::O_VEC + 5 * S::VEC) QP_SM(dg, S::O_VEC + 6 * S::VEC)
+    QP_SM(db, S::O_VEC + 7 * S::VEC) QP_SM(xp, S::O_VEC + 8 * S::VEC) QP_SM(jd, S::O_VEC + 9 * S::VEC)
+    QP_SM(d1, S::O_SMALL) QP_SM(rr, S::O_SMALL + KMAX) QP_SM(lam, S::O_SMALL + 2 * KMAX)
+    QP_SM(eopt, S::O_SMALL + 3 * KMAX) QP_SM(red, S::O_SMALL + 3 * KMAX + 8)
+#undef QP_SM
+    __device__ static __forceinline__ uint64_t* mbar_() { return reinterpret_cast<uint64_t*>(g_smem) + S::O_MBAR; }
+    __device__ static __forceinline__ int* state_() { return reinterpret_cast<int*>(reinterpret_cast<double*>(g_smem) + S::O_STATE); }
+    __device__ static __forceinline__ unsigned char* cstate_() { return g_smem + 8 * S::O_CSTATE; }
+    using tm = Team<TEAM>;
+// Local aliases of the slab regions (constant addresses: no registers, no memory loads).
+#define QP_BIND                                                                                         \
+    double* const rec = rec_(); double* const Jm = Jm_(); double* const Q1 = Q1_(); double* const Ad = Ad_(); \
+    double* const RN = RN_(); double* const u0 = u0_(); double* const u = u_(); double* const x = x_();     \
+    double* const w = w_(); double* const w2 = w2_(); double* const av = av_(); double* const dg = dg_();   \
+    double* const db = db_(); double* const xp = xp_(); double* const jd = jd_(); double* const d1 = d1_(); \
+    double* const rr = rr_(); double* const lam = lam_(); double* const eopt = eopt_(); double* const red = red_(); \
+    int* const st = state_(); int* const act_row = st + 4; int* const act_sgn = st + 4 + KMAX;             \
+    unsigned char* const cstate = cstate_(); const int tid = threadIdx.x;                                  \
+    (void)rec; (void)Jm; (void)Q1; (void)Ad; (void)RN; (void)u0; (void)u; (void)x; (void)w; (void)w2; (void)av; \
+    (void)dg; (void)db; (void)xp; (void)jd; (void)d1; (void)rr; (void)lam; (void)eopt; (void)red; (void)st; \
+    (void)act_row; (void)act_sgn; (void)cstate; (void)tid;
+    // st[0] = k (active constraints), st[1] = active inequalities, st[2] = working-set changes
 
-    __device__ void bind(unsigned char* slab, int lane_)
+    // ---- whitening: R^T R = D + eps I + Ad^T Ad via Householder QR of the stacked matrix, then J = R^-1
+    // on the leading NB x NB block; columns >= NB carry no dense task entries and stay diagonal (jd).
+    // u0 = R^-T (D db + Ad^T b + eps xp) comes out as the transformed right-hand side.
+    __device__ static __noinline__ void factor(int md, double eps)
     {
-        double* p = reinterpret_cast<double*>(slab);
-        Jm = p; p += S::SZ_J;
-        Q1 = p; Ad = p; p += S::SZ_Q;
-        RN = p; p += S::SZ_R;
-        u0 = p; p += S::VEC; u = p; p += S::VEC; x = p; p += S::VEC; w = p; p += S::VEC; w2 = p; p += S::VEC;
-        av = p; p += S::VEC; dg = p; p += S::VEC; db = p; p += S::VEC; xp = p; p += S::VEC;
-        d1 = p; p += KMAX; rr = p; p += KMAX; lam = p; p += KMAX; p += KMAX; eopt = p; p += 8;
-        act_row = reinterpret_cast<int*>(p); act_sgn = act_row + KMAX;
-        cstate = reinterpret_cast<unsigned char*>(act_sgn + KMAX);
-        lane = lane_;
-    }
-
-    // ---- whitening: R^T R = D + eps I + Ad^T Ad via Householder QR of the stacked matrix, then J = R^-1.
-    // u0 = R^-T (D db + Ad^T b + eps xp)  comes out as the transformed right-hand side.
-    __device__ void factor(int md, double eps)
-    {
-        for (int i = lane; i < N * LDJ; i += 32) Jm[i] = 0.0;
-        __syncwarp();
-        for (int i = lane; i < N; i += 32) {
+        QP_BIND
+        for (int i = tid; i < NB * LDJ; i += TEAM) Jm[i] = 0.0;
+        tm::sync();
+        for (int i = tid; i < N; i += TEAM) {
             const double dd = dg[i] + eps;
             const double rt = sqrt(dd);
-            Jm[i * LDJ + i] = rt;
+            if (i < NB) Jm[i * LDJ + i] = rt; else jd[i] = 1.0 / rt;
             u0[i] = dd > 0.0 ? (dg[i] * db[i] + eps * xp[i]) / rt : 0.0;
         }
-        __syncwarp();
-        for (int kc = 0; kc < N; ++kc) {
-            double sigma = 0.0;
-            for (int r = 0; r < md; ++r) { const double a = Ad[r * LDA + kc]; sigma = fma(a, a, sigma); }
-            if (sigma == 0.0) continue;                        // warp-uniform
+        tm::sync();
+#pragma unroll 1
+        for (int kc = 0; kc < NB; ++kc) {
+            double sg0 = 0.0, sg1 = 0.0;
+            int r = 0;
+#pragma unroll 2
+            for (; r + 1 < md; r += 2) {
+                const double a = Ad[r * LDA + kc], b = Ad[(r + 1) * LDA + kc];
+                sg0 = fma(a, a, sg0); sg1 = fma(b, b, sg1);
+            }
+            if (r < md) { const double a = Ad[r * LDA + kc]; sg0 = fma(a, a, sg0); }
+            const double sigma = sg0 + sg1;
+            if (sigma == 0.0) continue;                        // team-uniform
             const double alpha = Jm[kc * LDJ + kc];
             const double nrm = sqrt(fma(alpha, alpha, sigma));
             const double v1 = -sigma / (alpha + nrm);          // alpha - nrm, cancellation-free (alpha >= 0)
             const double tau = 2.0 / fma(v1, v1, sigma);
             const double top_rhs = u0[kc];
-            __syncwarp();
-            for (int j = kc + 1 + lane; j <= N; j += 32) {     // trailing columns + rhs column (j == N)
-                double s = (j == N) ? v1 * top_rhs : 0.0;
-                for (int r = 0; r < md; ++r) s = fma(Ad[r * LDA + kc], Ad[r * LDA + j], s);
-                s *= tau;
-                if (j == N) u0[kc] = top_rhs - s * v1; else Jm[j * LDJ + kc] = -s * v1;
-                for (int r = 0; r < md; ++r) Ad[r * LDA + j] = fma(-s, Ad[r * LDA + kc], Ad[r * LDA + j]);
+            tm::sync();
+#pragma unroll 1
+            for (int j = kc + 1 + tid; j <= NB; j += TEAM) {   // trailing columns + rhs column (j == NB)
+                double s0 = (j == NB) ? v1 * top_rhs : 0.0, s1 = 0.0;
+                r = 0;
+#pragma unroll 2
+                for (; r + 1 < md; r += 2) {
+                    s0 = fma(Ad[r * LDA + kc], Ad[r * LDA + j], s0);
+                    s1 = fma(Ad[(r + 1) * LDA + kc], Ad[(r + 1) * LDA + j], s1);
+                }
+                if (r < md) s0 = fma(Ad[r * LDA + kc], Ad[r * LDA + j], s0);
+                const double sc = (s0 + s1) * tau;
+                if (j == NB) u0[kc] = top_rhs - sc * v1; else Jm[j * LDJ + kc] = -sc * v1;
+#pragma unroll 4
+                for (r = 0; r < md; ++r) Ad[r * LDA + j] = fma(-sc, Ad[r * LDA + kc], Ad[r * LDA + j]);
             }
-            if (lane == 0) Jm[kc * LDJ + kc] = nrm;
-            __syncwarp();
+            if (tid == 0) Jm[kc * LDJ + kc] = nrm;
+            tm::sync();
         }
-        // in-place inverse of the upper-triangular R (column-major): row i of J overwrites row i of R
-        for (int i = N - 1; i >= 0; --i) {
+        // in-place inverse of the upper-triangular R (column-major): row i of J overwrites row i of R.
+        // The strictly lower part of Jm stays zero, so the l-loop runs to the pass' last column for every thread.
+#pragma unroll 1
+        for (int i = NB - 1; i >= 0; --i) {
             const double rinv = 1.0 / Jm[i * LDJ + i];
-            double acc[2];
+            constexpr int PASSES = (NB + TEAM - 1) / TEAM;
+            double acc[PASSES];
 #pragma unroll
-            for (int pss = 0; pss < 2; ++pss) {
-                const int j = lane + 32 * pss;
-                double a = (j == i) ? 1.0 : 0.0;
-                if (j < N && j > i)
-                    for (int l = i + 1; l <= j; ++l) a = fma(-Jm[l * LDJ + i], Jm[j * LDJ + l], a);
-                acc[pss] = a * rinv;
+            for (int pss = 0; pss < PASSES; ++pss) {
+                const int j = tid + TEAM * pss;
+                const int jl = (TEAM * (pss + 1) < NB ? TEAM * (pss + 1) : NB) - 1;   // last column of this pass
+                double a0 = (j == i) ? 1.0 : 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                if (j < NB && jl > i) {
+                    const double* Jc = Jm + j * LDJ;
+                    int l = i + 1;
+#pragma unroll 2
+                    for (; l + 3 <= jl; l += 4) {
+                        a0 = fma(-Jm[l * LDJ + i], Jc[l], a0);
+                        a1 = fma(-Jm[(l + 1) * LDJ + i], Jc[l + 1], a1);
+                        a2 = fma(-Jm[(l + 2) * LDJ + i], Jc[l + 2], a2);
+                        a3 = fma(-Jm[(l + 3) * LDJ + i], Jc[l + 3], a3);
+                    }
+#pragma unroll 1
+                    for (; l <= jl; ++l) a0 = fma(-Jm[l * LDJ + i], Jc[l], a0);
+                }
+                acc[pss] = ((a0 + a1) + (a2 + a3)) * rinv;
             }
-            __syncwarp();
+            tm::sync();
 #pragma unroll
-            for (int pss = 0; pss < 2; ++pss) {
-                const int j = lane + 32 * pss;
-                if (j < N && j >= i) Jm[j * LDJ + i] = acc[pss];
+            for (int pss = 0; pss < PASSES; ++pss) {
+                const int j = tid + TEAM * pss;
+                if (j < NB && j >= i) Jm[j * LDJ + i] = acc[pss];
             }
-            __syncwarp();
+            tm::sync();
         }
     }
 
-    // w_out = sgn * J^T av   (lanes over j; column j of J is contiguous in i)
-    __device__ void whiten(const double* a, double sgn, double* out)
+    // out = sgn * J^T a   (thread j: column j of J is contiguous in i)
+    __device__ static __noinline__ void whiten(const double* a, double sgn, double* out)
     {
-        for (int j = lane; j < N; j += 32) {
-            double s0 = 0.0, s1 = 0.0;
-            const double* col = Jm + j * LDJ;
-            int i = 0;
-            for (; i + 1 <= j; i += 2) { s0 = fma(col[i], a[i], s0); s1 = fma(col[i + 1], a[i + 1], s1); }
-            if (i <= j) s0 = fma(col[i], a[i], s0);
-            out[j] = sgn * (s0 + s1);
+        QP_BIND
+        for (int j = tid; j < N; j += TEAM) {
+            double r;
+            if (j < NB) {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                const double* col = Jm + j * LDJ;
+                int i = 0;
+#pragma unroll 2
+                for (; i + 3 <= j; i += 4) {
+                    s0 = fma(col[i], a[i], s0); s1 = fma(col[i + 1], a[i + 1], s1);
+                    s2 = fma(col[i + 2], a[i + 2], s2); s3 = fma(col[i + 3], a[i + 3], s3);
+                }
+#pragma unroll 1
+                for (; i <= j; ++i) s0 = fma(col[i], a[i], s0);
+                r = (s0 + s1) + (s2 + s3);
+            } else r = jd[j] * a[j];
+            out[j] = sgn * r;
         }
-        __syncwarp();
+        tm::sync();
     }
-    // x = J u  (lanes over i; row i of J strided by LDJ across j, consecutive across lanes)
-    __device__ void unwhiten(const double* uu, double* xx)
+    // xx = J uu  (thread i: row i of J is strided by LDJ across j, consecutive across threads)
+    __device__ static __noinline__ void unwhiten(const double* uu, double* xx)
     {
-        for (int i = lane; i < N; i += 32) {
-            double s0 = 0.0, s1 = 0.0;
-            int j = i;
-            for (; j + 1 < N; j += 2) { s0 = fma(Jm[j * LDJ + i], uu[j], s0); s1 = fma(Jm[(j + 1) * LDJ + i], uu[j + 1], s1); }
-            if (j < N) s0 = fma(Jm[j * LDJ + i], uu[j], s0);
-            xx[i] = s0 + s1;
+        QP_BIND
+        for (int i = tid; i < N; i += TEAM) {
+            double r;
+            if (i < NB) {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                int j = i;
+#pragma unroll 2
+                for (; j + 3 < NB; j += 4) {
+                    s0 = fma(Jm[j * LDJ + i], uu[j], s0); s1 = fma(Jm[(j + 1) * LDJ + i], uu[j + 1], s1);
+                    s2 = fma(Jm[(j + 2) * LDJ + i], uu[j + 2], s2); s3 = fma(Jm[(j + 3) * LDJ + i], uu[j + 3], s3);
+                }
+#pragma unroll 1
+                for (; j < NB; ++j) s0 = fma(Jm[j * LDJ + i], uu[j], s0);
+                r = (s0 + s1) + (s2 + s3);
+            } else r = jd[i] * uu[i];
+            xx[i] = r;
         }
-        __syncwarp();
+        tm::sync();
     }
-    __device__ double dot(const double* a, const double* b)
+    __device__ static __forceinline__ double dot(const double* a, const double* b)
     {
         double s = 0.0;
-        for (int i = lane; i < N; i += 32) s = fma(a[i], b[i], s);
-        return warp_sum(s);
+        for (int i = threadIdx.x; i < N; i += TEAM) s = fma(a[i], b[i], s);
+        return tm::sum(s, red_());
     }
 
     // d1 (+)= Q1^T v ; v -= Q1 d  (one Gram-Schmidt pass against the k active normals)
-    __device__ void gs_pass(double* v, bool accumulate)
+    __device__ static __noinline__ void gs_pass(double* v, bool accumulate, int k)
     {
-        if (lane < k) {
-            double s0 = 0.0, s1 = 0.0;
+        QP_BIND
+        if (tid < k) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             int i = 0;
-            for (; i + 1 < N; i += 2) { s0 = fma(Q1[i * LDQ + lane], v[i], s0); s1 = fma(Q1[(i + 1) * LDQ + lane], v[i + 1], s1); }
-            if (i < N) s0 = fma(Q1[i * LDQ + lane], v[i], s0);
-            rr[lane] = s0 + s1;                              // rr used as scratch for this pass' coefficients
-            d1[lane] = accumulate ? d1[lane] + s0 + s1 : s0 + s1;
+#pragma unroll 2
+            for (; i + 3 < N; i += 4) {
+                s0 = fma(Q1[i * LDQ + tid], v[i], s0); s1 = fma(Q1[(i + 1) * LDQ + tid], v[i + 1], s1);
+                s2 = fma(Q1[(i + 2) * LDQ + tid], v[i + 2], s2); s3 = fma(Q1[(i + 3) * LDQ + tid], v[i + 3], s3);
+            }
+#pragma unroll 1
+            for (; i < N; ++i) s0 = fma(Q1[i * LDQ + tid], v[i], s0);
+            const double s = (s0 + s1) + (s2 + s3);
+            rr[tid] = s;                                      // rr: scratch for this pass' coefficients
+            d1[tid] = accumulate ? d1[tid] + s : s;
         }
-        __syncwarp();
-        for (int i = lane; i < N; i += 32) {
-            double s = v[i];
-            for (int c = 0; c < k; ++c) s = fma(-Q1[i * LDQ + c], rr[c], s);
-            v[i] = s;
+        tm::sync();
+        for (int i = tid; i < N; i += TEAM) {
+            double s0 = v[i], s1 = 0.0;
+            const double* q = Q1 + i * LDQ;
+            int c = 0;
+#pragma unroll 2
+            for (; c + 1 < k; c += 2) { s0 = fma(-q[c], rr[c], s0); s1 = fma(-q[c + 1], rr[c + 1], s1); }
+            if (c < k) s0 = fma(-q[c], rr[c], s0);
+            v[i] = s0 + s1;
         }
-        __syncwarp();
+        tm::sync();
     }
 
-    // r = RN^-1 d1 (back substitution; lane c holds component c)
-    __device__ void solve_rn()
+    // rr = RN^-1 d1 (back substitution in warp 0; lane c holds component c)
+    __device__ static __noinline__ void solve_rn(int k)
     {
-        double dv = lane < k ? d1[lane] : 0.0;
-        for (int c = k - 1; c >= 0; --c) {
-            const double rc = __shfl_sync(0xffffffffu, dv, c) / RN[c * LDR + c];
-            if (lane == c) dv = rc;
-            else if (lane < c) dv = fma(-RN[c * LDR + lane], rc, dv);
+        QP_BIND
+        if (tid < 32) {
+            double dv = tid < k ? d1[tid] : 0.0;
+#pragma unroll 1
+            for (int c = k - 1; c >= 0; --c) {
+                const double rc = __shfl_sync(0xffffffffu, dv, c) / RN[c * LDR + c];
+                if (tid == c) dv = rc;
+                else if (tid < c) dv = fma(-RN[c * LDR + tid], rc, dv);
+            }
+            if (tid < k) rr[tid] = dv;
         }
-        if (lane < k) rr[lane] = dv;
-        __syncwarp();
+        tm::sync();
     }
 
-    __device__ void drop(int l)
+    // Removes active constraint at position l (k active before the call).
+    __device__ static __noinline__ void drop(int l, int k)
     {
+        QP_BIND
         const int row = act_row[l];
-        __syncwarp();
-        if (lane == 0) cstate[row] = 0;
-        // shift columns l+1.. of RN (and bookkeeping) one to the left
-        for (int c = l; c < k - 1; ++c) {
-            if (lane <= c + 1) RN[c * LDR + lane] = RN[(c + 1) * LDR + lane];
-            __syncwarp();
-        }
+        tm::sync();
+        if (tid == 0) { cstate[row] = 0; st[0] = k - 1; st[1] -= 1; }
+        // shift columns l+1.. of RN (and bookkeeping) one to the left; thread t only touches row t
+        if (tid < KMAX)
+            for (int c = l; c < k - 1; ++c)
+                if (tid <= c + 1) RN[c * LDR + tid] = RN[(c + 1) * LDR + tid];
         {
             double lv = 0.0; int ar = 0, as = 0;
-            if (lane >= l && lane < k - 1) { lv = lam[lane + 1]; ar = act_row[lane + 1]; as = act_sgn[lane + 1]; }
-            __syncwarp();
-            if (lane >= l && lane < k - 1) { lam[lane] = lv; act_row[lane] = ar; act_sgn[lane] = as; }
-            __syncwarp();
+            const bool mv = tid >= l && tid < k - 1;
+            if (mv) { lv = lam[tid + 1]; ar = act_row[tid + 1]; as = act_sgn[tid + 1]; }
+            tm::sync();
+            if (mv) { lam[tid] = lv; act_row[tid] = ar; act_sgn[tid] = as; }
+            tm::sync();
         }
         // Givens: re-triangularise rows i, i+1 ; same rotation on columns i, i+1 of Q1
+#pragma unroll 1
         for (int i = l; i < k - 1; ++i) {
             const double a = RN[i * LDR + i], b = RN[i * LDR + i + 1];
             const double h = hypot(a, b);
             const double c = h > 0.0 ? a / h : 1.0, s = h > 0.0 ? b / h : 0.0;
-            __syncwarp();
-            if (lane >= i && lane < k - 1) {
-                const double ra = RN[lane * LDR + i], rb = RN[lane * LDR + i + 1];
-                RN[lane * LDR + i] = c * ra + s * rb;
-                RN[lane * LDR + i + 1] = -s * ra + c * rb;
+            tm::sync();
+            if (tid >= i && tid < k - 1) {
+                const double ra = RN[tid * LDR + i], rb = RN[tid * LDR + i + 1];
+                RN[tid * LDR + i] = c * ra + s * rb;
+                RN[tid * LDR + i + 1] = -s * ra + c * rb;
             }
-            for (int r = lane; r < N; r += 32) {
+            for (int r = tid; r < N; r += TEAM) {
                 const double qa = Q1[r * LDQ + i], qb = Q1[r * LDQ + i + 1];
                 Q1[r * LDQ + i] = c * qa + s * qb;
                 Q1[r * LDQ + i + 1] = -s * qa + c * qb;
             }
-            __syncwarp();
+            tm::sync();
         }
-        --k; --n_act_ineq;
     }
 
     // Adds constraint `row` with sign sgn (normal sgn*a, already whitened into w), current slack sp <= 0.
     // Returns status; handles partial steps (drops) per Goldfarb-Idnani.
-    __device__ int add_constraint(int row, int sgn, bool is_eq, double sp, double bound_abs, int max_iter)
+    __device__ static __noinline__ int add_constraint(int row, int sgn, bool is_eq, double sp, double bound_abs, int max_iter)
     {
+        QP_BIND
         double up = 0.0;
         const double ww = dot(w, w);
+        int k = st[0], nai = st[1], iters = st[2];
+#pragma unroll 1
         for (;;) {
-            if (iters >= max_iter) return QPPVM_STATUS_MAX_ITER;
-            for (int i = lane; i < N; i += 32) w2[i] = w[i];
-            __syncwarp();
+            if (iters >= max_iter) { tm::sync(); if (tid == 0) st[2] = iters; tm::sync(); return QPPVM_STATUS_MAX_ITER; }
+            for (int i = tid; i < N; i += TEAM) w2[i] = w[i];
+            tm::sync();
             double nrm2 = ww;
             if (k > 0) {
-                gs_pass(w2, false);
-                gs_pass(w2, true);                            // CGS2: "twice is enough"
+                gs_pass(w2, false, k);
+                gs_pass(w2, true, k);                         // CGS2: "twice is enough"
                 nrm2 = dot(w2, w2);
             }
             const bool dependent = !(nrm2 > 1e-22 * ww) || k >= N;
             const bool full = k >= KMAX;
             double t1 = 1e300; int l = -1;
-            if (n_act_ineq > 0) {
-                solve_rn();
+            if (nai > 0) {
+                solve_rn(k);
                 double cand = 1e300; int ci = 0x7fffffff;
-                if (lane < k && (act_sgn[lane] & 1) && rr[lane] > 0.0) { cand = lam[lane] / rr[lane]; ci = lane; }
-                warp_argmin(cand, ci);
+                if (tid < k && (act_sgn[tid] & 1) && rr[tid] > 0.0) { cand = lam[tid] / rr[tid]; ci = tid; }
+                tm::argmin(cand, ci, red);
                 if (ci != 0x7fffffff) { t1 = cand; l = ci; }
             }
-            if (dependent && l < 0) {
-                if (is_eq && -sp <= 1e-8 * fmax(1.0, bound_abs)) return QPPVM_STATUS_OK;   // redundant, consistent
-                return QPPVM_STATUS_INFEASIBLE;
-            }
+            int fail = -1;
+            if (dependent && l < 0)
+                fail = (is_eq && -sp <= 1e-8 * fmax(1.0, bound_abs)) ? QPPVM_STATUS_OK   // redundant, consistent
+                                                                       : QPPVM_STATUS_INFEASIBLE;
             const double t2 = dependent ? 1e300 : -sp / nrm2;
             const double t = t1 < t2 ? t1 : t2;
-            if (full && t == t2) return QPPVM_STATUS_NUMERIC;   // active-set capacity exhausted
-            if (n_act_ineq > 0) { if (lane < k) lam[lane] -= t * rr[lane]; }
+            if (fail < 0 && full && t == t2) fail = QPPVM_STATUS_NUMERIC;   // active-set capacity exhausted
+            if (fail >= 0) { tm::sync(); if (tid == 0) st[2] = iters; tm::sync(); return fail; }
+            if (nai > 0) { if (tid < k) lam[tid] -= t * rr[tid]; }
             up += t;
             if (!dependent) {
-                for (int i = lane; i < N; i += 32) u[i] = fma(t, w2[i], u[i]);
+                for (int i = tid; i < N; i += TEAM) u[i] = fma(t, w2[i], u[i]);
                 sp = fma(t, nrm2, sp);
             }
-            __syncwarp();
+            tm::sync();
             ++iters;
             if (t == t2) {                                    // full step: row becomes active
                 const double nr = sqrt(nrm2), inv = 1.0 / nr;
-                for (int i = lane; i < N; i += 32) Q1[i * LDQ + k] = w2[i] * inv;
-                if (lane < k) RN[k * LDR + lane] = d1[lane];
-                if (lane == 0) {
+                for (int i = tid; i < N; i += TEAM) Q1[i * LDQ + k] = w2[i] * inv;
+                if (tid < k) RN[k * LDR + tid] = d1[tid];
+                if (tid == 0) {
                     RN[k * LDR + k] = nr; lam[k] = up; act_row[k] = row; act_sgn[k] = is_eq ? 2 * sgn : sgn;
                     cstate[row] = 1;
+                    st[0] = k + 1; st[1] = nai + (is_eq ? 0 : 1); st[2] = iters;
                 }
-                __syncwarp();
-                ++k; if (!is_eq) ++n_act_ineq;
+                tm::sync();
                 return QPPVM_STATUS_OK;
             }
-            drop(l);                                          // partial step: blocking constraint leaves
+            drop(l, k);                                       // partial step: blocking constraint leaves
+            --k; --nai;
         }
     }
 
-    // Scan all inactive inequality slots at x; most violated -> (row, sgn, slack<0, |bound|).  Also max violation.
-    __device__ bool scan(int& row, int& sgn, double& sp, double& babs)
+    // Scan all inactive inequality slots at x; returns the most violated row (-1: none) and publishes its
+    // slack (<0), sign and |bound| in red[8..10].
+    __device__ static __noinline__ int scan()
     {
+        QP_BIND
         double worst = 0.0; int widx = 0x7fffffff; int wsgn = 0; double wb = 0.0;
-        for (int q = lane; q < ((P::NI + 31) & ~31); q += 32) {
-            if (q < P::NI) {
-                int r; double val, lo, hi;
-                P::eval_slot(rec, q, x, r, val, lo, hi);
-                if (!cstate[r]) {
-                    const double tol = 1e-9 * fmax(1.0, fabs(val));
-                    const double sl = val - lo, su = hi - val;
-                    if (lo > -0.5 * QPPVM_INFTY && sl < -tol && sl < worst) { worst = sl; widx = r; wsgn = 1; wb = fabs(lo); }
-                    if (hi < 0.5 * QPPVM_INFTY && su < -tol && su < worst) { worst = su; widx = r; wsgn = -1; wb = fabs(hi); }
-                }
+        for (int q = tid; q < P::NI; q += TEAM) {
+            int r; double val, lo, hi;
+            P::eval_slot(rec, q, x, r, val, lo, hi);
+            if (!cstate[r]) {
+                const double tol = 1e-9 * fmax(1.0, fabs(val));
+                const double sl = val - lo, su = hi - val;
+                if (lo > -0.5 * QPPVM_INFTY && sl < -tol && sl < worst) { worst = sl; widx = r; wsgn = 1; wb = fabs(lo); }
+                if (hi < 0.5 * QPPVM_INFTY && su < -tol && su < worst) { worst = su; widx = r; wsgn = -1; wb = fabs(hi); }
             }
         }
         double v = worst; int idx = widx;
-        warp_argmin(v, idx);
-        if (idx == 0x7fffffff) return false;
-        // fetch sgn / bound from the winning lane (the lane whose (worst, widx) equals the winner)
-        const unsigned m = __ballot_sync(0xffffffffu, widx == idx && worst == v);
-        const int src = __ffs(m) - 1;
-        row = idx; sp = v;
-        sgn = __shfl_sync(0xffffffffu, wsgn, src);
-        babs = __shfl_sync(0xffffffffu, wb, src);
-        return true;
+        tm::argmin(v, idx, red);
+        if (idx == 0x7fffffff) return -1;
+        if (widx == idx && worst == v) { red[8] = v; red[9] = (double)wsgn; red[10] = wb; }   // the owner publishes
+        tm::sync();
+        return idx;
     }
 
-    // One level: returns status.  On return x holds the level solution, lam/act_* the multipliers.
-    __device__ int solve_level(int level, const Params& prm, float& kkt_out, double* ydiag)
+    __device__ static __noinline__ int add_equalities(int level, int max_iter)
     {
-        const double eps = P::regularised(level) ? prm.eps_reg : 0.0;
-        const int steps = eps > 0.0 ? prm.n_reg_steps : 0;
-        for (int i = lane; i < N; i += 32) xp[i] = 0.0;
-        for (int i = lane; i < P::NROWS; i += 32) cstate[i] = 0;
-        __syncwarp();
-        int md = P::load_tasks(rec, level, Ad, dg, db, lane);
-        __syncwarp();
-        factor(md, eps);                                      // Ad destroyed; Q1 may now alias it
+        QP_BIND
         int status = QPPVM_STATUS_OK;
-        k = 0; n_act_ineq = 0;
-        for (int i = lane; i < N; i += 32) u[i] = u0[i];
-        __syncwarp();
-        // ---- equalities first (dyn-feas, then level-0 optimality rows), never dropped
         const int neq = P::n_eq(level);
+#pragma unroll 1
         for (int e = 0; e < neq && status == QPPVM_STATUS_OK; ++e) {
             const int row = P::eq_row(level, e);
             double lo, hi;
-            P::build_row(rec, row, eopt, av, lo, hi, lane);
-            __syncwarp();
+            P::template build_row<TEAM>(rec, row, eopt, av, lo, hi, tid);
+            tm::sync();
             whiten(av, 1.0, w);
             const double s = dot(w, u) - lo;
             const int sgn = s > 0.0 ? -1 : 1;
-            if (sgn < 0) { for (int i = lane; i < N; i += 32) w[i] = -w[i]; __syncwarp(); }
-            status = add_constraint(row, sgn, true, -fabs(s), fabs(lo), prm.max_iter);
+            if (sgn < 0) { for (int i = tid; i < N; i += TEAM) w[i] = -w[i]; tm::sync(); }
+            status = add_constraint(row, sgn, true, -fabs(s), fabs(lo), max_iter);
         }
+        return status;
+    }
+
+    __device__ static __forceinline__ void reset_active_set()
+    {
+        QP_BIND
+        for (int i = tid; i < P::NROWS; i += TEAM) cstate[i] = 0;
+        if (tid == 0) { st[0] = 0; st[1] = 0; }
+        for (int i = tid; i < N; i += TEAM) u[i] = u0[i];
+        tm::sync();
+    }
+
+    // One level: returns status.  On return x holds the level solution.
+    // The KKT residual of the level is left in red[12].
+    __device__ static __noinline__ int solve_level(int level, double eps_reg, int n_reg_steps, int max_iter, double* ydiag)
+    {
+        QP_BIND
+        const double eps = P::regularised(level) ? eps_reg : 0.0;
+        const int steps = eps > 0.0 ? n_reg_steps : 0;
+        for (int i = tid; i < N; i += TEAM) xp[i] = 0.0;
+        if (tid == 0) st[2] = 0;
+        tm::sync();
+        const int md = P::template load_tasks<TEAM>(rec, level, Ad, dg, db, tid);
+        tm::sync();
+        factor(md, eps);                                      // Ad destroyed; Q1 may now alias it
+        reset_active_set();
+        // ---- equalities first (dyn-feas, then level-0 optimality rows), never dropped
+        int status = add_equalities(level, max_iter);
         // ---- inequalities + proximal regularisation steps
+#pragma unroll 1
         for (int step = 0; status == QPPVM_STATUS_OK; ++step) {
+#pragma unroll 1
             for (;;) {
                 unwhiten(u, x);
-                int row, sgn; double sp, babs;
-                if (!scan(row, sgn, sp, babs)) break;
+                const int row = scan();
+                if (row < 0) break;
+                const double sp = red[8], babs = red[10];
+                const int sgn = (int)red[9];
                 double lo, hi;
-                P::build_row(rec, row, eopt, av, lo, hi, lane);
-                __syncwarp();
+                P::template build_row<TEAM>(rec, row, eopt, av, lo, hi, tid);
+                tm::sync();
                 whiten(av, (double)sgn, w);
-                status = add_constraint(row, sgn, false, sp, babs, prm.max_iter);
+                status = add_constraint(row, sgn, false, sp, babs, max_iter);
                 if (status != QPPVM_STATUS_OK) break;
             }
             if (status != QPPVM_STATUS_OK || step >= steps) break;
             // qpOASES solveRegularisedQP(): g <- g_orig - eps x_prev, i.e. u0 += delta, delta = eps J^T (x - xp_old);
             // same active set: u += (I - Q1 Q1^T) delta, lam -= RN^-1 Q1^T delta.
-            for (int i = lane; i < N; i += 32) { av[i] = eps * (x[i] - xp[i]); xp[i] = x[i]; }
-            __syncwarp();
+            for (int i = tid; i < N; i += TEAM) { av[i] = eps * (x[i] - xp[i]); xp[i] = x[i]; }
+            tm::sync();
             whiten(av, 1.0, w);
-            for (int i = lane; i < N; i += 32) { u0[i] += w[i]; w2[i] = w[i]; }
-            __syncwarp();
+            for (int i = tid; i < N; i += TEAM) { u0[i] += w[i]; w2[i] = w[i]; }
+            tm::sync();
+            const int k = st[0];
             if (k > 0) {
-                gs_pass(w2, false);
-                gs_pass(w2, true);
-                solve_rn();
-                if (lane < k) lam[lane] -= rr[lane];
+                gs_pass(w2, false, k);
+                gs_pass(w2, true, k);
+                solve_rn(k);
+                if (tid < k) lam[tid] -= rr[tid];
                 // (equality multipliers are re-derived at output time from u - u0); inequality ones must stay >= 0
-                const bool neg = lane < k && (act_sgn[lane] & 1) && lam[lane] < 0.0;
-                if (__any_sync(0xffffffffu, neg)) {
+                const bool neg = tid < k && (act_sgn[tid] & 1) && lam[tid] < 0.0;
+                if (tm::any(neg)) {
                     // rare: active set changes under the proximal shift -> cold restart of this step from u0
-                    for (int i = lane; i < P::NROWS; i += 32) cstate[i] = 0;
-                    k = 0; n_act_ineq = 0;
-                    for (int i = lane; i < N; i += 32) u[i] = u0[i];
-                    __syncwarp();
-                    for (int e = 0; e < neq && status == QPPVM_STATUS_OK; ++e) {
-                        const int row = P::eq_row(level, e);
-                        double lo, hi;
-                        P::build_row(rec, row, eopt, av, lo, hi, lane);
-                        __syncwarp();
-                        whiten(av, 1.0, w);
-                        const double s = dot(w, u) - lo;
-                        const int sgn = s > 0.0 ? -1 : 1;
-                        if (sgn < 0) { for (int i = lane; i < N; i += 32) w[i] = -w[i]; __syncwarp(); }
-                        status = add_constraint(row, sgn, true, -fabs(s), fabs(lo), prm.max_iter);
-                    }
+                    reset_active_set();
+                    status = add_equalities(level, max_iter);
                     continue;
                 }
             }
-            for (int i = lane; i < N; i += 32) u[i] += w2[i];
-            __syncwarp();
+            for (int i = tid; i < N; i += TEAM) u[i] += w2[i];
+            tm::sync();
         }
         if (status == QPPVM_STATUS_OK) {                       // non-finite data must not reach the command
             bool bad = false;
-            for (int i = lane; i < N; i += 32) bad |= !isfinite(x[i]);
-            if (__any_sync(0xffffffffu, bad)) status = QPPVM_STATUS_NUMERIC;
+            for (int i = tid; i < N; i += TEAM) bad |= !isfinite(x[i]);
+            if (tm::any(bad)) status = QPPVM_STATUS_NUMERIC;
         }
-        if (status != QPPVM_STATUS_OK) { kkt_out = __int_as_float(0x7f800000); return status; }
-        kkt_out = (float)kkt(level, md, eps, ydiag);
+        if (status != QPPVM_STATUS_OK) return status;
+        const double kv = kkt(level, md, eps, ydiag);
+        if (tid == 0) red[12] = kv;
+        tm::sync();
         return status;
     }
 
-    // Signed multipliers y (qpOASES convention: > 0 active at lA, < 0 at uA) from u - u0 = sum lam_c w_c:
-    // RN lam = Q1^T (u - u0).  Recomputed here so that equality multipliers are exact after all updates.
-    __device__ void final_multipliers()
-    {
-        for (int i = lane; i < N; i += 32) w2[i] = u[i] - u0[i];
-        __syncwarp();
-        if (lane < k) {
-            double s = 0.0;
-            for (int i = 0; i < N; ++i) s = fma(Q1[i * LDQ + lane], w2[i], s);
-            d1[lane] = s;
-        }
-        __syncwarp();
-        solve_rn();                                           // rr = multipliers of the signed normals
-    }
-
     // KKT certificate of the solved (regularised, proximal-shifted) level problem, SURVEY.md 8(c).
-    __device__ double kkt(int level, int md, double eps, double* ydiag)
+    __device__ static __noinline__ double kkt(int level, int md, double eps, double* ydiag)
     {
-        final_multipliers();
-        // stationarity pieces need the original task rows again (Ad was overwritten by Q1)
-        // grad = D (x - db) + Ad^T (Ad x - b) + eps (x - xp) - sum_c y_c a_c ; kept in w (grad) and w2 (H x)
-        // step 1: constraint part, while Q1 is still alive we only need rr / act_*.
-        for (int i = lane; i < N; i += 32) { w[i] = 0.0; }
-        __syncwarp();
+        QP_BIND
+        const int k = st[0];
+        // Signed multipliers y (qpOASES convention: > 0 active at lA, < 0 at uA) from u - u0 = sum lam_c w_c:
+        // RN lam = Q1^T (u - u0); recomputed here so that equality multipliers are exact after all updates.
+        for (int i = tid; i < N; i += TEAM) w2[i] = u[i] - u0[i];
+        tm::sync();
+        if (tid < k) {
+            double s = 0.0;
+#pragma unroll 2
+            for (int i = 0; i < N; ++i) s = fma(Q1[i * LDQ + tid], w2[i], s);
+            d1[tid] = s;
+        }
+        tm::sync();
+        solve_rn(k);                                          // rr = multipliers of the signed normals
+        // grad = D (x - db) + Ad^T (Ad x - b) + eps (x - xp) - sum_c y_c a_c ; constraint part first (w)
+        for (int i = tid; i < N; i += TEAM) w[i] = 0.0;
+        tm::sync();
         double rprim = 0.0, rcomp = 0.0, cxmax = 0.0, ymax = 0.0;
+#pragma unroll 1
         for (int c = 0; c < k; ++c) {
             const int row = act_row[c];
             const int sg = act_sgn[c];
             double lo, hi;
-            P::build_row(rec, row, eopt, av, lo, hi, lane);
-            __syncwarp();
-            // rr[c] multiplies the signed whitened normal stored at insertion (sign = +-1, eq: +-2)
-            const bool iseq = !(sg & 1);
+            P::template build_row<TEAM>(rec, row, eopt, av, lo, hi, tid);
+            tm::sync();
+            const bool iseq = !(sg & 1);                       // sign = +-1, equalities +-2
             const double y = (sg > 0 ? 1.0 : -1.0) * rr[c];
             const double val = dot(av, x);
-            for (int i = lane; i < N; i += 32) w[i] = fma(-y, av[i], w[i]);
+            for (int i = tid; i < N; i += TEAM) w[i] = fma(-y, av[i], w[i]);
             cxmax = fmax(cxmax, fabs(val)); ymax = fmax(ymax, fabs(y));
             if (iseq) rprim = fmax(rprim, fabs(val - lo));
             else {
                 rprim = fmax(rprim, fmax(0.0, fmax(lo - val, val - hi)));
                 rcomp = fmax(rcomp, y > 0.0 ? y * fabs(val - lo) : -y * fabs(hi - val));
                 if (sg * y < 0.0) rcomp = fmax(rcomp, fabs(y));        // wrong-signed multiplier
-                if (y == 0.0 && lane == 0) cstate[row] = 2;            // weakly active: not reported in the mask
+                if (y == 0.0 && tid == 0) cstate[row] = 2;             // weakly active: not reported in the mask
             }
-            if (ydiag && lane == 0) ydiag[row] = y;
-            __syncwarp();
+            if (ydiag && tid == 0) ydiag[row] = y;
+            tm::sync();
         }
         // inactive inequalities: primal violation only
         {
             double viol = 0.0, cm = 0.0;
-            for (int q = lane; q < ((P::NI + 31) & ~31); q += 32)
-                if (q < P::NI) {
-                    int r; double val, lo, hi;
-                    P::eval_slot(rec, q, x, r, val, lo, hi);
-                    cm = fmax(cm, fabs(val));
-                    if (!cstate[r]) viol = fmax(viol, fmax(lo - val, val - hi));
-                }
-            rprim = fmax(rprim, warp_max(viol)); cxmax = fmax(cxmax, warp_max(cm));
+            for (int q = tid; q < P::NI; q += TEAM) {
+                int r; double val, lo, hi;
+                P::eval_slot(rec, q, x, r, val, lo, hi);
+                cm = fmax(cm, fabs(val));
+                if (!cstate[r]) viol = fmax(viol, fmax(lo - val, val - hi));
+            }
+            rprim = fmax(rprim, tm::max(viol, red)); cxmax = fmax(cxmax, tm::max(cm, red));
         }
-        // step 2: task part (reload the dense task rows over the dead Q1 region)
-        P::load_tasks(rec, level, Ad, dg, db, lane);
-        __syncwarp();
-        if (lane < md) {                                      // residual_r = Ad[r] x - b_r ; also keep (Ad x)_r
-            double s = 0.0;
-            for (int j = 0; j < N; ++j) s = fma(Ad[lane * LDA + j], x[j], s);
-            d1[lane] = s;                                     // (A x)_r
-            rr[lane] = Ad[lane * LDA + N];                    // b_r
+        // task part (reload the dense task rows over the dead Q1 region); (A x)_r -> w2, b_r -> av
+        tm::sync();
+        P::template load_tasks<TEAM>(rec, level, Ad, dg, db, tid);
+        tm::sync();
+        for (int r = tid; r < md; r += TEAM) {
+            double s0 = 0.0, s1 = 0.0;
+            int j = 0;
+#pragma unroll 2
+            for (; j + 1 < NB; j += 2) { s0 = fma(Ad[r * LDA + j], x[j], s0); s1 = fma(Ad[r * LDA + j + 1], x[j + 1], s1); }
+            if (j < NB) s0 = fma(Ad[r * LDA + j], x[j], s0);
+            w2[r] = s0 + s1;
+            av[r] = Ad[r * LDA + NB];
         }
-        __syncwarp();
+        tm::sync();
         double rs = 0.0, gmax = 0.0, hxmax = 0.0, xmax = 0.0;
-        for (int j = lane; j < N; j += 32) {
+        for (int j = tid; j < N; j += TEAM) {
             double hx = (dg[j] + eps) * x[j], g = -dg[j] * db[j] - eps * xp[j];
-            for (int r = 0; r < md; ++r) { hx = fma(Ad[r * LDA + j], d1[r], hx); g = fma(-Ad[r * LDA + j], rr[r], g); }
-            const double st = hx + g + w[j];
-            rs = fmax(rs, fabs(st)); gmax = fmax(gmax, fabs(g)); hxmax = fmax(hxmax, fabs(hx)); xmax = fmax(xmax, fabs(x[j]));
+            if (j < NB)
+#pragma unroll 2
+                for (int r = 0; r < md; ++r) { hx = fma(Ad[r * LDA + j], w2[r], hx); g = fma(-Ad[r * LDA + j], av[r], g); }
+            const double stn = hx + g + w[j];
+            rs = fmax(rs, fabs(stn)); gmax = fmax(gmax, fabs(g)); hxmax = fmax(hxmax, fabs(hx)); xmax = fmax(xmax, fabs(x[j]));
         }
-        rs = warp_max(rs); gmax = warp_max(gmax); hxmax = warp_max(hxmax); xmax = warp_max(xmax);
+        rs = tm::max(rs, red); gmax = tm::max(gmax, red); hxmax = tm::max(hxmax, red); xmax = tm::max(xmax, red);
         rs /= fmax(1.0, fmax(gmax, hxmax));
         rprim /= fmax(1.0, fmax(xmax, cxmax));
         rcomp /= fmax(1.0, ymax) * fmax(1.0, cxmax);
         return fmax(rs, fmax(rprim, rcomp));
     }
+#undef QP_BIND
 };
 
 // ------------------------------------------------------------------------------------------
-// Kernel: persistent warps pull problem indices from a global counter.
+// Kernel: persistent CTAs (one team each) pull problem indices from a global counter.
 // ------------------------------------------------------------------------------------------
-template <class P, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+template <class P, int TEAM>
+__global__ void __launch_bounds__(TEAM)
 qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out, double* __restrict__ diag,
                 long long batch, Params prm, unsigned long long* __restrict__ counter)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    using S = Slab<P>;
+    using SV = Solver<P, TEAM>;
     constexpr int N = P::N;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    Solver<P> sv;
-    sv.bind(smem + (size_t)warp * S::BYTES, lane);
+    const int tid = threadIdx.x;
     constexpr int OUT_BYTES = 8 * (N + P::NA) + 32;
     constexpr int DIAG = N + 2 * P::NROWS + QPPVM_M0;
+    __shared__ unsigned long long s_idx;
+    if (tid == 0) mbar_init(SV::mbar_(), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    uint32_t phase = 0;
+#pragma unroll 1
     for (;;) {
-        unsigned long long idx = 0;
-        if (lane == 0) idx = atomicAdd(counter, 1ull);
-        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (tid == 0) {
+            const unsigned long long i = atomicAdd(counter, 1ull);
+            s_idx = i;
+            if ((long long)i < batch)                          // one TMA bulk copy stages the whole record
+                bulk_load(SV::rec_(), recs + i * (size_t)P::REC, (uint32_t)(P::REC * sizeof(double)), SV::mbar_());
+        }
+        __syncthreads();
+        const unsigned long long idx = s_idx;
         if ((long long)idx >= batch) break;
-        sv.rec = recs + idx * (size_t)P::REC;
         double* xo = reinterpret_cast<double*>(out + idx * (size_t)OUT_BYTES);
         double* dg = diag ? diag + idx * (size_t)DIAG : nullptr;
-        if (dg) for (int i = lane; i < DIAG; i += 32) dg[i] = 0.0;
-        sv.iters = 0;
+        if (dg) for (int i = tid; i < DIAG; i += TEAM) dg[i] = 0.0;
+        mbar_wait(SV::mbar_(), phase); phase ^= 1;
         float kkt0 = __int_as_float(0x7f800000), kkt1 = kkt0;
         int it0 = 0, it1 = 0;
-        int status = sv.solve_level(0, prm, kkt0, dg ? dg + N : nullptr);
-        it0 = sv.iters;
+        int status = SV::solve_level(0, prm.eps_reg, prm.n_reg_steps, prm.max_iter, dg ? dg + N : nullptr);
+        it0 = SV::state_()[2];
+        if (status == QPPVM_STATUS_OK) kkt0 = (float)SV::red_()[12];
         if (status == QPPVM_STATUS_OK) {
-            P::task0_value(sv.rec, sv.x, sv.eopt, lane);
-            __syncwarp();
+            P::template task0_value<TEAM>(SV::rec_(), SV::x_(), SV::eopt_(), tid);
+            Team<TEAM>::sync();
             if (dg) {
-                for (int i = lane; i < N; i += 32) dg[i] = sv.x[i];
-                if (lane < QPPVM_M0) dg[N + 2 * P::NROWS + lane] = sv.eopt[lane];
+                for (int i = tid; i < N; i += TEAM) dg[i] = SV::x_()[i];
+                if (tid < QPPVM_M0) dg[N + 2 * P::NROWS + tid] = SV::eopt_()[tid];
             }
-            sv.iters = 0;
-            status = sv.solve_level(1, prm, kkt1, dg ? dg + N + P::NROWS : nullptr);
-            it1 = sv.iters;
+            Team<TEAM>::sync();
+            status = SV::solve_level(1, prm.eps_reg, prm.n_reg_steps, prm.max_iter, dg ? dg + N + P::NROWS : nullptr);
+            it1 = SV::state_()[2];
+            if (status == QPPVM_STATUS_OK) kkt1 = (float)SV::red_()[12];
         }
         const bool ok = status == QPPVM_STATUS_OK;
-        for (int i = lane; i < N; i += 32) xo[i] = ok ? sv.x[i] : 0.0;
-        P::recover(sv.rec, sv.x, xo + N, ok, lane);
+        for (int i = tid; i < N; i += TEAM) xo[i] = ok ? SV::x_()[i] : 0.0;
+        P::template recover<TEAM>(SV::rec_(), SV::x_(), xo + N, ok, tid);
         // trailer: status, iters, 128-bit active mask of level 1, kkt[2]
-        uint32_t mask = 0;
-        if (ok && lane < 4)
-            for (int b = 0; b < 32; ++b) {
-                const int r = lane * 32 + b;
-                if (r < P::NROWS && sv.cstate[r] == 1) mask |= 1u << b;
-            }
         uint32_t* tr = reinterpret_cast<uint32_t*>(xo + N + P::NA);
-        if (lane == 0) { tr[0] = (uint32_t)status; tr[1] = (uint32_t)((it0 & 0xffff) | (it1 << 16)); }
-        if (lane < 4) tr[2 + lane] = mask;
-        if (lane == 0) { tr[6] = __float_as_uint(kkt0); tr[7] = __float_as_uint(kkt1); }
-        __syncwarp();
+        if (tid < 4) {
+            uint32_t mask = 0;
+            if (ok)
+                for (int b = 0; b < 32; ++b) {
+                    const int r = tid * 32 + b;
+                    if (r < P::NROWS && SV::cstate_()[r] == 1) mask |= 1u << b;
+                }
+            tr[2 + tid] = mask;
+        }
+        if (tid == 0) {
+            tr[0] = (uint32_t)status; tr[1] = (uint32_t)((it0 & 0xffff) | (it1 << 16));
+            tr[6] = __float_as_uint(kkt0); tr[7] = __float_as_uint(kkt1);
+        }
+        __syncthreads();                                       // slab (incl. s_idx, rec) is reused by the next problem
     }
 }
 

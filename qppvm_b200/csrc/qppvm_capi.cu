@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include "qp_kernel.cuh"
@@ -15,7 +16,7 @@ char g_create_error[512] = "";
 
 struct ShapeEntry {
     int kind, n_a, n_c, flags;
-    const void* kernel;
+    const void* kernel[2];       // TEAM = 32, 64 threads per problem
     int slab_bytes;
 };
 
@@ -23,7 +24,8 @@ struct ShapeEntry {
 template <class P>
 constexpr ShapeEntry entry()
 {
-    return ShapeEntry{P::KIND, P::NA, P::NC, P::FLAGS, (const void*)&qp_solve_kernel<P, 1>, Slab<P>::BYTES};
+    return ShapeEntry{P::KIND, P::NA, P::NC, P::FLAGS,
+                      {(const void*)&qp_solve_kernel<P, 32>, (const void*)&qp_solve_kernel<P, 64>}, Slab<P>::BYTES};
 }
 constexpr int F_ALL = QPPVM_FLAG_FRICTION_CONES | QPPVM_FLAG_TORQUE_LIMITS;
 const ShapeEntry g_shapes[] = {
@@ -42,6 +44,8 @@ struct qppvm_handle {
     qppvm_desc desc;
     qppvm_layout L;
     const ShapeEntry* shape;
+    const void* kernel;
+    int team;                              // threads per problem (= CTA size)
     int sm_count, ctas_per_sm;
     unsigned long long* counters;          // HOST_STREAMS + 2 device counters
     cudaStream_t streams[HOST_STREAMS];
@@ -84,7 +88,7 @@ int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t 
     Params prm{h->desc.eps_regularisation * QPPVM_QPOASES_EPS_REG, h->desc.n_reg_steps, h->desc.max_iter};
     long long b = batch;
     void* args[] = {(void*)&rec, (void*)&out, (void*)&diag, (void*)&b, (void*)&prm, (void*)&counter};
-    CU(h, cudaLaunchKernel(h->shape->kernel, dim3(grid), dim3(32), args, (size_t)h->shape->slab_bytes, st));
+    CU(h, cudaLaunchKernel(h->kernel, dim3(grid), dim3(h->team), args, (size_t)h->shape->slab_bytes, st));
     h->launches += 1;
     return QPPVM_OK;
 }
@@ -198,10 +202,15 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
     cudaDeviceProp prop;
     CUC(cudaGetDeviceProperties(&prop, d->device));
     h->sm_count = prop.multiProcessorCount;
-    CUC(cudaFuncSetAttribute(sh->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh->slab_bytes));
-    CUC(cudaFuncSetAttribute(sh->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // threads per problem: 64 by default (twice the warps per SM at the same shared-memory footprint);
+    // QPPVM_TEAM=32|64 overrides for tuning.
+    h->team = 64;
+    if (const char* e = getenv("QPPVM_TEAM")) { const int t = atoi(e); if (t == 32 || t == 64) h->team = t; }
+    h->kernel = sh->kernel[h->team == 64 ? 1 : 0];
+    CUC(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh->slab_bytes));
+    CUC(cudaFuncSetAttribute(h->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int occ = 0;
-    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh->kernel, 32, (size_t)sh->slab_bytes));
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->kernel, h->team, (size_t)sh->slab_bytes));
     if (occ < 1) { fail(nullptr, QPPVM_ERR_CUDA, "kernel does not fit on an SM (%d B smem)", sh->slab_bytes); delete h; return QPPVM_ERR_CUDA; }
     h->ctas_per_sm = occ;
     CUC(cudaMalloc(&h->counters, sizeof(unsigned long long) * (HOST_STREAMS + 2)));
@@ -243,6 +252,8 @@ int qppvm_solve_batch_diag(qppvm_handle* h, const double* rec, void* out, double
 {
     if (!h) return QPPVM_ERR_ARG;
     if (batch < 0 || (batch > 0 && (!rec || !out))) return fail(h, QPPVM_ERR_ARG, "bad batch arguments");
+    if (((uintptr_t)rec & 15) || ((uintptr_t)out & 7) || ((uintptr_t)diag & 7))
+        return fail(h, QPPVM_ERR_ARG, "records must be 16-byte aligned (TMA bulk copy), outputs 8-byte aligned");
     CU(h, cudaSetDevice(h->desc.device));
     return launch(h, rec, out, diag, batch, (cudaStream_t)stream, h->counters + HOST_STREAMS);
 }
