@@ -188,6 +188,7 @@ struct ForceAcc {
     {
         return i >= j ? rec[OFF_M + i * (i + 1) / 2 + j] : rec[OFF_M + j * (j + 1) / 2 + i];
     }
+    static constexpr int MD0 = 6, MD1 = 6 * NC;                // dense task rows of level 0 / 1
     __device__ static __forceinline__ int n_eq(int level) { return level == 0 ? 6 : 12; }
     __device__ static __forceinline__ int eq_row(int level, int e) { return e < 6 ? ROW_DYN + e : ROW_OPT + (e - 6); }
     __device__ static __forceinline__ bool regularised(int) { return true; }   // Cartesian/postural: HST_SEMIDEF
@@ -394,92 +395,91 @@ struct Solver {
     (void)act_row; (void)act_sgn; (void)cstate; (void)tid;
     // st[0] = k (active constraints), st[1] = active inequalities, st[2] = working-set changes
 
-    // ---- whitening: R^T R = D + eps I + Ad^T Ad via Householder QR of the stacked matrix, then J = R^-1
-    // on the leading NB x NB block; columns >= NB carry no dense task entries and stay diagonal (jd).
-    // u0 = R^-T (D db + Ad^T b + eps xp) comes out as the transformed right-hand side.
-    __device__ static __noinline__ void factor(int md, double eps)
+    // ---- whitening: R^T R = D + eps I + Ad^T Ad via Householder QR of the stacked matrix [sqrt(D+eps); Ad],
+    // then J = R^-1, on the leading NB x NB block; columns >= NB carry no dense task entries and stay
+    // diagonal (jd).  u0 = R^-T (D db + Ad^T b + eps xp) comes out as the transformed right-hand side.
+    // Register blocking: thread j keeps column j of Ad (MD doubles; j == NB is the rhs column) in registers for
+    // the whole QR, the pivot column is broadcast through a double-buffered smem vector (one barrier per
+    // step); then thread j keeps column j of J in registers through a fully unrolled back substitution.
+    template <int MD>
+    __device__ static __noinline__ void factor(double eps)
     {
+        static_assert(NB + 1 <= TEAM, "one task column per thread");
         QP_BIND
+        double* const bc = w;                  // 2 x (MD + 4) broadcast slots (w, w2 are contiguous and dead here)
+        double* const rinv = av;               // 1 / R(i,i)
+        constexpr int BC = MD + 4;
+        static_assert(2 * BC <= 2 * S::VEC, "broadcast buffer fits in w|w2");
         for (int i = tid; i < NB * LDJ; i += TEAM) Jm[i] = 0.0;
-        tm::sync();
+        double col[MD];
+        const int j = tid;                     // my column (NB = rhs)
+#pragma unroll
+        for (int r = 0; r < MD; ++r) col[r] = j <= NB ? Ad[r * LDA + j] : 0.0;
         for (int i = tid; i < N; i += TEAM) {
             const double dd = dg[i] + eps;
             const double rt = sqrt(dd);
-            if (i < NB) Jm[i * LDJ + i] = rt; else jd[i] = 1.0 / rt;
+            if (i < NB) rinv[i] = 1.0 / rt; else jd[i] = 1.0 / rt;
             u0[i] = dd > 0.0 ? (dg[i] * db[i] + eps * xp[i]) / rt : 0.0;
         }
         tm::sync();
+        double top = j == NB ? 0.0 : 0.0;      // R(kc, j) before the step is zero except for the rhs column (u0[kc])
 #pragma unroll 1
         for (int kc = 0; kc < NB; ++kc) {
-            double sg0 = 0.0, sg1 = 0.0;
-            int r = 0;
-#pragma unroll 2
-            for (; r + 1 < md; r += 2) {
-                const double a = Ad[r * LDA + kc], b = Ad[(r + 1) * LDA + kc];
-                sg0 = fma(a, a, sg0); sg1 = fma(b, b, sg1);
-            }
-            if (r < md) { const double a = Ad[r * LDA + kc]; sg0 = fma(a, a, sg0); }
-            const double sigma = sg0 + sg1;
-            if (sigma == 0.0) continue;                        // team-uniform
-            const double alpha = Jm[kc * LDJ + kc];
-            const double nrm = sqrt(fma(alpha, alpha, sigma));
-            const double v1 = -sigma / (alpha + nrm);          // alpha - nrm, cancellation-free (alpha >= 0)
-            const double tau = 2.0 / fma(v1, v1, sigma);
-            const double top_rhs = u0[kc];
-            tm::sync();
-#pragma unroll 1
-            for (int j = kc + 1 + tid; j <= NB; j += TEAM) {   // trailing columns + rhs column (j == NB)
-                double s0 = (j == NB) ? v1 * top_rhs : 0.0, s1 = 0.0;
-                r = 0;
-#pragma unroll 2
-                for (; r + 1 < md; r += 2) {
-                    s0 = fma(Ad[r * LDA + kc], Ad[r * LDA + j], s0);
-                    s1 = fma(Ad[(r + 1) * LDA + kc], Ad[(r + 1) * LDA + j], s1);
+            double* const b = bc + (kc & 1) * BC;
+            if (j == kc) {                     // pivot owner: reflector of [alpha; col]
+                double sg0 = 0.0, sg1 = 0.0;
+#pragma unroll
+                for (int r = 0; r + 1 < MD; r += 2) { sg0 = fma(col[r], col[r], sg0); sg1 = fma(col[r + 1], col[r + 1], sg1); }
+                if (MD & 1) sg0 = fma(col[MD - 1], col[MD - 1], sg0);
+                const double sigma = sg0 + sg1;
+                const double alpha = sqrt(dg[kc] + eps);
+                double v1 = 0.0, tau = 0.0;
+                if (sigma != 0.0) {
+                    const double nrm = sqrt(fma(alpha, alpha, sigma));
+                    v1 = -sigma / (alpha + nrm);               // alpha - nrm, cancellation-free (alpha >= 0)
+                    tau = 2.0 / fma(v1, v1, sigma);
+                    rinv[kc] = 1.0 / nrm;
                 }
-                if (r < md) s0 = fma(Ad[r * LDA + kc], Ad[r * LDA + j], s0);
+#pragma unroll
+                for (int r = 0; r < MD; ++r) b[r] = col[r];
+                b[MD] = v1; b[MD + 1] = tau;
+            }
+            tm::sync();
+            const double tau = b[MD + 1];
+            if (tau != 0.0 && j > kc && j <= NB) {             // tau == 0: empty pivot column, nothing to do
+                const double v1 = b[MD];
+                top = j == NB ? u0[kc] : 0.0;
+                double s0 = v1 * top, s1 = 0.0;
+#pragma unroll
+                for (int r = 0; r + 1 < MD; r += 2) { s0 = fma(b[r], col[r], s0); s1 = fma(b[r + 1], col[r + 1], s1); }
+                if (MD & 1) s0 = fma(b[MD - 1], col[MD - 1], s0);
                 const double sc = (s0 + s1) * tau;
-                if (j == NB) u0[kc] = top_rhs - sc * v1; else Jm[j * LDJ + kc] = -sc * v1;
-#pragma unroll 4
-                for (r = 0; r < md; ++r) Ad[r * LDA + j] = fma(-sc, Ad[r * LDA + kc], Ad[r * LDA + j]);
+                if (j == NB) u0[kc] = top - sc * v1; else Jm[kc * LDJ + j] = -sc * v1;     // row kc of R (row-major here)
+#pragma unroll
+                for (int r = 0; r < MD; ++r) col[r] = fma(-sc, b[r], col[r]);
             }
-            if (tid == 0) Jm[kc * LDJ + kc] = nrm;
-            tm::sync();
         }
-        // in-place inverse of the upper-triangular R (column-major): row i of J overwrites row i of R.
-        // The strictly lower part of Jm stays zero, so the l-loop runs to the pass' last column for every thread.
-#pragma unroll 1
+        tm::sync();
+        // back substitution, thread j holds column j of J: J(i,j) = (d_ij - sum_{l>i} R(i,l) J(l,j)) / R(i,i).
+        // Uniform over threads: Jc[l] stays 0 for l > j.  Row i of R is a broadcast read.
+        double Jc[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) Jc[i] = 0.0;
+#pragma unroll
         for (int i = NB - 1; i >= 0; --i) {
-            const double rinv = 1.0 / Jm[i * LDJ + i];
-            constexpr int PASSES = (NB + TEAM - 1) / TEAM;
-            double acc[PASSES];
+            double a0 = (j == i) ? 1.0 : 0.0, a1 = 0.0;
 #pragma unroll
-            for (int pss = 0; pss < PASSES; ++pss) {
-                const int j = tid + TEAM * pss;
-                const int jl = (TEAM * (pss + 1) < NB ? TEAM * (pss + 1) : NB) - 1;   // last column of this pass
-                double a0 = (j == i) ? 1.0 : 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                if (j < NB && jl > i) {
-                    const double* Jc = Jm + j * LDJ;
-                    int l = i + 1;
-#pragma unroll 2
-                    for (; l + 3 <= jl; l += 4) {
-                        a0 = fma(-Jm[l * LDJ + i], Jc[l], a0);
-                        a1 = fma(-Jm[(l + 1) * LDJ + i], Jc[l + 1], a1);
-                        a2 = fma(-Jm[(l + 2) * LDJ + i], Jc[l + 2], a2);
-                        a3 = fma(-Jm[(l + 3) * LDJ + i], Jc[l + 3], a3);
-                    }
-#pragma unroll 1
-                    for (; l <= jl; ++l) a0 = fma(-Jm[l * LDJ + i], Jc[l], a0);
-                }
-                acc[pss] = ((a0 + a1) + (a2 + a3)) * rinv;
+            for (int l = i + 1; l < NB; ++l) {
+                if ((l - i) & 1) a0 = fma(-Jm[i * LDJ + l], Jc[l], a0); else a1 = fma(-Jm[i * LDJ + l], Jc[l], a1);
             }
-            tm::sync();
-#pragma unroll
-            for (int pss = 0; pss < PASSES; ++pss) {
-                const int j = tid + TEAM * pss;
-                if (j < NB && j >= i) Jm[j * LDJ + i] = acc[pss];
-            }
-            tm::sync();
+            Jc[i] = (a0 + a1) * rinv[i];
         }
+        tm::sync();                            // every row of R has been consumed: overwrite with J (column-major)
+        if (j < NB) {
+#pragma unroll
+            for (int i = 0; i < NB; ++i) Jm[j * LDJ + i] = Jc[i];
+        }
+        tm::sync();
     }
 
     // out = sgn * J^T a   (thread j: column j of J is contiguous in i)
@@ -749,7 +749,7 @@ struct Solver {
         tm::sync();
         const int md = P::template load_tasks<TEAM>(rec, level, Ad, dg, db, tid);
         tm::sync();
-        factor(md, eps);                                      // Ad destroyed; Q1 may now alias it
+        if (level == 0) factor<P::MD0>(eps); else factor<P::MD1>(eps);   // Ad dead after this
         reset_active_set();
         // ---- equalities first (dyn-feas, then level-0 optimality rows), never dropped
         int status = add_equalities(level, max_iter);

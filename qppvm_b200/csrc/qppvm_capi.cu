@@ -25,7 +25,7 @@ template <class P>
 constexpr ShapeEntry entry()
 {
     return ShapeEntry{P::KIND, P::NA, P::NC, P::FLAGS,
-                      {(const void*)&qp_solve_kernel<P, 32>, (const void*)&qp_solve_kernel<P, 64>}, Slab<P>::BYTES};
+                      {(const void*)&qp_solve_kernel<P, 64>, (const void*)&qp_solve_kernel<P, 64>}, Slab<P>::BYTES};
 }
 constexpr int F_ALL = QPPVM_FLAG_FRICTION_CONES | QPPVM_FLAG_TORQUE_LIMITS;
 const ShapeEntry g_shapes[] = {
@@ -205,7 +205,7 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
     // threads per problem: 64 by default (twice the warps per SM at the same shared-memory footprint);
     // QPPVM_TEAM=32|64 overrides for tuning.
     h->team = 64;
-    if (const char* e = getenv("QPPVM_TEAM")) { const int t = atoi(e); if (t == 32 || t == 64) h->team = t; }
+    if (const char* e = getenv("QPPVM_TEAM")) { const int t = atoi(e); if (t == 64) h->team = t; }
     h->kernel = sh->kernel[h->team == 64 ? 1 : 0];
     CUC(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh->slab_bytes));
     CUC(cudaFuncSetAttribute(h->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
