@@ -455,12 +455,14 @@ static int gi_solve(int n, const double* Jfac, double* x, int nc, const double* 
         } else {
             double worst = 0;
             for (int i = 0; i < nc; ++i) {
-                if (act[i] != 0 || lA[i] == uA[i]) continue;
+                /* the side opposite to an active one is still checked: an empty box (lA > uA) must surface as
+                 * infeasible instead of being masked by the active side */
+                if (act[i] == 2 || act[i] == 3 || lA[i] == uA[i]) continue;
                 double cx = 0;
                 for (int j = 0; j < n; ++j) cx += C[i * n + j] * x[j];
                 double tol = 1e-9 * fmax(1.0, fabs(cx));
-                if (lA[i] > -0.5 * QPPVM_INFTY && cx - lA[i] < -tol && cx - lA[i] < worst) { worst = cx - lA[i]; p = i; psgn = 1; }
-                if (uA[i] < 0.5 * QPPVM_INFTY && uA[i] - cx < -tol && uA[i] - cx < worst) { worst = uA[i] - cx; p = i; psgn = -1; }
+                if (act[i] != 1 && lA[i] > -0.5 * QPPVM_INFTY && cx - lA[i] < -tol && cx - lA[i] < worst) { worst = cx - lA[i]; p = i; psgn = 1; }
+                if (act[i] != -1 && uA[i] < 0.5 * QPPVM_INFTY && uA[i] - cx < -tol && uA[i] - cx < worst) { worst = uA[i] - cx; p = i; psgn = -1; }
             }
             if (p < 0) break;              /* primal feasible: optimal */
             sp = worst;
@@ -498,7 +500,14 @@ static int gi_solve(int n, const double* Jfac, double* x, int nc, const double* 
                 if (-sp <= 1e-8 * fmax(1.0, fabs(lA[p]))) { act[p] = 2; break; }
                 status = QPPVM_STATUS_INFEASIBLE; goto done;
             }
-            if (t1 == INFINITY && t2 == INFINITY) { status = QPPVM_STATUS_INFEASIBLE; goto done; }
+            if (t1 == INFINITY && t2 == INFINITY) {
+                /* dependent on the working set and nothing can leave: an implied inequality whose violation is
+                 * rounding noise (degenerate vertex: the optimality rows pin the previous level's optimum onto
+                 * its active bounds) counts as satisfied within tolerance and is not scanned again */
+                double bnd = psgn > 0 ? lA[p] : uA[p];
+                if (!peq && -sp <= 1e-6 * fmax(1.0, fabs(bnd))) { act[p] = 3; break; }
+                status = QPPVM_STATUS_INFEASIBLE; goto done;
+            }
             double t = (t1 < t2) ? t1 : t2;
             /* ---- step 4: move */
             for (int i = 0; i < k; ++i) g.u[i] -= t * r[i];

@@ -32,6 +32,7 @@ namespace qppvm {
 constexpr int KMAX = 32;          // max simultaneously active constraints (eq + ineq)
 constexpr int LDQ = KMAX + 1;     // row stride of Q1 (odd: conflict-free 64-bit column walks)
 constexpr int LDR = KMAX + 1;     // column stride of RN
+constexpr int STATUS_IMPLIED = 100;   // internal: violated row is implied by the working set within tolerance
 
 struct Params {
     double eps_reg;     // eps_regularisation * 2.221e-13
@@ -189,6 +190,8 @@ struct ForceAcc {
         return i >= j ? rec[OFF_M + i * (i + 1) / 2 + j] : rec[OFF_M + j * (j + 1) / 2 + i];
     }
     static constexpr int MD0 = 6, MD1 = 6 * NC;                // dense task rows of level 0 / 1
+    static constexpr int EXTRA = 0;                            // policy scratch in the slab (doubles)
+    template <int TEAM> __device__ static __forceinline__ bool prepare(const double*, double*, int) { return true; }
     __device__ static __forceinline__ int n_eq(int level) { return level == 0 ? 6 : 12; }
     __device__ static __forceinline__ int eq_row(int level, int e) { return e < 6 ? ROW_DYN + e : ROW_OPT + (e - 6); }
     __device__ static __forceinline__ bool regularised(int) { return true; }   // Cartesian/postural: HST_SEMIDEF
@@ -197,7 +200,7 @@ struct ForceAcc {
     // weights / targets into dg, db (postural rows are unit rows -> kept as a diagonal).
     // Level 0: waist Cartesian (ForceAcc.cpp:118-122).  Level 1: postural + contact Cartesian (:131).
     template <int TEAM>
-    __device__ static int load_tasks(const double* rec, int level, double* Ad, double* dg, double* db, int tid)
+    __device__ static int load_tasks(const double* rec, const double*, int level, double* Ad, double* dg, double* db, int tid)
     {
         constexpr int LDA = NB + 1;
         const int md = level == 0 ? 6 : 6 * NC;
@@ -218,7 +221,7 @@ struct ForceAcc {
     // Coefficients of constraint row `row` as a dense n-vector (smem av) + its two-sided bounds.
     // eopt: A0 x0* (level-1 optimality right-hand sides).
     template <int TEAM>
-    __device__ static void build_row(const double* rec, int row, const double* eopt,
+    __device__ static void build_row(const double* rec, const double*, int row, const double* eopt,
                                      double* av, double& lo, double& hi, int tid)
     {
         if (row < ROW_BOX) {                                   // DynamicFeasibility (base rows of M qdd + h - J^T w)
@@ -307,7 +310,7 @@ struct ForceAcc {
 
     // Level-0 task value A0 x0* (6 numbers) -> eopt.
     template <int TEAM>
-    __device__ static void task0_value(const double* rec, const double* x, double* eopt, int tid)
+    __device__ static void task0_value(const double* rec, const double*, const double* x, double* eopt, int tid)
     {
         if (tid < QPPVM_M0) {
             double s0 = 0.0, s1 = 0.0;
@@ -337,6 +340,169 @@ struct ForceAcc {
 };
 
 // ------------------------------------------------------------------------------------------
+// Problem policy: Torque stack  x = tau (fixed base)   (ref:src/QPPVMPlugin.cpp:112-188, 201-259)
+//   level 0: (ee_right + ee_left): A = (J M^-1)[rows 0..2], b = A J^T F, F = K e + D edot   
+//   level 1: joint impedance:       A = M^-1, b = M^-1 (K (q_ref - q) + D (-qdot))          
+//   bounds : tau_min_const - h <= tau <= tau_max_const - h                                  (cpp:203-205)
+//   output : tau_d = tau_qp + h, and tau_qp = 0 when the solve fails                        (cpp:246-256)
+// Policy scratch (ext): M^-1 (N x LDM, symmetric) | A0 (6 x N, kept for the level-1 optimality rows) | T (N x LDM).
+// ------------------------------------------------------------------------------------------
+template <int NA_>
+struct Torque {
+    static constexpr int KIND = QPPVM_KIND_TORQUE;
+    static constexpr int NA = NA_, NC = 2, FLAGS = 0;
+    static constexpr int NV = NA, N = NA, NB = NA;
+    static constexpr int MD0 = 6, MD1 = NA, MD_MAX = NA;
+    static constexpr int ROW_BOX = 0, ROW_OPT = NA, NROWS = NA + QPPVM_M0;
+    static constexpr int NI = NA;
+    static constexpr int OFF_J = 0, OFF_M = 12 * NA, OFF_H = OFF_M + NA * (NA + 1) / 2, OFF_FEE = OFF_H + NA;
+    static constexpr int OFF_TAUJ = OFF_FEE + 12, OFF_TAULIM = OFF_TAUJ + NA;
+    static constexpr int REC_UNPADDED = OFF_TAULIM + 2 * NA;
+    static constexpr int REC = REC_UNPADDED + (REC_UNPADDED & 1);
+    static constexpr int LDM = NA | 1;
+    static constexpr int O_A0 = NA * LDM, O_T = O_A0 + 6 * NA;
+    static constexpr int EXTRA = O_T + NA * LDM + ((O_T + NA * LDM) & 1);
+
+    __device__ static __forceinline__ int n_eq(int level) { return level == 0 ? 0 : 6; }
+    __device__ static __forceinline__ int eq_row(int, int e) { return ROW_OPT + e; }
+    // CartesianImpedanceCtrl: HST_SEMIDEF -> regularised; JointImpedanceCtrl: HST_POSDEF -> not
+    __device__ static __forceinline__ bool regularised(int level) { return level == 0; }
+
+    // M^-1 by Cholesky (M = L L^T), T = L^-1, M^-1 = T^T T; then A0 = (J_t M^-1)[0..2] for both hands.
+    // Element (i, j) of a square buffer X lives at X[j * LDM + i].
+    template <int TEAM>
+    __device__ static bool prepare(const double* rec, double* ext, int tid)
+    {
+        double* const L = ext;
+        double* const A0 = ext + O_A0;
+        double* const T = ext + O_T;
+        for (int t = tid; t < NA * NA; t += TEAM) {
+            const int i = t / NA, j = t - i * NA;
+            L[j * LDM + i] = i >= j ? rec[OFF_M + i * (i + 1) / 2 + j] : 0.0;
+            T[j * LDM + i] = 0.0;
+        }
+        Team<TEAM>::sync();
+        bool ok = true;
+#pragma unroll 1
+        for (int k = 0; k < NA; ++k) {                       // right-looking Cholesky, thread i owns row i
+            const double d = L[k * LDM + k];
+            if (!(d > 0.0)) ok = false;                      // team-uniform
+            const double inv = rsqrt(d);
+            Team<TEAM>::sync();
+            for (int i = k + tid; i < NA; i += TEAM) L[k * LDM + i] *= inv;       // column k (diagonal: d / sqrt(d))
+            Team<TEAM>::sync();
+            for (int i = k + 1 + tid; i < NA; i += TEAM) {
+                const double lik = L[k * LDM + i];
+#pragma unroll 2
+                for (int j = k + 1; j <= i; ++j) L[j * LDM + i] = fma(-lik, L[k * LDM + j], L[j * LDM + i]);
+            }
+            Team<TEAM>::sync();
+        }
+        if (!ok) return false;
+        for (int c = tid; c < NA; c += TEAM) {               // T = L^-1 (lower), thread c owns column c
+            T[c * LDM + c] = 1.0 / L[c * LDM + c];
+#pragma unroll 1
+            for (int i = c + 1; i < NA; ++i) {
+                double sacc = 0.0;
+#pragma unroll 2
+                for (int l = c; l < i; ++l) sacc = fma(L[l * LDM + i], T[c * LDM + l], sacc);
+                T[c * LDM + i] = -sacc / L[i * LDM + i];
+            }
+        }
+        Team<TEAM>::sync();
+        for (int t = tid; t < NA * NA; t += TEAM) {          // M^-1 = T^T T over the dead L
+            const int i = t / NA, j = t - i * NA;
+            double sacc = 0.0;
+#pragma unroll 2
+            for (int k = (i > j ? i : j); k < NA; ++k) sacc = fma(T[i * LDM + k], T[j * LDM + k], sacc);
+            L[j * LDM + i] = sacc;
+        }
+        Team<TEAM>::sync();
+        for (int t = tid; t < 6 * NA; t += TEAM) {           // A0 row (3 t + r) = J_t[r] M^-1
+            const int row = t / NA, j = t - row * NA;
+            const double* Jr = rec + OFF_J + ((row / 3) * 6 + (row % 3)) * NA;
+            double sacc = 0.0;
+#pragma unroll 2
+            for (int k = 0; k < NA; ++k) sacc = fma(Jr[k], L[j * LDM + k], sacc);
+            A0[row * NA + j] = sacc;
+        }
+        Team<TEAM>::sync();
+        return true;
+    }
+
+    template <int TEAM>
+    __device__ static int load_tasks(const double* rec, const double* ext, int level, double* Ad, double* dg, double* db, int tid)
+    {
+        constexpr int LDA = NB + 1;
+        const double* Minv = ext;
+        const double* A0 = ext + O_A0;
+        for (int j = tid; j < N; j += TEAM) { dg[j] = 0.0; db[j] = 0.0; }
+        if (level == 0) {
+            for (int t = tid; t < 6 * NA; t += TEAM) { const int r = t / NA, j = t - r * NA; Ad[r * LDA + j] = A0[t]; }
+            if (tid < 6) {                                   // b = A (J^T F)  (full 6-row J and 6-vector F)
+                const int tsk = tid / 3;
+                const double* J = rec + OFF_J + tsk * 6 * NA;
+                const double* F = rec + OFF_FEE + 6 * tsk;
+                double sacc = 0.0;
+                for (int j = 0; j < NA; ++j) {
+                    double jtf = 0.0;
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) jtf = fma(J[r * NA + j], F[r], jtf);
+                    sacc = fma(A0[tid * NA + j], jtf, sacc);
+                }
+                Ad[tid * LDA + NB] = sacc;
+            }
+            return 6;
+        }
+        for (int t = tid; t < NA * NA; t += TEAM) { const int r = t / NA, j = t - r * NA; Ad[r * LDA + j] = Minv[j * LDM + r]; }
+        for (int r = tid; r < NA; r += TEAM) {               // b = M^-1 tau_j
+            double sacc = 0.0;
+#pragma unroll 2
+            for (int j = 0; j < NA; ++j) sacc = fma(Minv[j * LDM + r], rec[OFF_TAUJ + j], sacc);
+            Ad[r * LDA + NB] = sacc;
+        }
+        return NA;
+    }
+
+    template <int TEAM>
+    __device__ static void build_row(const double* rec, const double* ext, int row, const double* eopt,
+                                     double* av, double& lo, double& hi, int tid)
+    {
+        if (row < ROW_OPT) {                                 // TorqueLimits: simple bound on tau_row
+            for (int j = tid; j < N; j += TEAM) av[j] = j == row ? 1.0 : 0.0;
+            const double h = rec[OFF_H + row];
+            lo = rec[OFF_TAULIM + row] - h; hi = rec[OFF_TAULIM + NA + row] - h;
+        } else {                                             // optimality rows: A0 x = A0 x0*
+            const int r = row - ROW_OPT;
+            for (int j = tid; j < N; j += TEAM) av[j] = ext[O_A0 + r * NA + j];
+            lo = hi = eopt[r];
+        }
+    }
+    __device__ static void eval_slot(const double* rec, int q, const double* x,
+                                     int& row, double& val, double& lo, double& hi)
+    {
+        row = q; val = x[q];
+        const double h = rec[OFF_H + q];
+        lo = rec[OFF_TAULIM + q] - h; hi = rec[OFF_TAULIM + NA + q] - h;
+    }
+    template <int TEAM>
+    __device__ static void task0_value(const double*, const double* ext, const double* x, double* eopt, int tid)
+    {
+        if (tid < QPPVM_M0) {
+            double sacc = 0.0;
+            for (int j = 0; j < NA; ++j) sacc = fma(ext[O_A0 + tid * NA + j], x[j], sacc);
+            eopt[tid] = sacc;
+        }
+    }
+    // tau_d = tau_qp + h ; tau_qp = 0 on failure (ref:src/QPPVMPlugin.cpp:246-256)
+    template <int TEAM>
+    __device__ static void recover(const double* rec, const double* x, double* tau_out, bool ok, int tid)
+    {
+        for (int a = tid; a < NA; a += TEAM) tau_out[a] = (ok ? x[a] : 0.0) + rec[OFF_H + a];
+    }
+};
+
+// ------------------------------------------------------------------------------------------
 // Shared-memory slab of one team
 // ------------------------------------------------------------------------------------------
 template <class P>
@@ -357,7 +523,8 @@ struct Slab {
     static constexpr int O_MBAR = O_SMALL + 3 * KMAX + 8 + 16;
     static constexpr int O_STATE = O_MBAR + 1;        // ints: k, n_act_ineq, iters, - | act_row[KMAX] | act_sgn[KMAX]
     static constexpr int O_CSTATE = O_STATE + 2 + KMAX;   // bytes
-    static constexpr int DOUBLES = O_CSTATE + ((P::NROWS + 15) & ~15) / 8;
+    static constexpr int O_EXT = O_CSTATE + ((P::NROWS + 15) & ~15) / 8;   // policy scratch
+    static constexpr int DOUBLES = O_EXT + P::EXTRA;
     static constexpr int BYTES = DOUBLES * 8;
 };
 
@@ -375,7 +542,7 @@ struct Solver {
     QP_SM(w2, S::O_VEC + 4 * S::VEC) QP_SM(av, S::O_VEC + 5 * S::VEC) QP_SM(dg, S::O_VEC + 6 * S::VEC)
     QP_SM(db, S::O_VEC + 7 * S::VEC) QP_SM(xp, S::O_VEC + 8 * S::VEC) QP_SM(jd, S::O_VEC + 9 * S::VEC)
     QP_SM(d1, S::O_SMALL) QP_SM(rr, S::O_SMALL + KMAX) QP_SM(lam, S::O_SMALL + 2 * KMAX)
-    QP_SM(eopt, S::O_SMALL + 3 * KMAX) QP_SM(red, S::O_SMALL + 3 * KMAX + 8)
+    QP_SM(eopt, S::O_SMALL + 3 * KMAX) QP_SM(red, S::O_SMALL + 3 * KMAX + 8) QP_SM(ext, S::O_EXT)
 #undef QP_SM
     __device__ static __forceinline__ uint64_t* mbar_() { return reinterpret_cast<uint64_t*>(g_smem) + S::O_MBAR; }
     __device__ static __forceinline__ int* state_() { return reinterpret_cast<int*>(reinterpret_cast<double*>(g_smem) + S::O_STATE); }
@@ -388,6 +555,7 @@ struct Solver {
     double* const w = w_(); double* const w2 = w2_(); double* const av = av_(); double* const dg = dg_();   \
     double* const db = db_(); double* const xp = xp_(); double* const jd = jd_(); double* const d1 = d1_(); \
     double* const rr = rr_(); double* const lam = lam_(); double* const eopt = eopt_(); double* const red = red_(); \
+    double* const ext = ext_(); (void)ext;                                                                 \
     int* const st = state_(); int* const act_row = st + 4; int* const act_sgn = st + 4 + KMAX;             \
     unsigned char* const cstate = cstate_(); const int tid = threadIdx.x;                                  \
     (void)rec; (void)Jm; (void)Q1; (void)Ad; (void)RN; (void)u0; (void)u; (void)x; (void)w; (void)w2; (void)av; \
@@ -406,10 +574,10 @@ struct Solver {
     {
         static_assert(NB + 1 <= TEAM, "one task column per thread");
         QP_BIND
-        double* const bc = w;                  // 2 x (MD + 4) broadcast slots (w, w2 are contiguous and dead here)
-        double* const rinv = av;               // 1 / R(i,i)
+        double* const bc = w;                  // 2 x (MD + 4) broadcast slots (w, w2, av are contiguous and dead here)
+        double* const rinv = jd;               // 1 / R(i,i) for i < NB (jd proper only uses i >= NB)
         constexpr int BC = MD + 4;
-        static_assert(2 * BC <= 2 * S::VEC, "broadcast buffer fits in w|w2");
+        static_assert(2 * BC <= 3 * S::VEC, "broadcast buffer fits in w|w2|av");
         for (int i = tid; i < NB * LDJ; i += TEAM) Jm[i] = 0.0;
         double col[MD];
         const int j = tid;                     // my column (NB = rhs)
@@ -652,13 +820,22 @@ struct Solver {
                 if (ci != 0x7fffffff) { t1 = cand; l = ci; }
             }
             int fail = -1;
-            if (dependent && l < 0)
-                fail = (is_eq && -sp <= 1e-8 * fmax(1.0, bound_abs)) ? QPPVM_STATUS_OK   // redundant, consistent
-                                                                       : QPPVM_STATUS_INFEASIBLE;
+            if (dependent && l < 0) {
+                // linearly dependent on the working set and nothing can leave: a redundant equality, or an implied
+                // inequality whose violation is rounding noise (degenerate vertex of the level-1 feasible set, where
+                // the optimality rows pin the level-0 optimum onto its active bounds) -> satisfied within tolerance.
+                if (is_eq) fail = (-sp <= 1e-8 * fmax(1.0, bound_abs)) ? QPPVM_STATUS_OK : QPPVM_STATUS_INFEASIBLE;
+                else fail = (-sp <= 1e-6 * fmax(1.0, bound_abs)) ? STATUS_IMPLIED : QPPVM_STATUS_INFEASIBLE;
+            }
             const double t2 = dependent ? 1e300 : -sp / nrm2;
             const double t = t1 < t2 ? t1 : t2;
             if (fail < 0 && full && t == t2) fail = QPPVM_STATUS_NUMERIC;   // active-set capacity exhausted
-            if (fail >= 0) { tm::sync(); if (tid == 0) st[2] = iters; tm::sync(); return fail; }
+            if (fail >= 0) {
+                tm::sync();
+                if (tid == 0) { st[2] = iters; red[13] = sp; red[14] = bound_abs; red[15] = (double)k; }   // diagnostics
+                tm::sync();
+                return fail;
+            }
             if (nai > 0) { if (tid < k) lam[tid] -= t * rr[tid]; }
             up += t;
             if (!dependent) {
@@ -673,7 +850,7 @@ struct Solver {
                 if (tid < k) RN[k * LDR + tid] = d1[tid];
                 if (tid == 0) {
                     RN[k * LDR + k] = nr; lam[k] = up; act_row[k] = row; act_sgn[k] = is_eq ? 2 * sgn : sgn;
-                    cstate[row] = 1;
+                    cstate[row] = (is_eq || sgn > 0) ? 1 : 3;
                     st[0] = k + 1; st[1] = nai + (is_eq ? 0 : 1); st[2] = iters;
                 }
                 tm::sync();
@@ -693,11 +870,14 @@ struct Solver {
         for (int q = tid; q < P::NI; q += TEAM) {
             int r; double val, lo, hi;
             P::eval_slot(rec, q, x, r, val, lo, hi);
-            if (!cstate[r]) {
+            // cstate: 0 inactive, 1 active at lA, 3 active at uA, 2 implied / weakly active.  The side opposite to an
+            // active one is still checked: an empty box (lA > uA) must surface as infeasible, not be masked.
+            const int cs = cstate[r];
+            if (cs != 2) {
                 const double tol = 1e-9 * fmax(1.0, fabs(val));
                 const double sl = val - lo, su = hi - val;
-                if (lo > -0.5 * QPPVM_INFTY && sl < -tol && sl < worst) { worst = sl; widx = r; wsgn = 1; wb = fabs(lo); }
-                if (hi < 0.5 * QPPVM_INFTY && su < -tol && su < worst) { worst = su; widx = r; wsgn = -1; wb = fabs(hi); }
+                if (cs != 1 && lo > -0.5 * QPPVM_INFTY && sl < -tol && sl < worst) { worst = sl; widx = r; wsgn = 1; wb = fabs(lo); }
+                if (cs != 3 && hi < 0.5 * QPPVM_INFTY && su < -tol && su < worst) { worst = su; widx = r; wsgn = -1; wb = fabs(hi); }
             }
         }
         double v = worst; int idx = widx;
@@ -717,7 +897,7 @@ struct Solver {
         for (int e = 0; e < neq && status == QPPVM_STATUS_OK; ++e) {
             const int row = P::eq_row(level, e);
             double lo, hi;
-            P::template build_row<TEAM>(rec, row, eopt, av, lo, hi, tid);
+            P::template build_row<TEAM>(rec, ext, row, eopt, av, lo, hi, tid);
             tm::sync();
             whiten(av, 1.0, w);
             const double s = dot(w, u) - lo;
@@ -747,7 +927,7 @@ struct Solver {
         for (int i = tid; i < N; i += TEAM) xp[i] = 0.0;
         if (tid == 0) st[2] = 0;
         tm::sync();
-        const int md = P::template load_tasks<TEAM>(rec, level, Ad, dg, db, tid);
+        const int md = P::template load_tasks<TEAM>(rec, ext, level, Ad, dg, db, tid);
         tm::sync();
         if (level == 0) factor<P::MD0>(eps); else factor<P::MD1>(eps);   // Ad dead after this
         reset_active_set();
@@ -764,10 +944,15 @@ struct Solver {
                 const double sp = red[8], babs = red[10];
                 const int sgn = (int)red[9];
                 double lo, hi;
-                P::template build_row<TEAM>(rec, row, eopt, av, lo, hi, tid);
+                P::template build_row<TEAM>(rec, ext, row, eopt, av, lo, hi, tid);
                 tm::sync();
                 whiten(av, (double)sgn, w);
                 status = add_constraint(row, sgn, false, sp, babs, max_iter);
+                if (status == STATUS_IMPLIED) {               // not added; excluded from further scans
+                    if (tid == 0) cstate[row] = 2;
+                    tm::sync();
+                    status = QPPVM_STATUS_OK;
+                }
                 if (status != QPPVM_STATUS_OK) break;
             }
             if (status != QPPVM_STATUS_OK || step >= steps) break;
@@ -834,7 +1019,7 @@ struct Solver {
             const int row = act_row[c];
             const int sg = act_sgn[c];
             double lo, hi;
-            P::template build_row<TEAM>(rec, row, eopt, av, lo, hi, tid);
+            P::template build_row<TEAM>(rec, ext, row, eopt, av, lo, hi, tid);
             tm::sync();
             const bool iseq = !(sg & 1);                       // sign = +-1, equalities +-2
             const double y = (sg > 0 ? 1.0 : -1.0) * rr[c];
@@ -858,13 +1043,13 @@ struct Solver {
                 int r; double val, lo, hi;
                 P::eval_slot(rec, q, x, r, val, lo, hi);
                 cm = fmax(cm, fabs(val));
-                if (!cstate[r]) viol = fmax(viol, fmax(lo - val, val - hi));
+                if (!(cstate[r] & 1)) viol = fmax(viol, fmax(lo - val, val - hi));
             }
             rprim = fmax(rprim, tm::max(viol, red)); cxmax = fmax(cxmax, tm::max(cm, red));
         }
         // task part (reload the dense task rows over the dead Q1 region); (A x)_r -> w2, b_r -> av
         tm::sync();
-        P::template load_tasks<TEAM>(rec, level, Ad, dg, db, tid);
+        P::template load_tasks<TEAM>(rec, ext, level, Ad, dg, db, tid);
         tm::sync();
         for (int r = tid; r < md; r += TEAM) {
             double s0 = 0.0, s1 = 0.0;
@@ -929,11 +1114,13 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
         mbar_wait(SV::mbar_(), phase); phase ^= 1;
         float kkt0 = __int_as_float(0x7f800000), kkt1 = kkt0;
         int it0 = 0, it1 = 0;
-        int status = SV::solve_level(0, prm.eps_reg, prm.n_reg_steps, prm.max_iter, dg ? dg + N : nullptr);
+        int status = P::template prepare<TEAM>(SV::rec_(), SV::ext_(), tid) ? QPPVM_STATUS_OK : QPPVM_STATUS_NUMERIC;
+        if (status == QPPVM_STATUS_OK)
+            status = SV::solve_level(0, prm.eps_reg, prm.n_reg_steps, prm.max_iter, dg ? dg + N : nullptr);
         it0 = SV::state_()[2];
         if (status == QPPVM_STATUS_OK) kkt0 = (float)SV::red_()[12];
         if (status == QPPVM_STATUS_OK) {
-            P::template task0_value<TEAM>(SV::rec_(), SV::x_(), SV::eopt_(), tid);
+            P::template task0_value<TEAM>(SV::rec_(), SV::ext_(), SV::x_(), SV::eopt_(), tid);
             Team<TEAM>::sync();
             if (dg) {
                 for (int i = tid; i < N; i += TEAM) dg[i] = SV::x_()[i];
@@ -945,6 +1132,7 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
             if (status == QPPVM_STATUS_OK) kkt1 = (float)SV::red_()[12];
         }
         const bool ok = status == QPPVM_STATUS_OK;
+        if (dg && !ok && tid < 3) dg[N + 2 * P::NROWS + 3 + tid] = SV::red_()[13 + tid];   // slack, |bound|, k at failure
         for (int i = tid; i < N; i += TEAM) xo[i] = ok ? SV::x_()[i] : 0.0;
         P::template recover<TEAM>(SV::rec_(), SV::x_(), xo + N, ok, tid);
         // trailer: status, iters, 128-bit active mask of level 1, kkt[2]
@@ -954,7 +1142,7 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
             if (ok)
                 for (int b = 0; b < 32; ++b) {
                     const int r = tid * 32 + b;
-                    if (r < P::NROWS && SV::cstate_()[r] == 1) mask |= 1u << b;
+                    if (r < P::NROWS && (SV::cstate_()[r] & 1)) mask |= 1u << b;
                 }
             tr[2 + tid] = mask;
         }

@@ -33,6 +33,8 @@ const ShapeEntry g_shapes[] = {
     entry<ForceAcc<29, 2, F_ALL>>(),   // configs [0], [4]: + cones + torque limits
     entry<ForceAcc<33, 4, F_ALL>>(),   // configs [2], [3]: WALK-MAN-like, 4 contacts
     entry<ForceAcc<33, 4, 0>>(),
+    entry<Torque<29>>(),               // literal QPPVMPlugin stack (fixed base), 29 and 39 joints
+    entry<Torque<39>>(),
 };
 constexpr int N_SHAPES = sizeof(g_shapes) / sizeof(g_shapes[0]);
 

@@ -35,3 +35,25 @@ def compare(L, gpu: dict, ora: dict, gdiag: dict | None = None, odiag: dict | No
             sign_ok = np.sign(gdiag["y1"][ok]) * sa_o == np.sign(odiag["y1"][ok]) * sa_o
             r["strong_sign_equal"] = float(sign_ok.all(axis=1).mean())
     return r
+
+
+def mask_bits(mask_words, n_rows):
+    """(B,4) uint32 -> (B,n_rows) bool."""
+    bits = np.unpackbits(np.ascontiguousarray(mask_words).view(np.uint8), axis=1, bitorder="little")
+    return bits[:, :n_rows].astype(bool)
+
+
+def mask_differences_are_degenerate(desc, L, recs, x, x0, mask_a, mask_b, rel_tol=1e-5):
+    """Active sets may differ only on rows that are TIGHT at the solution (weakly active / implied rows at a
+    degenerate vertex, where the multipliers are not unique).  Returns (n_differing_problems, all_tight)."""
+    from tests.assemble_np import level_matrices
+    a, b = mask_bits(mask_a, L.n_rows), mask_bits(mask_b, L.n_rows)
+    diff = np.nonzero((a != b).any(axis=1))[0]
+    ok = True
+    for i in diff:
+        _, _, C, lA, uA, _ = level_matrices(desc, recs[i], 1, x0[i])
+        cx = C @ x[i]
+        rows = np.nonzero(a[i] != b[i])[0]
+        slack = np.minimum(np.abs(cx[rows] - lA[rows]), np.abs(uA[rows] - cx[rows]))
+        ok &= bool((slack <= rel_tol * np.maximum(1.0, np.abs(cx[rows]))).all())
+    return len(diff), ok

@@ -8,8 +8,8 @@ import numpy as np
 import pytest
 
 from qppvm_b200 import gen
-from qppvm_b200.layout import CONFIGS, layout
-from tests.helpers import PRIMAL_TOL, KKT_TOL, compare, rel_inf
+from qppvm_b200.layout import CONFIGS, Desc, KIND_TORQUE, layout
+from tests.helpers import PRIMAL_TOL, KKT_TOL, compare, rel_inf, mask_differences_are_degenerate
 
 pytestmark = pytest.mark.gpu
 
@@ -47,6 +47,33 @@ def test_parity_vs_oracle(torch_mod, oracle_mod, ci, batch):
     assert r["mask_equal"] == 1.0 and r["strong_active_equal"] == 1.0 and r["strong_sign_equal"] == 1.0
     assert r["eopt"] <= PRIMAL_TOL
     assert rel_inf(gdg["x0"], odg["x0"]).max() <= 1e-4      # level-0 point: eps-defined directions
+
+
+@pytest.mark.parametrize("n_a", (29, 39))
+def test_parity_torque_kind(torch_mod, oracle_mod, n_a):
+    """The literal QPPVMPlugin stack (x = tau, fixed base): ref:src/QPPVMPlugin.cpp:112-188, 201-259."""
+    from qppvm_b200 import api
+    desc = Desc(kind=KIND_TORQUE, n_a=n_a, n_contacts=2, flags=0, eps_regularisation=1.0)
+    L = layout(desc)
+    recs = gen.generate(desc, 384, 4242)
+    oo, od = oracle_mod.solve_batch(desc, recs, diag=True)
+    o, odg = oracle_mod.split_out(desc, oo), api.split_diag(L, od)
+    g, gdg = _solve_gpu(torch_mod, desc, recs)
+    r = compare(L, g, o, gdg, odg)
+    assert r["status_equal"] and r["both_ok"] == 384
+    assert r["primal"] <= PRIMAL_TOL and r["tau"] <= PRIMAL_TOL          # tau = tau_qp + h
+    assert r["kkt_gpu"] <= KKT_TOL and r["eopt"] <= PRIMAL_TOL
+    # level 1 sits on a degenerate vertex whenever level 0 is bound-limited (its optimality rows pin the
+    # level-0 optimum onto the active bounds): the primal point is unique, the multipliers are not.  Active sets
+    # must agree except on rows that are tight at the solution.
+    ndiff, tight = mask_differences_are_degenerate(desc, L, recs, g["x"], gdg["x0"], g["active"], o["active"])
+    assert tight and ndiff <= 0.05 * 384
+    # failure convention: tau_qp = 0 -> command = h (QPPVMPlugin.cpp:246-256)
+    bad = recs[:4].copy()
+    bad[:, L.off_taulim:L.off_taulim + n_a] = 5.0; bad[:, L.off_taulim + n_a:L.off_taulim + 2 * n_a] = -5.0
+    gb, _ = _solve_gpu(torch_mod, desc, bad, diag=False)
+    assert (gb["status"] != 0).all() and (gb["x"] == 0).all()
+    np.testing.assert_array_equal(gb["tau"], bad[:, L.off_h:L.off_h + n_a])
 
 
 def test_empty_single_and_ragged_batches(torch_mod, oracle_mod):

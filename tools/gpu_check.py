@@ -12,8 +12,9 @@ from oracle import oracle  # noqa: E402
 from tests.helpers import compare  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-for ci in (1, 0, 2):
-    d = layout.CONFIGS[ci]["desc"]
+TORQUE = layout.Desc(kind=layout.KIND_TORQUE, n_a=29, n_contacts=2, flags=0, eps_regularisation=1.0)
+for ci in (1, 0, 2, 7):
+    d = TORQUE if ci == 7 else layout.CONFIGS[ci]["desc"]
     L = layout.layout(d)
     recs = gen.generate(d, B, gen.config_seed(ci))
     t = time.time(); oo, od = oracle.solve_batch(d, recs, diag=True); t_or = time.time() - t
@@ -31,7 +32,7 @@ for ci in (1, 0, 2):
     for i in bad[:5]:
         print("  bad", i, "status", g["status"][i], o["status"][i], "it", g["iters0"][i], g["iters1"][i], "kkt", g["kkt"][i], o["kkt"][i],
               "dx", np.abs(g["x"][i] - o["x"][i]).max(), "dx0", np.abs(gd["x0"][i] - odg["x0"][i]).max(),
-              "mask", g["active"][i], o["active"][i])
+              "mask", g["active"][i], o["active"][i], "fail(slack,|bound|,k)", gd["eopt"][i][3:6])
     # timing
     for nb in (4096, 32768):
         big = rd.repeat((nb + B - 1) // B, 1)[:nb].contiguous()
