@@ -1,0 +1,54 @@
+/*
+ * Drop-in for the reference's QPPVM RT plugin (ref:include/QPPVM_RT_plugin/QPPVMPlugin.h:37-106): same class name,
+ * namespace, virtual surface and registration symbol; the OpenSoT torque stack + QPOases_sot members are replaced
+ * by one qppvm_handle of kind QPPVM_KIND_TORQUE (include/qppvm_b200.h).
+ */
+#ifndef __QPPVM_PLUGIN_H__
+#define __QPPVM_PLUGIN_H__
+
+#include <XCM/XBotControlPlugin.h>
+#include <string>
+#include <vector>
+#include "../../include/qppvm_b200.h"
+
+namespace demo {
+
+class QPPVMPlugin : public XBot::XBotControlPlugin {
+public:
+    QPPVMPlugin();
+    virtual ~QPPVMPlugin();
+    virtual bool init_control_plugin(XBot::Handle::Ptr handle);
+    virtual void on_start(double time);
+    virtual void control_loop(double time, double period);
+    virtual bool close();
+
+    const std::vector<double>& last_record() const { return _record; }
+    const std::vector<double>& last_output() const { return _out; }
+    int last_status() const { return _status; }
+
+private:
+    double _start_time = 0.0;
+    bool _set_ref = false;
+    void syncFromMotorSide(XBot::RobotInterface::Ptr robot, XBot::ModelInterface::Ptr model);
+    void sense();
+    void QPPVMControl(const double time);
+    void impedance_wrench(const std::string& link, const Eigen::Affine3d& ref, const Eigen::MatrixXd& J, double* F6) const;
+
+    XBot::JointIdMap _jidmap;
+    XBot::RobotInterface::Ptr _robot;
+    XBot::ModelInterface::Ptr _model;
+    XBot::MatLogger::Ptr _matlogger;
+    Eigen::VectorXd _q, _dq, _q_ref, _q_home, _k, _d, _tau_d, _h;
+    Eigen::VectorXd _tau_max, _tau_min, _tau_max_const, _tau_min_const;
+    Eigen::Affine3d _ref_left, _ref_right, _start_pose;
+    Eigen::MatrixXd _Jtmp, _M;
+    double _Kc = 700.0, _Dc = 70.0, _Kj = 5.0, _Dj = 2.0;     // ref:src/QPPVMPlugin.cpp:105-106, 136-137, 148-149
+
+    qppvm_handle* _solver = nullptr;
+    qppvm_layout _L;
+    std::vector<double> _record, _out;
+    int _status = 0;
+};
+
+}  // namespace demo
+#endif
