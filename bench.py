@@ -231,6 +231,24 @@ def main():
     e2e_ok = float(((ge["status"] == 0) & (ge["kkt"].max(axis=1) <= 1e-6)).mean())
     e2e_val = world * e2e_steps * batch * e2e_ok / t_e2e.item()
 
+    # ---- N > 1: the same shards fed from rank 0 over NCCL (scatter records, gather outputs), device to device
+    sg = None
+    if world > 1:
+        from qppvm_b200 import shard
+        root_recs = torch.cat([d_recs[0]] * world) if rank == 0 else None      # world * batch records on the root GPU
+        sg_steps = max(3, min(args.steps, 50))
+        for i in range(2):
+            shard.solve_sharded(lambda r: solver.solve_batch(r)[0], root_recs, world * batch, L.rec_doubles, dev)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(sg_steps):
+            shard.solve_sharded(lambda r: solver.solve_batch(r)[0], root_recs, world * batch, L.rec_doubles, dev)
+        torch.cuda.synchronize(dev)
+        t_sg = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_sg, op=dist.ReduceOp.MAX)
+        sg = {"value": world * batch * sg_steps / t_sg.item(), "unit": "solves/s", "steps": sg_steps,
+              "what": "NCCL scatter of records from rank 0 + solve + gather of outputs to rank 0 (root-egress bound)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -271,6 +289,8 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_fp64": roofline_fp64,
             "converged_frac": frac.item(), "kkt_max": kkt_max}
+    if sg:
+        line["scatter_gather"] = sg
 
     if world == 1 and not args.no_latency:
         # single-tick latency (the metric's second half): config [4] shape, host in / host out per tick

@@ -2,7 +2,7 @@
 // library exactly as the loader would, builds it through its registration symbol, and drives
 // init_control_plugin / on_start / control_loop / close against FAKE XBot::Handle / RobotInterface / ModelInterface
 // objects that serve a recorded sequence of synthetic states.  What the plugin commanded is written to a file that
-// tests/test_plugin.py compares with the oracle.
+// tests/test_plugin.py compares with the CPU checker.
 //
 //   plugin_test <plugin.so> <factory symbol> <states.bin> <out.bin> <n_ticks> <n_v> <floating 0|1> link...
 #include <XCM/XBotControlPlugin.h>
