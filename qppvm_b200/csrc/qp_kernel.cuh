@@ -29,9 +29,14 @@
 
 namespace qppvm {
 
-constexpr int KMAX = 32;          // max simultaneously active constraints (eq + ineq)
-constexpr int LDQ = KMAX + 1;     // row stride of Q1 (odd: conflict-free 64-bit column walks)
-constexpr int LDR = KMAX + 1;     // column stride of RN
+// Active-set capacity KMAX (eq + ineq, <= 32 so one warp lane per active row), per problem shape.
+__host__ __device__ constexpr int kmax_for(int n_eq, int n_ineq, int n)
+{
+    int k = n_eq + n_ineq;
+    if (k > n) k = n;               // at most n linearly independent rows
+    if (k > 32) k = 32;
+    return k < 8 ? 8 : k;
+}
 constexpr int STATUS_IMPLIED = 100;   // internal: violated row is implied by the working set within tolerance
 
 struct Params {
@@ -191,6 +196,7 @@ struct ForceAcc {
     }
     static constexpr int MD0 = 6, MD1 = 6 * NC;                // dense task rows of level 0 / 1
     static constexpr int EXTRA = 0;                            // policy scratch in the slab (doubles)
+    static constexpr int KMAX = kmax_for(12, 3 * NC + (CONES ? 5 * NC : 0) + (TLIM ? NA : 0), N);
     template <int TEAM> __device__ static __forceinline__ bool prepare(const double*, double*, int) { return true; }
     __device__ static __forceinline__ int n_eq(int level) { return level == 0 ? 6 : 12; }
     __device__ static __forceinline__ int eq_row(int level, int e) { return e < 6 ? ROW_DYN + e : ROW_OPT + (e - 6); }
@@ -360,6 +366,7 @@ struct Torque {
     static constexpr int REC_UNPADDED = OFF_TAULIM + 2 * NA;
     static constexpr int REC = REC_UNPADDED + (REC_UNPADDED & 1);
     static constexpr int LDM = NA | 1;
+    static constexpr int KMAX = kmax_for(6, NA, N);
     static constexpr int O_A0 = NA * LDM, O_T = O_A0 + 6 * NA;
     static constexpr int EXTRA = O_T + NA * LDM + ((O_T + NA * LDM) & 1);
 
@@ -508,6 +515,10 @@ struct Torque {
 template <class P>
 struct Slab {
     static constexpr int N = P::N, NB = P::NB;
+    static constexpr int KMAX = P::KMAX;
+    static constexpr int LDQ = KMAX | 1;              // row stride of Q1 (odd: conflict-free 64-bit column walks)
+    static constexpr int LDR = KMAX | 1;              // column stride of RN
+    static constexpr int KP = (KMAX + 1) & ~1;        // even padding of the small per-constraint vectors
     static constexpr int LDJ = NB | 1;                // odd column stride
     static constexpr int LDA = NB + 1;
     static constexpr int VEC = (N + 3) & ~3;
@@ -518,11 +529,11 @@ struct Slab {
     static constexpr int O_Q = O_J + SZ_J;            // Q1, aliased by Ad during the factorisation
     static constexpr int SZ_Q = (N * LDQ > P::MD_MAX * LDA) ? N * LDQ : P::MD_MAX * LDA;
     static constexpr int O_R = O_Q + SZ_Q;
-    static constexpr int O_VEC = O_R + KMAX * LDR;    // u0 u x w w2 av dg db xp jd
-    static constexpr int O_SMALL = O_VEC + 10 * VEC;  // d1 rr lam (KMAX each) | eopt 8 | red 16
-    static constexpr int O_MBAR = O_SMALL + 3 * KMAX + 8 + 16;
-    static constexpr int O_STATE = O_MBAR + 1;        // ints: k, n_act_ineq, iters, - | act_row[KMAX] | act_sgn[KMAX]
-    static constexpr int O_CSTATE = O_STATE + 2 + KMAX;   // bytes
+    static constexpr int O_VEC = O_R + KMAX * LDR + ((KMAX * LDR) & 1);    // u0 u x w w2 av dg db xp jd
+    static constexpr int O_SMALL = O_VEC + 10 * VEC;  // d1 rr lam (KP each) | eopt 8 | red 16
+    static constexpr int O_MBAR = O_SMALL + 3 * KP + 8 + 16;
+    static constexpr int O_STATE = O_MBAR + 1;        // ints: k, n_act_ineq, iters, - | act_row[KP] | act_sgn[KP]
+    static constexpr int O_CSTATE = O_STATE + 2 + KP;     // bytes
     static constexpr int O_EXT = O_CSTATE + ((P::NROWS + 15) & ~15) / 8;   // policy scratch
     static constexpr int DOUBLES = O_EXT + P::EXTRA;
     static constexpr int BYTES = DOUBLES * 8;
@@ -535,14 +546,15 @@ template <class P, int TEAM>
 struct Solver {
     using S = Slab<P>;
     static constexpr int N = P::N, NB = P::NB, LDJ = S::LDJ, LDA = S::LDA;
+    static constexpr int KMAX = S::KMAX, LDQ = S::LDQ, LDR = S::LDR, KP = S::KP;
 
 #define QP_SM(name, off) __device__ static __forceinline__ double* name##_() { return reinterpret_cast<double*>(g_smem) + (off); }
     QP_SM(rec, S::O_REC) QP_SM(Jm, S::O_J) QP_SM(Q1, S::O_Q) QP_SM(Ad, S::O_Q) QP_SM(RN, S::O_R)
     QP_SM(u0, S::O_VEC) QP_SM(u, S::O_VEC + S::VEC) QP_SM(x, S::O_VEC + 2 * S::VEC) QP_SM(w, S::O_VEC + 3 * S::VEC)
     QP_SM(w2, S::O_VEC + 4 * S::VEC) QP_SM(av, S::O_VEC + 5 * S::VEC) QP_SM(dg, S::O_VEC + 6 * S::VEC)
     QP_SM(db, S::O_VEC + 7 * S::VEC) QP_SM(xp, S::O_VEC + 8 * S::VEC) QP_SM(jd, S::O_VEC + 9 * S::VEC)
-    QP_SM(d1, S::O_SMALL) QP_SM(rr, S::O_SMALL + KMAX) QP_SM(lam, S::O_SMALL + 2 * KMAX)
-    QP_SM(eopt, S::O_SMALL + 3 * KMAX) QP_SM(red, S::O_SMALL + 3 * KMAX + 8) QP_SM(ext, S::O_EXT)
+    QP_SM(d1, S::O_SMALL) QP_SM(rr, S::O_SMALL + KP) QP_SM(lam, S::O_SMALL + 2 * KP)
+    QP_SM(eopt, S::O_SMALL + 3 * KP) QP_SM(red, S::O_SMALL + 3 * KP + 8) QP_SM(ext, S::O_EXT)
 #undef QP_SM
     __device__ static __forceinline__ uint64_t* mbar_() { return reinterpret_cast<uint64_t*>(g_smem) + S::O_MBAR; }
     __device__ static __forceinline__ int* state_() { return reinterpret_cast<int*>(reinterpret_cast<double*>(g_smem) + S::O_STATE); }
@@ -556,7 +568,7 @@ struct Solver {
     double* const db = db_(); double* const xp = xp_(); double* const jd = jd_(); double* const d1 = d1_(); \
     double* const rr = rr_(); double* const lam = lam_(); double* const eopt = eopt_(); double* const red = red_(); \
     double* const ext = ext_(); (void)ext;                                                                 \
-    int* const st = state_(); int* const act_row = st + 4; int* const act_sgn = st + 4 + KMAX;             \
+    int* const st = state_(); int* const act_row = st + 4; int* const act_sgn = st + 4 + KP;               \
     unsigned char* const cstate = cstate_(); const int tid = threadIdx.x;                                  \
     (void)rec; (void)Jm; (void)Q1; (void)Ad; (void)RN; (void)u0; (void)u; (void)x; (void)w; (void)w2; (void)av; \
     (void)dg; (void)db; (void)xp; (void)jd; (void)d1; (void)rr; (void)lam; (void)eopt; (void)red; (void)st; \
