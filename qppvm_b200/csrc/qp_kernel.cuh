@@ -525,7 +525,10 @@ struct Slab {
     // offsets in doubles from the slab base
     static constexpr int O_REC = 0;                   // staged record (16-B aligned: first in the slab)
     static constexpr int O_J = O_REC + P::REC;
-    static constexpr int SZ_J = NB * LDJ + (NB * LDJ & 1);
+    // J (and R before it) packed upper-triangular: NB (NB + 1) / 2 doubles.  R is row-major packed
+    // (R(i,l) at i NB - i (i - 1) / 2 + (l - i)), J column-major packed (J(i,j) at j (j + 1) / 2 + i): triangular
+    // numbers are a permutation mod 16, so a half-warp walking 16 consecutive columns is bank-conflict free.
+    static constexpr int SZ_J = NB * (NB + 1) / 2 + ((NB * (NB + 1) / 2) & 1);
     static constexpr int O_Q = O_J + SZ_J;            // Q1, aliased by Ad during the factorisation
     static constexpr int SZ_Q = (N * LDQ > P::MD_MAX * LDA) ? N * LDQ : P::MD_MAX * LDA;
     static constexpr int O_R = O_Q + SZ_Q;
@@ -590,7 +593,7 @@ struct Solver {
         double* const rinv = jd;               // 1 / R(i,i) for i < NB (jd proper only uses i >= NB)
         constexpr int BC = MD + 4;
         static_assert(2 * BC <= 3 * S::VEC, "broadcast buffer fits in w|w2|av");
-        for (int i = tid; i < NB * LDJ; i += TEAM) Jm[i] = 0.0;
+        for (int i = tid; i < NB * (NB + 1) / 2; i += TEAM) Jm[i] = 0.0;
         double col[MD];
         const int j = tid;                     // my column (NB = rhs)
 #pragma unroll
@@ -634,7 +637,7 @@ struct Solver {
                 for (int r = 0; r + 1 < MD; r += 2) { s0 = fma(b[r], col[r], s0); s1 = fma(b[r + 1], col[r + 1], s1); }
                 if (MD & 1) s0 = fma(b[MD - 1], col[MD - 1], s0);
                 const double sc = (s0 + s1) * tau;
-                if (j == NB) u0[kc] = top - sc * v1; else Jm[kc * LDJ + j] = -sc * v1;     // row kc of R (row-major here)
+                if (j == NB) u0[kc] = top - sc * v1; else Jm[kc * NB - kc * (kc - 1) / 2 + (j - kc)] = -sc * v1;   // R(kc, j)
 #pragma unroll
                 for (int r = 0; r < MD; ++r) col[r] = fma(-sc, b[r], col[r]);
             }
@@ -650,14 +653,15 @@ struct Solver {
             double a0 = (j == i) ? 1.0 : 0.0, a1 = 0.0;
 #pragma unroll
             for (int l = i + 1; l < NB; ++l) {
-                if ((l - i) & 1) a0 = fma(-Jm[i * LDJ + l], Jc[l], a0); else a1 = fma(-Jm[i * LDJ + l], Jc[l], a1);
+                const double ril = Jm[i * NB - i * (i - 1) / 2 + (l - i)];
+                if ((l - i) & 1) a0 = fma(-ril, Jc[l], a0); else a1 = fma(-ril, Jc[l], a1);
             }
             Jc[i] = (a0 + a1) * rinv[i];
         }
-        tm::sync();                            // every row of R has been consumed: overwrite with J (column-major)
+        tm::sync();                            // every row of R has been consumed: overwrite with J (packed columns)
         if (j < NB) {
 #pragma unroll
-            for (int i = 0; i < NB; ++i) Jm[j * LDJ + i] = Jc[i];
+            for (int i = 0; i < NB; ++i) if (i <= j) Jm[j * (j + 1) / 2 + i] = Jc[i];
         }
         tm::sync();
     }
@@ -670,7 +674,7 @@ struct Solver {
             double r;
             if (j < NB) {
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                const double* col = Jm + j * LDJ;
+                const double* col = Jm + j * (j + 1) / 2;
                 int i = 0;
 #pragma unroll 2
                 for (; i + 3 <= j; i += 4) {
@@ -694,13 +698,14 @@ struct Solver {
             if (i < NB) {
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
                 int j = i;
+                const double* Ji = Jm + i;
 #pragma unroll 2
                 for (; j + 3 < NB; j += 4) {
-                    s0 = fma(Jm[j * LDJ + i], uu[j], s0); s1 = fma(Jm[(j + 1) * LDJ + i], uu[j + 1], s1);
-                    s2 = fma(Jm[(j + 2) * LDJ + i], uu[j + 2], s2); s3 = fma(Jm[(j + 3) * LDJ + i], uu[j + 3], s3);
+                    s0 = fma(Ji[j * (j + 1) / 2], uu[j], s0); s1 = fma(Ji[(j + 1) * (j + 2) / 2], uu[j + 1], s1);
+                    s2 = fma(Ji[(j + 2) * (j + 3) / 2], uu[j + 2], s2); s3 = fma(Ji[(j + 3) * (j + 4) / 2], uu[j + 3], s3);
                 }
 #pragma unroll 1
-                for (; j < NB; ++j) s0 = fma(Jm[j * LDJ + i], uu[j], s0);
+                for (; j < NB; ++j) s0 = fma(Ji[j * (j + 1) / 2], uu[j], s0);
                 r = (s0 + s1) + (s2 + s3);
             } else r = jd[i] * uu[i];
             xx[i] = r;
