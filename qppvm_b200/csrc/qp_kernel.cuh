@@ -946,7 +946,15 @@ struct Solver {
         tm::sync();
         const int md = P::template load_tasks<TEAM>(rec, ext, level, Ad, dg, db, tid);
         tm::sync();
-        if (level == 0) factor<P::MD0>(eps); else factor<P::MD1>(eps);   // Ad dead after this
+        // One instantiation serves both levels when level 1 is at most twice as tall (level 0 is padded with zero
+        // rows): the kernel is instruction-fetch sensitive, a second copy of the unrolled inversion costs more
+        // than a few FMAs on zeros.
+        constexpr int MDF0 = (P::MD1 <= 2 * P::MD0) ? P::MD1 : P::MD0;
+        if (MDF0 != P::MD0 && level == 0) {
+            for (int t = tid; t < (MDF0 - P::MD0) * LDA; t += TEAM) Ad[P::MD0 * LDA + t] = 0.0;
+            tm::sync();
+        }
+        if (level == 0) factor<MDF0>(eps); else factor<P::MD1>(eps);   // Ad dead after this
         reset_active_set();
         // ---- equalities first (dyn-feas, then level-0 optimality rows), never dropped
         int status = add_equalities(level, max_iter);
