@@ -38,7 +38,7 @@ const ShapeEntry g_shapes[] = {
 };
 constexpr int N_SHAPES = sizeof(g_shapes) / sizeof(g_shapes[0]);
 
-constexpr int HOST_STREAMS = 3;
+constexpr int HOST_STREAMS = 4;
 
 }  // namespace
 
@@ -216,7 +216,9 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
     if (occ < 1) { fail(nullptr, QPPVM_ERR_CUDA, "kernel does not fit on an SM (%d B smem)", sh->slab_bytes); delete h; return QPPVM_ERR_CUDA; }
     h->ctas_per_sm = occ;
     CUC(cudaMalloc(&h->counters, sizeof(unsigned long long) * (HOST_STREAMS + 2)));
-    h->chunk = 2048;
+    // host path: records per pipelined chunk (H2D of chunk i+1 overlaps the solve of chunk i); QPPVM_CHUNK overrides
+    h->chunk = 1024;
+    if (const char* e = getenv("QPPVM_CHUNK")) { const long c = atol(e); if (c >= 64 && c <= (1 << 20)) h->chunk = c; }
     for (int i = 0; i < HOST_STREAMS; ++i) {
         CUC(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
         CUC(cudaMalloc(&h->d_rec[i], sizeof(double) * L.rec_doubles * h->chunk));
