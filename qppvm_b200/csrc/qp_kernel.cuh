@@ -1122,10 +1122,13 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     uint32_t phase = 0;
+    unsigned long long next_static = blockIdx.x;               // counter == nullptr: static round-robin schedule
 #pragma unroll 1
     for (;;) {
         if (tid == 0) {
-            const unsigned long long i = atomicAdd(counter, 1ull);
+            unsigned long long i;
+            if (counter) i = atomicAdd(counter, 1ull);
+            else { i = next_static; next_static += gridDim.x; }
             s_idx = i;
             if ((long long)i < batch)                          // one TMA bulk copy stages the whole record
                 bulk_load(SV::rec_(), recs + i * (size_t)P::REC, (uint32_t)(P::REC * sizeof(double)), SV::mbar_());

@@ -83,7 +83,7 @@ int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t 
            cudaStream_t st, unsigned long long* counter)
 {
     if (batch <= 0) return QPPVM_OK;
-    CU(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    if (counter) CU(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     long long want = batch;                                   // one warp (= one CTA) per problem in flight
     long long cap = (long long)h->sm_count * h->ctas_per_sm;
     int grid = (int)(want < cap ? want : cap);
@@ -291,11 +291,12 @@ int qppvm_solve_one(qppvm_handle* h, const double* rec, void* out)
     if (!h || !rec || !out) return h ? fail(h, QPPVM_ERR_ARG, "null argument") : QPPVM_ERR_ARG;
     CU(h, cudaSetDevice(h->desc.device));
     const size_t rb = sizeof(double) * h->L.rec_doubles, ob = (size_t)h->L.out_bytes;
+    // Latency mode: one launch, nothing else on the stream.  The record sits in pinned host memory that the GPU
+    // addresses directly (UVA): the kernel's TMA bulk copy pulls it across PCIe and the outputs are stored straight
+    // back into pinned host memory, so there is no memcpy / memset node before or after the kernel.
     memcpy(h->h_one_rec, rec, rb);
-    CU(h, cudaMemcpyAsync(h->d_one_rec, h->h_one_rec, rb, cudaMemcpyHostToDevice, h->one_stream));
-    int rc = launch(h, h->d_one_rec, h->d_one_out, nullptr, 1, h->one_stream, h->counters + HOST_STREAMS + 1);
+    int rc = launch(h, h->h_one_rec, h->h_one_out, nullptr, 1, h->one_stream, nullptr);
     if (rc) return rc;
-    CU(h, cudaMemcpyAsync(h->h_one_out, h->d_one_out, ob, cudaMemcpyDeviceToHost, h->one_stream));
     CU(h, cudaStreamSynchronize(h->one_stream));
     memcpy(out, h->h_one_out, ob);
     return QPPVM_OK;
