@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "whole-body QP solves/sec (2-level cascade, KKT<=1e-6)"
-N_BUF = 4     # distinct input batches rotated so the inputs (4 x 45 MB at config 1) exceed the 126 MB L2
+N_BUF = 4     # default; main() sizes it so that the rotated inputs exceed the 126 MB L2 (4 x 45 MB at config 1)
 # SURVEY.md 8(d) minimum-work FP64 model (FLOP per solve)
 F_ALG = {(29, 2): 182e3, (33, 4): 335e3}
 
@@ -91,11 +91,12 @@ def cpu_reference(desc, recs, target_s, mode):
     """Times the oracle (restated active-set path, not the qpOASES binary) on a bounded sample."""
     from oracle import oracle
     threads = oracle.num_threads()
+    if len(recs) < 2048:                                   # tiny workloads (single-tick configs): tile to a useful sample
+        recs = np.tile(recs, ((2048 + len(recs) - 1) // len(recs), 1))
     t0 = time.perf_counter(); oracle.solve_batch(desc, recs[:512], mode=mode); rate = 512 / (time.perf_counter() - t0)
     n = int(max(rate * target_s, 512))
-    reps = (n + len(recs) - 1) // len(recs)
     done, t0 = 0, time.perf_counter()
-    for r in range(reps):
+    while done < n and time.perf_counter() - t0 < 2.0 * target_s:     # bounded by work AND by wall clock
         m = min(len(recs), n - done)
         oracle.solve_batch(desc, recs[:m], mode=mode)
         done += m
@@ -120,10 +121,11 @@ def run_reference(args, desc, L, cfg_name, batch):
     from oracle import oracle
     recs = gen.generate(desc, batch, gen.config_seed(args.config))
     threads = oracle.num_threads()
-    t0 = time.perf_counter(); oracle.solve_batch(desc, recs[:256], mode=oracle.FACTOR_CHOLESKY)
-    rate = 256 / (time.perf_counter() - t0)
+    ncal = min(256, batch)
+    t0 = time.perf_counter(); oracle.solve_batch(desc, recs[:ncal], mode=oracle.FACTOR_CHOLESKY)
+    rate = ncal / (time.perf_counter() - t0)
     budget = 120.0 / max(1, args.steps + args.warmup)            # whole run ~<= 2 min
-    sample = int(max(32, min(batch, rate * budget)))
+    sample = int(max(1, min(batch, rate * budget)))
     for _ in range(args.warmup):
         oracle.solve_batch(desc, recs[:sample], mode=oracle.FACTOR_CHOLESKY)
     t0 = time.perf_counter()
@@ -153,6 +155,8 @@ def main():
     L = layout(desc)
     batch = args.batch or min(cfg["batch"], 65536)
     cfg_name = "configs[%d]: %s" % (args.config, cfg["name"])
+    global N_BUF
+    N_BUF = int(min(4, max(1, -(-int(1.3 * 126e6) // (batch * L.rec_doubles * 8)))))
     if args.impl == "reference":
         return run_reference(args, desc, L, cfg_name, batch)
 
@@ -260,11 +264,12 @@ def main():
     alg_bytes = L.algorithmic_bytes() * batch
     fp64_peak = solver.fp64_peak_tflops()
     f_alg = F_ALG.get((desc.n_a, desc.n_contacts))
-    traffic = None
+    traffic = None                                         # ncu dram bytes per launch, scaled to this launch's record count
     tpath = os.path.join(ROOT, "profiles", "traffic_config%d.json" % args.config)
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = int(tj["dram_bytes_per_launch"] / tj["records_per_launch"] * batch)
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": alg_bytes / launch_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -306,6 +311,15 @@ def main():
         line["single_tick"] = {"p50_us": float(np.percentile(lat, 50) * 1e6), "p99_us": float(np.percentile(lat, 99) * 1e6),
                                "max_us": float(lat.max() * 1e6), "ticks": 3000,
                                "workload": "configs[4]: one QP per tick through qppvm_solve_one (host in/out)"}
+        if not args.no_cpu_baseline:                       # the same ticks on one host core (restated active-set path)
+            from oracle import oracle
+            clat = np.empty(400)
+            for i in range(420):
+                t0 = time.perf_counter(); oracle.solve_batch(d4, r4[i % 256:i % 256 + 1], mode=oracle.FACTOR_CHOLESKY, threads=1)
+                if i >= 20:
+                    clat[i - 20] = time.perf_counter() - t0
+            line["single_tick"]["cpu_port_p50_us"] = float(np.percentile(clat, 50) * 1e6)
+            line["single_tick"]["cpu_port_p99_us"] = float(np.percentile(clat, 99) * 1e6)
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
         v, threads, n_done, dt = cpu_reference(desc, host_recs, 12.0, oracle.FACTOR_CHOLESKY)
