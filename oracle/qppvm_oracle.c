@@ -693,6 +693,7 @@ int oracle_solve_batch(const qppvm_desc* d, const double* recs, void* out, doubl
 #else
     threads = 1;
 #endif
+    if ((long long)threads > batch) threads = batch > 0 ? (int)batch : 1;   /* no idle threads (and their scratch) on tiny batches */
 #pragma omp parallel num_threads(threads)
     {
         scratch* s = scratch_new();
