@@ -166,14 +166,15 @@ class Robot:
             c = np.einsum("bij,j->bi", R[:, i], self.com[i])
             Jc = jac(i, p[:, i] + c)
             Jv, Jw = Jc[:, 0:3], Jc[:, 3:6]
-            Iw = np.einsum("bij,j,bkj->bik", R[:, i], self.inertia[i], R[:, i])
-            M += self.mass[i] * np.einsum("bki,bkj->bij", Jv, Jv)
-            M += np.einsum("bki,bkl,blj->bij", Jw, Iw, Jw)
+            Iw = (R[:, i] * self.inertia[i][None, None, :]) @ R[:, i].transpose(0, 2, 1)
+            JvT, JwT = Jv.transpose(0, 2, 1), Jw.transpose(0, 2, 1)
+            M += self.mass[i] * (JvT @ Jv)                     # batched BLAS (einsum was 75 % of the generator)
+            M += JwT @ (Iw @ Jw)
             ac = a[:, i] + np.cross(al[:, i], c) + np.cross(w[:, i], np.cross(w[:, i], c))
             # the base itself translates: its classical acceleration bias is zero (v0 is world-frame)
-            h += np.einsum("bki,bk->bi", Jv, self.mass[i] * (ac + gvec))
-            Iww = np.einsum("bij,bj->bi", Iw, w[:, i])
-            h += np.einsum("bki,bk->bi", Jw, np.einsum("bij,bj->bi", Iw, al[:, i]) + np.cross(w[:, i], Iww))
+            h += (JvT @ (self.mass[i] * (ac + gvec))[:, :, None])[:, :, 0]
+            Iww = (Iw @ w[:, i][:, :, None])[:, :, 0]
+            h += (JwT @ ((Iw @ al[:, i][:, :, None])[:, :, 0] + np.cross(w[:, i], Iww))[:, :, None])[:, :, 0]
         out = {"M": 0.5 * (M + M.transpose(0, 2, 1)), "h": h, "links": {}}
         for b in links:
             out["links"][b] = dict(J=jac(b, p[:, b]), Jdqd=np.concatenate([a[:, b], al[:, b]], axis=1),
