@@ -534,7 +534,7 @@ struct Slab {
     static constexpr int O_R = O_Q + SZ_Q;
     static constexpr int O_VEC = O_R + KMAX * LDR + ((KMAX * LDR) & 1);    // u0 u x w w2 av dg db xp jd
     static constexpr int O_SMALL = O_VEC + 10 * VEC;  // d1 rr lam (KP each) | eopt 8 | red 16
-    static constexpr int O_MBAR = O_SMALL + 3 * KP + 8 + 16;
+    static constexpr int O_MBAR = O_SMALL + 4 * KP + 8 + 16;   // d1 rr lam rdi
     static constexpr int O_STATE = O_MBAR + 1;        // ints: k, n_act_ineq, iters, - | act_row[KP] | act_sgn[KP]
     static constexpr int O_CSTATE = O_STATE + 2 + KP;     // bytes
     static constexpr int O_EXT = O_CSTATE + ((P::NROWS + 15) & ~15) / 8;   // policy scratch
@@ -556,8 +556,8 @@ struct Solver {
     QP_SM(u0, S::O_VEC) QP_SM(u, S::O_VEC + S::VEC) QP_SM(x, S::O_VEC + 2 * S::VEC) QP_SM(w, S::O_VEC + 3 * S::VEC)
     QP_SM(w2, S::O_VEC + 4 * S::VEC) QP_SM(av, S::O_VEC + 5 * S::VEC) QP_SM(dg, S::O_VEC + 6 * S::VEC)
     QP_SM(db, S::O_VEC + 7 * S::VEC) QP_SM(xp, S::O_VEC + 8 * S::VEC) QP_SM(jd, S::O_VEC + 9 * S::VEC)
-    QP_SM(d1, S::O_SMALL) QP_SM(rr, S::O_SMALL + KP) QP_SM(lam, S::O_SMALL + 2 * KP)
-    QP_SM(eopt, S::O_SMALL + 3 * KP) QP_SM(red, S::O_SMALL + 3 * KP + 8) QP_SM(ext, S::O_EXT)
+    QP_SM(d1, S::O_SMALL) QP_SM(rr, S::O_SMALL + KP) QP_SM(lam, S::O_SMALL + 2 * KP) QP_SM(rdi, S::O_SMALL + 3 * KP)
+    QP_SM(eopt, S::O_SMALL + 4 * KP) QP_SM(red, S::O_SMALL + 4 * KP + 8) QP_SM(ext, S::O_EXT)
 #undef QP_SM
     __device__ static __forceinline__ uint64_t* mbar_() { return reinterpret_cast<uint64_t*>(g_smem) + S::O_MBAR; }
     __device__ static __forceinline__ int* state_() { return reinterpret_cast<int*>(reinterpret_cast<double*>(g_smem) + S::O_STATE); }
@@ -570,7 +570,7 @@ struct Solver {
     double* const w = w_(); double* const w2 = w2_(); double* const av = av_(); double* const dg = dg_();   \
     double* const db = db_(); double* const xp = xp_(); double* const jd = jd_(); double* const d1 = d1_(); \
     double* const rr = rr_(); double* const lam = lam_(); double* const eopt = eopt_(); double* const red = red_(); \
-    double* const ext = ext_(); (void)ext;                                                                 \
+    double* const ext = ext_(); (void)ext; double* const rdi = rdi_(); (void)rdi;                          \
     int* const st = state_(); int* const act_row = st + 4; int* const act_sgn = st + 4 + KP;               \
     unsigned char* const cstate = cstate_(); const int tid = threadIdx.x;                                  \
     (void)rec; (void)Jm; (void)Q1; (void)Ad; (void)RN; (void)u0; (void)u; (void)x; (void)w; (void)w2; (void)av; \
@@ -719,23 +719,39 @@ struct Solver {
         return tm::sum(s, red_());
     }
 
-    // d1 (+)= Q1^T v ; v -= Q1 d  (one Gram-Schmidt pass against the k active normals)
+    // d1 (+)= Q1^T v ; v -= Q1 d  (one Gram-Schmidt pass against the k active normals).
+    // The k dot products of length N are shared by all threads: column c is split over SEG = TEAM / CW threads
+    // (CW = 16 or 32 columns wide), each walking every SEG-th row; the partial sums meet through a shuffle inside
+    // the warp and a small exchange buffer across warps (red[0 .. 2 * KMAX)).
     __device__ static __noinline__ void gs_pass(double* v, bool accumulate, int k)
     {
         QP_BIND
-        if (tid < k) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int i = 0;
+        double* const part = w2 == v ? av : w2;            // WARPS x 32 partial sums; never the vector being processed
+        {
+            const bool narrow = k <= 16;
+            const int cw = narrow ? 16 : 32;
+            const int c = tid & (cw - 1), seg = tid / cw, nseg = TEAM / cw;
+            double s0 = 0.0, s1 = 0.0;
+            if (c < k) {
+                int i = seg;
 #pragma unroll 2
-            for (; i + 3 < N; i += 4) {
-                s0 = fma(Q1[i * LDQ + tid], v[i], s0); s1 = fma(Q1[(i + 1) * LDQ + tid], v[i + 1], s1);
-                s2 = fma(Q1[(i + 2) * LDQ + tid], v[i + 2], s2); s3 = fma(Q1[(i + 3) * LDQ + tid], v[i + 3], s3);
+                for (; i + nseg < N; i += 2 * nseg) {
+                    s0 = fma(Q1[i * LDQ + c], v[i], s0);
+                    s1 = fma(Q1[(i + nseg) * LDQ + c], v[i + nseg], s1);
+                }
+                if (i < N) s0 = fma(Q1[i * LDQ + c], v[i], s0);
             }
-#pragma unroll 1
-            for (; i < N; ++i) s0 = fma(Q1[i * LDQ + tid], v[i], s0);
-            const double s = (s0 + s1) + (s2 + s3);
-            rr[tid] = s;                                      // rr: scratch for this pass' coefficients
-            d1[tid] = accumulate ? d1[tid] + s : s;
+            double sacc = s0 + s1;
+            if (narrow) sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);     // the two segments living in this warp
+            if ((tid & 31) < cw && (tid & 31) == c) part[(tid >> 5) * 32 + c] = sacc;
+        }
+        tm::sync();
+        if (tid < k) {
+            double sacc = part[tid];
+#pragma unroll
+            for (int wv = 1; wv < tm::WARPS; ++wv) sacc += part[wv * 32 + tid];
+            rr[tid] = sacc;                                  // rr: scratch for this pass' coefficients
+            d1[tid] = accumulate ? d1[tid] + sacc : sacc;
         }
         tm::sync();
         for (int i = tid; i < N; i += TEAM) {
@@ -758,7 +774,7 @@ struct Solver {
             double dv = tid < k ? d1[tid] : 0.0;
 #pragma unroll 1
             for (int c = k - 1; c >= 0; --c) {
-                const double rc = __shfl_sync(0xffffffffu, dv, c) / RN[c * LDR + c];
+                const double rc = __shfl_sync(0xffffffffu, dv, c) * rdi[c];
                 if (tid == c) dv = rc;
                 else if (tid < c) dv = fma(-RN[c * LDR + tid], rc, dv);
             }
@@ -805,6 +821,8 @@ struct Solver {
             }
             tm::sync();
         }
+        if (tid >= l && tid < k - 1) rdi[tid] = 1.0 / RN[tid * LDR + tid];   // diagonals changed under the Givens sweep
+        tm::sync();
     }
 
     // Adds constraint `row` with sign sgn (normal sgn*a, already whitened into w), current slack sp <= 0.
@@ -866,7 +884,7 @@ struct Solver {
                 for (int i = tid; i < N; i += TEAM) Q1[i * LDQ + k] = w2[i] * inv;
                 if (tid < k) RN[k * LDR + tid] = d1[tid];
                 if (tid == 0) {
-                    RN[k * LDR + k] = nr; lam[k] = up; act_row[k] = row; act_sgn[k] = is_eq ? 2 * sgn : sgn;
+                    RN[k * LDR + k] = nr; rdi[k] = inv; lam[k] = up; act_row[k] = row; act_sgn[k] = is_eq ? 2 * sgn : sgn;
                     cstate[row] = (is_eq || sgn > 0) ? 1 : 3;
                     st[0] = k + 1; st[1] = nai + (is_eq ? 0 : 1); st[2] = iters;
                 }
