@@ -196,6 +196,7 @@ struct ForceAcc {
     }
     static constexpr int MD0 = 6, MD1 = 6 * NC;                // dense task rows of level 0 / 1
     static constexpr int EXTRA = 0;                            // policy scratch in the slab (doubles)
+    static constexpr bool STAGE_RECORD = TLIM;                 // see Slab::STAGE
     static constexpr int KMAX = kmax_for(12, 3 * NC + (CONES ? 5 * NC : 0) + (TLIM ? NA : 0), N);
     template <int TEAM> __device__ static __forceinline__ bool prepare(const double*, double*, int) { return true; }
     __device__ static __forceinline__ int n_eq(int level) { return level == 0 ? 6 : 12; }
@@ -366,6 +367,7 @@ struct Torque {
     static constexpr int REC_UNPADDED = OFF_TAULIM + 2 * NA;
     static constexpr int REC = REC_UNPADDED + (REC_UNPADDED & 1);
     static constexpr int LDM = NA | 1;
+    static constexpr bool STAGE_RECORD = false;                // see Slab::STAGE
     static constexpr int KMAX = kmax_for(6, NA, N);
     static constexpr int O_A0 = NA * LDM, O_T = O_A0 + 6 * NA;
     static constexpr int EXTRA = O_T + NA * LDM + ((O_T + NA * LDM) & 1);
@@ -524,7 +526,11 @@ struct Slab {
     static constexpr int VEC = (N + 3) & ~3;
     // offsets in doubles from the slab base
     static constexpr int O_REC = 0;                   // staged record (16-B aligned: first in the slab)
-    static constexpr int O_J = O_REC + P::REC;
+    // Stage the record in shared memory (one TMA bulk copy) or leave it in global memory behind L1/L2.  Measured
+    // per shape (profiles/README.md): shapes whose inequality scan re-reads M every iteration (torque-limit rows)
+    // want it staged; for the others the 11-18 KB are worth more as 4 extra resident CTAs per SM.
+    static constexpr bool STAGE = P::STAGE_RECORD;
+    static constexpr int O_J = O_REC + (STAGE ? P::REC : 2);
     // J (and R before it) packed upper-triangular: NB (NB + 1) / 2 doubles.  R is row-major packed
     // (R(i,l) at i NB - i (i - 1) / 2 + (l - i)), J column-major packed (J(i,j) at j (j + 1) / 2 + i): triangular
     // numbers are a permutation mod 16, so a half-warp walking 16 consecutive columns is bank-conflict free.
@@ -552,7 +558,12 @@ struct Solver {
     static constexpr int KMAX = S::KMAX, LDQ = S::LDQ, LDR = S::LDR, KP = S::KP;
 
 #define QP_SM(name, off) __device__ static __forceinline__ double* name##_() { return reinterpret_cast<double*>(g_smem) + (off); }
-    QP_SM(rec, S::O_REC) QP_SM(Jm, S::O_J) QP_SM(Q1, S::O_Q) QP_SM(Ad, S::O_Q) QP_SM(RN, S::O_R)
+    __device__ static __forceinline__ double* rec_()
+    {
+        if (S::STAGE) return reinterpret_cast<double*>(g_smem) + S::O_REC;
+        return *reinterpret_cast<double**>(g_smem);            // pointer to the record in global memory
+    }
+    QP_SM(Jm, S::O_J) QP_SM(Q1, S::O_Q) QP_SM(Ad, S::O_Q) QP_SM(RN, S::O_R)
     QP_SM(u0, S::O_VEC) QP_SM(u, S::O_VEC + S::VEC) QP_SM(x, S::O_VEC + 2 * S::VEC) QP_SM(w, S::O_VEC + 3 * S::VEC)
     QP_SM(w2, S::O_VEC + 4 * S::VEC) QP_SM(av, S::O_VEC + 5 * S::VEC) QP_SM(dg, S::O_VEC + 6 * S::VEC)
     QP_SM(db, S::O_VEC + 7 * S::VEC) QP_SM(xp, S::O_VEC + 8 * S::VEC) QP_SM(jd, S::O_VEC + 9 * S::VEC)
@@ -1148,8 +1159,11 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
             if (counter) i = atomicAdd(counter, 1ull);
             else { i = next_static; next_static += gridDim.x; }
             s_idx = i;
-            if ((long long)i < batch)                          // one TMA bulk copy stages the whole record
-                bulk_load(SV::rec_(), recs + i * (size_t)P::REC, (uint32_t)(P::REC * sizeof(double)), SV::mbar_());
+            if ((long long)i < batch) {
+                if (Slab<P>::STAGE)                            // one TMA bulk copy stages the whole record
+                    bulk_load(SV::rec_(), recs + i * (size_t)P::REC, (uint32_t)(P::REC * sizeof(double)), SV::mbar_());
+                else *reinterpret_cast<const double**>(g_smem) = recs + i * (size_t)P::REC;
+            }
         }
         __syncthreads();
         const unsigned long long idx = s_idx;
@@ -1157,7 +1171,7 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
         double* xo = reinterpret_cast<double*>(out + idx * (size_t)OUT_BYTES);
         double* dg = diag ? diag + idx * (size_t)DIAG : nullptr;
         if (dg) for (int i = tid; i < DIAG; i += TEAM) dg[i] = 0.0;
-        mbar_wait(SV::mbar_(), phase); phase ^= 1;
+        if (Slab<P>::STAGE) { mbar_wait(SV::mbar_(), phase); phase ^= 1; }
         float kkt0 = __int_as_float(0x7f800000), kkt1 = kkt0;
         int it0 = 0, it1 = 0;
         int status = P::template prepare<TEAM>(SV::rec_(), SV::ext_(), tid) ? QPPVM_STATUS_OK : QPPVM_STATUS_NUMERIC;
