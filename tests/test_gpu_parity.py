@@ -123,6 +123,28 @@ def test_shard_invariance(torch_mod):
     assert torch.equal(whole, torch.cat(parts))
 
 
+@pytest.mark.parametrize("ci", (1, 0, 2))
+def test_repeated_launches_are_bitwise_identical(torch_mod, ci):
+    """Race proxy (compute-sanitizer is closed on this pool): the kernel has no atomics on data and a fixed
+    reduction order, so any run-to-run difference would be a shared-memory race or an uninitialised read."""
+    from qppvm_b200 import api
+    torch = torch_mod
+    desc = CONFIGS[ci]["desc"]
+    s = api.Solver(desc)
+    recs = torch.from_numpy(gen.generate(desc, 2500, 77 + ci)).cuda()
+    ref, dref = s.solve_batch(recs, diag=True)
+    ref, dref = ref.clone(), dref.clone()
+    for _ in range(4):
+        out, dg = s.solve_batch(recs, diag=True)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref) and torch.equal(dg, dref)
+    with pytest.raises(api.QPError):                      # records must be 16-byte aligned (TMA bulk copy)
+        flat = torch.empty(recs.numel() + 1, dtype=torch.float64, device="cuda")
+        mis = flat[1:].view(recs.shape)
+        mis.copy_(recs)
+        s.solve_batch(mis)
+
+
 def test_infeasible_and_iteration_limit_status(torch_mod, oracle_mod):
     from qppvm_b200 import api
     torch = torch_mod
