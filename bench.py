@@ -235,6 +235,33 @@ def main():
     e2e_ok = float(((ge["status"] == 0) & (ge["kkt"].max(axis=1) <= 1e-6)).mean())
     e2e_val = world * e2e_steps * batch * e2e_ok / t_e2e.item()
 
+    # ---- end to end from compact STATES: rigid-body front end + solve on the device; the host
+    # ships 1 KB states instead of 11-18 KB records.  Extra leg, not the headline `e2e` (whose inputs are records,
+    # i.e. what the reference's plugin hands to OpenSoT after model->update()).
+    e2e_states = None
+    if desc.kind == 1:
+        rob = gen.robot_for(desc.n_a)
+        solver.set_robot(rob, (rob.foot + rob.hand)[:desc.n_contacts])
+        h_states = torch.from_numpy(gen.generate_states(desc, N_BUF * batch, gen.config_seed(args.config),
+                                                        start=rank * N_BUF * batch)).pin_memory()
+        sd = h_states.shape[1]
+        st_ptr = [h_states[i * batch:(i + 1) * batch].data_ptr() for i in range(N_BUF)]
+        for i in range(3):
+            solver.solve_states_host_ptr(st_ptr[i % N_BUF], h_out.data_ptr(), batch)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            solver.solve_states_host_ptr(st_ptr[i % N_BUF], h_out.data_ptr(), batch)
+        torch.cuda.synchronize(dev)
+        t_st = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_st, op=dist.ReduceOp.MAX)
+        gs = api.split_out(L, h_out.numpy())
+        st_ok = float(((gs["status"] == 0) & (gs["kkt"].max(axis=1) <= 1e-6)).mean())
+        e2e_states = {"value": world * e2e_steps * batch * st_ok / t_st.item(), "unit": "solves/s",
+                      "h2d_bytes_per_step": batch * sd * 8, "d2h_bytes_per_step": batch * L.out_bytes, "steps": e2e_steps,
+                      "api": "qppvm_solve_states_host (states -> on-device rigid-body dynamics -> solve -> torques)"}
+
     # ---- N > 1: the same shards fed from rank 0 over NCCL (scatter records, gather outputs), device to device
     sg = None
     if world > 1:
@@ -296,6 +323,8 @@ def main():
             "converged_frac": frac.item(), "kkt_max": kkt_max}
     if sg:
         line["scatter_gather"] = sg
+    if e2e_states:
+        line["e2e_states"] = e2e_states
 
     if world == 1 and not args.no_latency:
         # single-tick latency (the metric's second half): config [4] shape, host in / host out per tick

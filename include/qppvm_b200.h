@@ -147,6 +147,32 @@ int qppvm_solve_batch_host(qppvm_handle* h, const double* records_host, void* ou
 /* Latency mode: one record, host in / host out, synchronous (one control tick). */
 int qppvm_solve_one(qppvm_handle* h, const double* record_host, void* out_host);
 
+/* ---- rigid-body front end: compact states -> records on the device ------------------
+ * Replaces, for batched use, what the reference obtains on the CPU from XBot::ModelInterface after
+ * model->update() (ref:src/ForceAcc.cpp:256-282, getJacobian :208, M and h inside DynamicFeasibility :109-114)
+ * and the OpenSoT task right-hand sides.  ForceAcc kind only.
+ * State layout (doubles): q n_a | qd n_a | R0 3x3 row-major | p0 3 | base twist (v0, w0) 6 | gains 4
+ *                         (lambda, lambda2 factors: waist, postural/contacts) | waist orientation error 3 |
+ *                         contact pose errors 6c | mu c | tau-limit scale n_a.                                  */
+typedef struct qppvm_robot {
+    int32_t n_a;                    /* actuated joints; bodies = n_a + 1, body 0 = floating base            */
+    const int32_t* parent;          /* [n_a + 1] parent body of each body, parent[0] = -1                   */
+    const double* axis;             /* [n_a + 1][3] joint axis in the parent frame (unit)                   */
+    const double* offset;           /* [n_a + 1][3] joint origin in the parent frame                        */
+    const double* mass;             /* [n_a + 1]                                                            */
+    const double* com;              /* [n_a + 1][3] centre of mass in the body frame                        */
+    const double* inertia;          /* [n_a + 1][3] principal inertia about the COM (body axes)             */
+    const double* q_home;           /* [n_a] postural reference                                             */
+    const double* tau_max;          /* [n_a] effort limits (scaled per state by the tau-limit scale)        */
+    const int32_t* contact_body;    /* [n_contacts] contact link bodies, in force-variable order            */
+} qppvm_robot;
+int qppvm_state_doubles(const qppvm_desc* desc);                    /* -1 on a bad description */
+int qppvm_set_robot(qppvm_handle* h, const qppvm_robot* robot);     /* copies the tables to the device */
+int qppvm_records_from_states(qppvm_handle* h, const double* states_dev, double* records_dev,
+                              int64_t batch, void* cuda_stream);
+/* states (host) -> records (device, never leave it) -> solve -> outputs (host); chunked and overlapped. */
+int qppvm_solve_states_host(qppvm_handle* h, const double* states_host, void* out_host, int64_t batch);
+
 /* Number of kernel launches issued through this handle so far. */
 int64_t qppvm_kernel_launches(const qppvm_handle* h);
 /* Measures the FP64 FMA peak of the device (TFLOP/s) with a register-resident DFMA

@@ -27,9 +27,17 @@ class CLayout(C.Structure):
     _fields_ = [(f, C.c_int32) for f in Layout.FIELDS]
 
 
+class CRobot(C.Structure):
+    _fields_ = [("n_a", C.c_int32), ("parent", C.POINTER(C.c_int32)), ("axis", C.POINTER(C.c_double)),
+                ("offset", C.POINTER(C.c_double)), ("mass", C.POINTER(C.c_double)), ("com", C.POINTER(C.c_double)),
+                ("inertia", C.POINTER(C.c_double)), ("q_home", C.POINTER(C.c_double)), ("tau_max", C.POINTER(C.c_double)),
+                ("contact_body", C.POINTER(C.c_int32))]
+
+
 EXPORTS = ("qppvm_get_layout", "qppvm_create", "qppvm_destroy", "qppvm_last_error", "qppvm_solve_batch",
            "qppvm_solve_batch_diag", "qppvm_solve_batch_host", "qppvm_solve_one", "qppvm_kernel_launches",
-           "qppvm_fp64_peak", "qppvm_supported_shapes")
+           "qppvm_fp64_peak", "qppvm_supported_shapes", "qppvm_state_doubles", "qppvm_set_robot",
+           "qppvm_records_from_states", "qppvm_solve_states_host")
 
 _lib = None
 
@@ -56,6 +64,10 @@ def load_library():
         lib.qppvm_kernel_launches.restype = C.c_int64
         lib.qppvm_fp64_peak.argtypes = [P, C.POINTER(C.c_double)]
         lib.qppvm_supported_shapes.argtypes = [C.POINTER(C.c_int32), C.c_int]
+        lib.qppvm_state_doubles.argtypes = [C.POINTER(CDesc)]
+        lib.qppvm_set_robot.argtypes = [P, C.POINTER(CRobot)]
+        lib.qppvm_records_from_states.argtypes = [P, P, P, C.c_int64, P]
+        lib.qppvm_solve_states_host.argtypes = [P, P, P, C.c_int64]
         _lib = lib
     return _lib
 
@@ -149,6 +161,45 @@ class Solver:
         if out is None:
             out = np.empty(L.out_doubles)
         self._check(self._lib.qppvm_solve_one(self._h, record.ctypes.data, out.ctypes.data))
+        return out
+
+    # ---- rigid-body front end: compact states instead of records -------
+    def set_robot(self, robot, contact_bodies):
+        """robot: qppvm_b200.gen.Robot (kinematic tree tables); contact_bodies: body index per contact."""
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        keep = dict(parent=i32(robot.parent), axis=f64(robot.axis), offset=f64(robot.offset), mass=f64(robot.mass),
+                    com=f64(robot.com), inertia=f64(robot.inertia), q_home=f64(robot.q_home), tau_max=f64(robot.tau_max),
+                    contact=i32(contact_bodies))
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        r = CRobot(robot.n_a, ip(keep["parent"]), dp(keep["axis"]), dp(keep["offset"]), dp(keep["mass"]), dp(keep["com"]),
+                   dp(keep["inertia"]), dp(keep["q_home"]), dp(keep["tau_max"]), ip(keep["contact"]))
+        self._check(self._lib.qppvm_set_robot(self._h, C.byref(r)))
+
+    @property
+    def state_doubles(self) -> int:
+        return self._lib.qppvm_state_doubles(C.byref(cdesc(self.desc)))
+
+    def records_from_states(self, states, records=None, stream=None):
+        import torch
+        assert states.is_cuda and states.dtype == torch.float64 and states.is_contiguous()
+        assert states.shape[1] == self.state_doubles
+        B = states.shape[0]
+        if records is None:
+            records = torch.empty((B, self.layout.rec_doubles), dtype=torch.float64, device=states.device)
+        st = torch.cuda.current_stream(states.device) if stream is None else stream
+        self._check(self._lib.qppvm_records_from_states(self._h, states.data_ptr(), records.data_ptr(), B, st.cuda_stream))
+        return records
+
+    def solve_states_host_ptr(self, states_ptr: int, out_ptr: int, batch: int):
+        self._check(self._lib.qppvm_solve_states_host(self._h, states_ptr, out_ptr, batch))
+
+    def solve_states_host(self, states: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        assert states.dtype == np.float64 and states.flags.c_contiguous and states.shape[1] == self.state_doubles
+        if out is None:
+            out = np.empty((states.shape[0], self.layout.out_doubles))
+        self._check(self._lib.qppvm_solve_states_host(self._h, states.ctypes.data, out.ctypes.data, states.shape[0]))
         return out
 
     @property

@@ -7,6 +7,8 @@
 #include <string.h>
 #include <new>
 #include "qp_kernel.cuh"
+#include "rbd_kernel.cuh"
+#include <vector>
 
 using namespace qppvm;
 
@@ -54,6 +56,8 @@ struct qppvm_handle {
     double* d_rec[HOST_STREAMS];
     unsigned char* d_out[HOST_STREAMS];
     int64_t chunk;                         // records per host-path chunk
+    double* d_state[HOST_STREAMS];         // host-path staging for the state front end
+    RobotTables rob; RbdShape rsh; void* rob_blob; bool has_robot;
     double* d_one_rec; unsigned char* d_one_out;
     double* h_one_rec; unsigned char* h_one_out;   // pinned staging for latency mode
     cudaStream_t one_stream;
@@ -243,6 +247,8 @@ int qppvm_destroy(qppvm_handle* h)
         cudaFree(h->d_rec[i]); cudaFree(h->d_out[i]);
     }
     if (h->one_stream) cudaStreamDestroy(h->one_stream);
+    for (int i = 0; i < HOST_STREAMS; ++i) cudaFree(h->d_state[i]);
+    cudaFree(h->rob_blob);
     cudaFree(h->d_one_rec); cudaFree(h->d_one_out);
     cudaFreeHost(h->h_one_rec); cudaFreeHost(h->h_one_out);
     cudaFree(h->counters);
@@ -299,6 +305,116 @@ int qppvm_solve_one(qppvm_handle* h, const double* rec, void* out)
     if (rc) return rc;
     CU(h, cudaStreamSynchronize(h->one_stream));
     memcpy(out, h->h_one_out, ob);
+    return QPPVM_OK;
+}
+
+static int state_layout(const qppvm_desc* d, RbdShape* sh)
+{
+    qppvm_layout L;
+    if (!d || d->kind != QPPVM_KIND_FORCEACC || qppvm_get_layout(d, &L)) return -1;
+    const int na = L.n_a, c = L.n_c;
+    int o = 0;
+    RbdShape s;
+    memset(&s, 0, sizeof(s));
+    s.n_a = na; s.n_v = L.n_v; s.n_c = c; s.flags = d->flags;
+    s.off_jwaist = L.off_jwaist; s.off_jc = L.off_jc; s.off_M = L.off_M; s.off_h = L.off_h; s.off_jdqd = L.off_jdqd;
+    s.off_rhs = L.off_rhs; s.off_taulim = L.off_taulim; s.off_cone = L.off_cone; s.off_fbox = L.off_fbox; s.rec_doubles = L.rec_doubles;
+    s.s_q = o; o += na; s.s_qd = o; o += na; s.s_R0 = o; o += 9; s.s_p0 = o; o += 3; s.s_tw = o; o += 6; s.s_gains = o; o += 4;
+    s.s_ori = o; o += 3; s.s_foot = o; o += 6 * c; s.s_mu = o; o += c; s.s_tscale = o; o += na;
+    s.state_doubles = o;
+    if (sh) *sh = s;
+    return o;
+}
+
+int qppvm_state_doubles(const qppvm_desc* d) { return state_layout(d, nullptr); }
+
+int qppvm_set_robot(qppvm_handle* h, const qppvm_robot* r)
+{
+    if (!h || !r) return QPPVM_ERR_ARG;
+    if (state_layout(&h->desc, &h->rsh) < 0) return fail(h, QPPVM_ERR_UNSUPPORTED, "the state front end covers the ForceAcc kind only");
+    const int na = h->desc.n_a, nb = na + 1, nc = h->desc.n_contacts;
+    if (r->n_a != na || nb > RBD_MAXB) return fail(h, QPPVM_ERR_ARG, "robot has %d joints, handle expects %d (max %d bodies)", r->n_a, na, RBD_MAXB);
+    std::vector<int> depth(nb, 0);
+    std::vector<unsigned long long> anc(nb, 0ull);
+    int maxd = 0;
+    for (int i = 1; i < nb; ++i) {
+        const int pa = r->parent[i];
+        if (pa < 0 || pa >= i) return fail(h, QPPVM_ERR_ARG, "bodies must be topologically ordered (parent[i] < i)");
+        depth[i] = depth[pa] + 1; anc[i] = anc[pa] | (1ull << (i - 1));
+        if (depth[i] > maxd) maxd = depth[i];
+    }
+    for (int i = 0; i < nc; ++i)
+        if (r->contact_body[i] < 0 || r->contact_body[i] >= nb) return fail(h, QPPVM_ERR_ARG, "bad contact body");
+    // one blob: doubles first (8-byte aligned), then the integer tables
+    const size_t nd = (size_t)nb * 3 * 4 + nb + 2 * na;              // axis offset com inertia | mass | q_home tau_max
+    const size_t bytes = nd * 8 + (size_t)nb * 8 + (size_t)(2 * nb + 4) * 4;
+    std::vector<unsigned char> host(bytes, 0);
+    double* hd = reinterpret_cast<double*>(host.data());
+    size_t o = 0;
+    auto putd = [&](const double* src, size_t n) { memcpy(hd + o, src, n * 8); const size_t at = o; o += n; return at; };
+    const size_t o_axis = putd(r->axis, nb * 3), o_off = putd(r->offset, nb * 3), o_com = putd(r->com, nb * 3), o_in = putd(r->inertia, nb * 3);
+    const size_t o_mass = putd(r->mass, nb), o_qh = putd(r->q_home, na), o_tm = putd(r->tau_max, na);
+    unsigned long long* hanc = reinterpret_cast<unsigned long long*>(host.data() + nd * 8);
+    memcpy(hanc, anc.data(), nb * 8);
+    int* hi = reinterpret_cast<int*>(host.data() + nd * 8 + (size_t)nb * 8);
+    memcpy(hi, r->parent, nb * 4); memcpy(hi + nb, depth.data(), nb * 4);
+    for (int i = 0; i < 4; ++i) hi[2 * nb + i] = i < nc ? r->contact_body[i] : 0;
+    CU(h, cudaSetDevice(h->desc.device));
+    if (h->rob_blob) { cudaFree(h->rob_blob); h->rob_blob = nullptr; }
+    CU(h, cudaMalloc(&h->rob_blob, bytes));
+    CU(h, cudaMemcpy(h->rob_blob, host.data(), bytes, cudaMemcpyHostToDevice));
+    const double* dd = reinterpret_cast<const double*>(h->rob_blob);
+    const int* di = reinterpret_cast<const int*>((const unsigned char*)h->rob_blob + nd * 8 + (size_t)nb * 8);
+    h->rob.n_a = na; h->rob.n_b = nb; h->rob.max_depth = maxd;
+    h->rob.axis = dd + o_axis; h->rob.offset = dd + o_off; h->rob.com = dd + o_com; h->rob.inertia = dd + o_in;
+    h->rob.mass = dd + o_mass; h->rob.q_home = dd + o_qh; h->rob.tau_max = dd + o_tm;
+    h->rob.anc = reinterpret_cast<const unsigned long long*>((const unsigned char*)h->rob_blob + nd * 8);
+    h->rob.parent = di; h->rob.depth = di + nb; h->rob.contact_body = di + 2 * nb;
+    for (int i = 0; i < HOST_STREAMS; ++i)
+        if (!h->d_state[i]) CU(h, cudaMalloc(&h->d_state[i], sizeof(double) * h->rsh.state_doubles * h->chunk));
+    h->has_robot = true;
+    return QPPVM_OK;
+}
+
+static int launch_rbd(qppvm_handle* h, const double* states, double* recs, int64_t batch, cudaStream_t st)
+{
+    if (batch <= 0) return QPPVM_OK;
+    const long long cap = (long long)h->sm_count * 8;
+    const int grid = (int)(batch < cap ? batch : cap);
+    rbd_records_kernel<<<grid, RBD_TEAM, 0, st>>>(h->rob, h->rsh, states, recs, (long long)batch);
+    CU(h, cudaGetLastError());
+    h->launches += 1;
+    return QPPVM_OK;
+}
+
+int qppvm_records_from_states(qppvm_handle* h, const double* states, double* recs, int64_t batch, void* stream)
+{
+    if (!h) return QPPVM_ERR_ARG;
+    if (!h->has_robot) return fail(h, QPPVM_ERR_ARG, "qppvm_set_robot has not been called");
+    if (batch < 0 || (batch > 0 && (!states || !recs))) return fail(h, QPPVM_ERR_ARG, "bad batch arguments");
+    CU(h, cudaSetDevice(h->desc.device));
+    return launch_rbd(h, states, recs, batch, (cudaStream_t)stream);
+}
+
+int qppvm_solve_states_host(qppvm_handle* h, const double* states, void* out, int64_t batch)
+{
+    if (!h) return QPPVM_ERR_ARG;
+    if (!h->has_robot) return fail(h, QPPVM_ERR_ARG, "qppvm_set_robot has not been called");
+    if (batch < 0 || (batch > 0 && (!states || !out))) return fail(h, QPPVM_ERR_ARG, "bad batch arguments");
+    CU(h, cudaSetDevice(h->desc.device));
+    const size_t sb = sizeof(double) * h->rsh.state_doubles, ob = (size_t)h->L.out_bytes;
+    int s = 0;
+    for (int64_t c0 = 0; c0 < batch; c0 += h->chunk, s = (s + 1) % HOST_STREAMS) {
+        const int64_t n = batch - c0 < h->chunk ? batch - c0 : h->chunk;
+        cudaStream_t st = h->streams[s];
+        CU(h, cudaMemcpyAsync(h->d_state[s], (const char*)states + c0 * sb, n * sb, cudaMemcpyHostToDevice, st));
+        int rc = launch_rbd(h, h->d_state[s], h->d_rec[s], n, st);
+        if (rc) return rc;
+        rc = launch(h, h->d_rec[s], h->d_out[s], nullptr, n, st, h->counters + s);
+        if (rc) return rc;
+        CU(h, cudaMemcpyAsync((char*)out + c0 * ob, h->d_out[s], n * ob, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < HOST_STREAMS; ++i) CU(h, cudaStreamSynchronize(h->streams[i]));
     return QPPVM_OK;
 }
 

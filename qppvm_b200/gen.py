@@ -220,21 +220,27 @@ def unpack_lower(Mp: np.ndarray, n: int) -> np.ndarray:
     return M
 
 
-def generate(desc: Desc, count: int, seed: int = BASE_SEED, start: int = 0,
-             chunk: int = 2048) -> np.ndarray:
-    """Records for problems [start, start+count): float64 array (count, rec_doubles)."""
-    L = layout(desc)
-    out = np.zeros((count, L.rec_doubles))
-    for c0 in range(0, count, chunk):
-        n = min(chunk, count - c0)
-        out[c0:c0 + n] = _generate_chunk(desc, L, seed, start + c0, n)
+def state_doubles(desc: Desc) -> int:
+    """Compact synthetic state of one problem (what the rigid-body front end consumes):
+    q | qd | R0 (3x3 row-major) | p0 | base twist (v0, w0) | gains 4 | ori_err 3 | foot_err 6c | mu c | tau_scale n_a."""
+    na, c = desc.n_a, desc.n_contacts
+    return 2 * na + 9 + 3 + 6 + 4 + 3 + 6 * c + c + na
+
+
+def state_offsets(desc: Desc) -> dict:
+    na, c = desc.n_a, desc.n_contacts
+    o, out = 0, {}
+    for name, n in (("q", na), ("qd", na), ("R0", 9), ("p0", 3), ("tw", 6), ("gains", 4), ("ori_err", 3),
+                    ("foot_err", 6 * c), ("mu", c), ("tau_scale", na)):
+        out[name] = (o, o + n)
+        o += n
     return out
 
 
-def _generate_chunk(desc: Desc, L: Layout, seed: int, start: int, n: int) -> np.ndarray:
-    rob = robot_for(desc.n_a)
-    na, nv, c = L.n_a, desc.n_a + 6, L.n_c
-    U = _uniforms(seed, start, n)
+def generate_states(desc: Desc, count: int, seed: int = BASE_SEED, start: int = 0) -> np.ndarray:
+    """Compact states for problems [start, start+count): float64 (count, state_doubles)."""
+    na, c = desc.n_a, desc.n_contacts
+    U = _uniforms(seed, start, count)
     k = 0
 
     def take(m):
@@ -246,6 +252,7 @@ def _generate_chunk(desc: Desc, L: Layout, seed: int, start: int, n: int) -> np.
     def normal(m, sigma):
         return sigma * ndtri(np.clip(take(m), 1e-12, 1 - 1e-12))
 
+    rob = robot_for(na)
     q = rob.q_home[None] + (take(na) * 0.6 - 0.3)             # q_home + U(-0.3, 0.3)
     qd = normal(na, 0.5)                                      # N(0, 0.5^2) rad/s
     rpy = take(3) * np.array([0.4, 0.4, 2 * np.pi]) - np.array([0.2, 0.2, np.pi])
@@ -254,10 +261,38 @@ def _generate_chunk(desc: Desc, L: Layout, seed: int, start: int, n: int) -> np.
     tw = normal(6, 0.2)
     gains = 0.8 + 0.4 * take(4)                               # "perturbed gains" x U(0.8, 1.2)
     ori_err = take(3) * 0.1 - 0.05
-    foot_err = normal(24, 1e-3)
-    mu = 0.4 + 0.5 * take(4)
+    foot_err = normal(24, 1e-3)[:, :6 * c]
+    mu = (0.4 + 0.5 * take(4))[:, :c]
     tau_scale = 0.5 + 0.5 * take(na)
     assert k <= DRAWS
+    if desc.kind == KIND_TORQUE:                              # fixed base
+        R0 = np.tile(np.eye(3), (count, 1, 1)); p0 = np.zeros((count, 3)); tw = np.zeros((count, 6))
+    return np.concatenate([q, qd, R0.reshape(count, 9), p0, tw, gains, ori_err, foot_err, mu, tau_scale], axis=1)
+
+
+def generate(desc: Desc, count: int, seed: int = BASE_SEED, start: int = 0,
+             chunk: int = 2048) -> np.ndarray:
+    """Records for problems [start, start+count): float64 array (count, rec_doubles)."""
+    L = layout(desc)
+    out = np.zeros((count, L.rec_doubles))
+    for c0 in range(0, count, chunk):
+        n = min(chunk, count - c0)
+        out[c0:c0 + n] = records_from_states(desc, generate_states(desc, n, seed, start + c0))
+    return out
+
+
+def records_from_states(desc: Desc, states: np.ndarray) -> np.ndarray:
+    """Rigid-body dynamics + task right-hand sides: compact states -> QP records (the CPU statement of what
+    ``model->update()`` + the OpenSoT task updates produce each tick, and of the on-device front end)."""
+    L = layout(desc)
+    rob = robot_for(desc.n_a)
+    na, nv, c = L.n_a, desc.n_a + 6, L.n_c
+    n = states.shape[0]
+    so = state_offsets(desc)
+    g = lambda name: states[:, so[name][0]:so[name][1]]
+    q, qd, p0, tw, gains, ori_err, foot_err, mu, tau_scale = (g(k) for k in
+        ("q", "qd", "p0", "tw", "gains", "ori_err", "foot_err", "mu", "tau_scale"))
+    R0 = g("R0").reshape(n, 3, 3)
 
     rec = np.zeros((n, L.rec_doubles))
     if desc.kind == KIND_FORCEACC:
@@ -303,10 +338,11 @@ def _generate_chunk(desc: Desc, L: Layout, seed: int, start: int, n: int) -> np.
         Mj = dyn["M"][:, 6:, 6:]
         rec[:, L.off_M:L.off_M + na * (na + 1) // 2] = pack_lower(Mj)
         rec[:, L.off_h:L.off_h + na] = dyn["h"][:, 6:]
+        ferr = np.zeros((n, 12)); ferr[:, :foot_err.shape[1]] = foot_err[:, :12]
         for ti, b in enumerate(rob.hand[::-1]):                # right first (QPPVMPlugin.cpp:177)
             Jh = dyn["links"][b]["J"][:, :, 6:]
             rec[:, L.off_jc + ti * 6 * na:L.off_jc + (ti + 1) * 6 * na] = Jh.reshape(n, -1)
-            e = np.concatenate([foot_err[:, 6 * ti:6 * ti + 3] * 30.0, ori_err * (1 - 2 * ti)], axis=1)
+            e = np.concatenate([ferr[:, 6 * ti:6 * ti + 3] * 30.0, ori_err * (1 - 2 * ti)], axis=1)
             F = 700.0 * gains[:, 0:1] * e - 70.0 * gains[:, 1:2] * np.einsum("bij,bj->bi", Jh, qd)
             rec[:, L.off_fee + 6 * ti:L.off_fee + 6 * ti + 6] = F     # K=700, D=70: QPPVMPlugin.cpp:136-137
         rec[:, L.off_tauj:L.off_tauj + na] = (5.0 * gains[:, 2:3] * (rob.q_home[None] - q)
