@@ -379,8 +379,7 @@ int qppvm_set_robot(qppvm_handle* h, const qppvm_robot* r)
 static int launch_rbd(qppvm_handle* h, const double* states, double* recs, int64_t batch, cudaStream_t st)
 {
     if (batch <= 0) return QPPVM_OK;
-    const long long cap = (long long)h->sm_count * 8;
-    const int grid = (int)(batch < cap ? batch : cap);
+    const int grid = (int)((batch + RBD_TEAM - 1) / RBD_TEAM);          // one thread per state
     rbd_records_kernel<<<grid, RBD_TEAM, 0, st>>>(h->rob, h->rsh, states, recs, (long long)batch);
     CU(h, cudaGetLastError());
     h->launches += 1;
