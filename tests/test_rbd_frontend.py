@@ -57,3 +57,36 @@ def test_states_to_torques_matches_oracle(oracle_mod):
     assert np.array_equal(out["active"], o["active"]) and out["kkt"].max() <= 1e-6
     with pytest.raises(api.QPError):                                   # front end needs the robot tables first
         api.Solver(desc).solve_states_host(states[:4])
+
+
+@pytest.mark.gpu
+def test_config3_one_million_states(oracle_mod):
+    """BASELINE configs[3] at full size on one GPU: 2^20 WALK-MAN-like states (4 contacts, cones + tau-limits).
+    States come from the seeded generator, records from the device front end (18.6 GB, never leave the GPU); every
+    solve must converge with the in-kernel KKT certificate <= 1e-6, and a random sample is checked against the oracle."""
+    import torch
+    from qppvm_b200 import api
+    desc, B = CONFIGS[3]["desc"], 1 << 20
+    L = layout(desc)
+    rob = gen.robot_for(desc.n_a)
+    s = api.Solver(desc)
+    s.set_robot(rob, (rob.foot + rob.hand)[:desc.n_contacts])
+    states = gen.generate_states(desc, B, gen.config_seed(3))
+    recs = s.records_from_states(torch.from_numpy(states).cuda())
+    out, _ = s.solve_batch(recs)
+    torch.cuda.synchronize()
+    tr = out[:, L.n_x + L.n_a:].contiguous().view(torch.int32)          # trailer words: status, iters, mask x4, kkt x2
+    bad = torch.nonzero(tr[:, 0] != 0)[:, 0]
+    # random states with scaled-down torque limits are, very rarely, genuinely infeasible (seed 20263118: one in
+    # 2^20): every non-OK status must be confirmed by the oracle on the same record
+    assert bad.numel() <= B // 100000
+    if bad.numel():
+        ob = oracle_mod.split_out(desc, oracle_mod.solve_batch(desc, recs[bad].cpu().numpy())[0])
+        assert np.array_equal(ob["status"], tr[bad, 0].cpu().numpy())
+    kkt = tr[:, 6:8].contiguous().view(torch.float32)
+    assert float(kkt[tr[:, 0] == 0].max()) <= 1e-6
+    idx = torch.from_numpy(np.random.default_rng(3).choice(B, 384, replace=False)).cuda()
+    idx = idx[tr[idx, 0] == 0]
+    g = api.split_out(L, out[idx].cpu().numpy())
+    o = oracle_mod.split_out(desc, oracle_mod.solve_batch(desc, recs[idx].cpu().numpy())[0])
+    assert rel_inf(g["x"], o["x"]).max() <= PRIMAL_TOL and np.array_equal(g["active"], o["active"])
