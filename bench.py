@@ -87,18 +87,26 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1, so the count is passed explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference(desc, recs, target_s, mode):
     """Times the oracle (restated active-set path, not the qpOASES binary) on a bounded sample."""
     from oracle import oracle
-    threads = oracle.num_threads()
+    threads = host_threads()
     if len(recs) < 2048:                                   # tiny workloads (single-tick configs): tile to a useful sample
         recs = np.tile(recs, ((2048 + len(recs) - 1) // len(recs), 1))
-    t0 = time.perf_counter(); oracle.solve_batch(desc, recs[:512], mode=mode); rate = 512 / (time.perf_counter() - t0)
+    t0 = time.perf_counter(); oracle.solve_batch(desc, recs[:512], mode=mode, threads=threads); rate = 512 / (time.perf_counter() - t0)
     n = int(max(rate * target_s, 512))
     done, t0 = 0, time.perf_counter()
     while done < n and time.perf_counter() - t0 < 2.0 * target_s:     # bounded by work AND by wall clock
         m = min(len(recs), n - done)
-        oracle.solve_batch(desc, recs[:m], mode=mode)
+        oracle.solve_batch(desc, recs[:m], mode=mode, threads=threads)
         done += m
     dt = time.perf_counter() - t0
     return done / dt, threads, done, dt
@@ -119,18 +127,19 @@ def run_reference(args, desc, L, cfg_name, batch):
         return
     from qppvm_b200 import gen
     from oracle import oracle
-    recs = gen.generate(desc, batch, gen.config_seed(args.config))
-    threads = oracle.num_threads()
+    recs = gen.generate(desc, min(batch, 8192), gen.config_seed(args.config))   # a step samples from these
+    batch = len(recs) if len(recs) < batch else batch
+    threads = host_threads()
     ncal = min(256, batch)
-    t0 = time.perf_counter(); oracle.solve_batch(desc, recs[:ncal], mode=oracle.FACTOR_CHOLESKY)
+    t0 = time.perf_counter(); oracle.solve_batch(desc, recs[:ncal], mode=oracle.FACTOR_CHOLESKY, threads=threads)
     rate = ncal / (time.perf_counter() - t0)
     budget = 120.0 / max(1, args.steps + args.warmup)            # whole run ~<= 2 min
-    sample = int(max(1, min(batch, rate * budget)))
+    sample = int(max(1, min(len(recs), rate * budget)))
     for _ in range(args.warmup):
-        oracle.solve_batch(desc, recs[:sample], mode=oracle.FACTOR_CHOLESKY)
+        oracle.solve_batch(desc, recs[:sample], mode=oracle.FACTOR_CHOLESKY, threads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out, _ = oracle.solve_batch(desc, recs[:sample], mode=oracle.FACTOR_CHOLESKY)
+        out, _ = oracle.solve_batch(desc, recs[:sample], mode=oracle.FACTOR_CHOLESKY, threads=threads)
     dt = time.perf_counter() - t0
     o = oracle.split_out(desc, out)
     good = float(((o["status"] == 0) & (o["kkt"].max(axis=1) <= 1e-6)).mean())
