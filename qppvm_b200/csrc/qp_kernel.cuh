@@ -182,6 +182,14 @@ struct ForceAcc {
     static constexpr int NI_BOX = 3 * NC, NI_CONE = CONES ? 5 * NC : 0, NI_TAU = TLIM ? NA : 0;
     static constexpr int NI = NI_BOX + NI_CONE + NI_TAU;
     // record offsets (doubles)
+    __host__ __device__ static constexpr int OFF_M_() { return 6 * (NA_ + 6) + NC_ * 6 * (NA_ + 6); }
+    __host__ __device__ static constexpr int REC_()
+    {
+        const int nv = NA_ + 6;
+        const int u = OFF_M_() + nv * (nv + 1) / 2 + nv + 6 * (1 + NC_) + 6 * (1 + NC_) + nv
+                      + ((FLAGS_ & QPPVM_FLAG_TORQUE_LIMITS) ? 2 * NA_ : 0) + ((FLAGS_ & QPPVM_FLAG_FRICTION_CONES) ? 10 * NC_ : 0) + 6 * NC_;
+        return u + (u & 1);
+    }
     static constexpr int OFF_JW = 0, OFF_JC = OFF_JW + 6 * NV, OFF_M = OFF_JC + NC * 6 * NV;
     static constexpr int OFF_H = OFF_M + NV * (NV + 1) / 2, OFF_JDQD = OFF_H + NV;
     static constexpr int OFF_RHS = OFF_JDQD + 6 * (1 + NC), OFF_TAULIM = OFF_RHS + 6 * (1 + NC) + NV;
@@ -189,15 +197,31 @@ struct ForceAcc {
     static constexpr int OFF_FBOX = OFF_CONE + (CONES ? 10 * NC : 0);
     static constexpr int REC_UNPADDED = OFF_FBOX + 6 * NC;
     static constexpr int REC = REC_UNPADDED + (REC_UNPADDED & 1);
+    static_assert(REC == REC_() && OFF_M == OFF_M_(), "layout helpers agree");
 
     __device__ static __forceinline__ double M(const double* rec, int i, int j)
     {
-        return i >= j ? rec[OFF_M + i * (i + 1) / 2 + j] : rec[OFF_M + j * (j + 1) / 2 + i];
+        return i >= j ? rec[OFF_M - SB + i * (i + 1) / 2 + j] : rec[OFF_M - SB + j * (j + 1) / 2 + i];
     }
     static constexpr int MD0 = 6, MD1 = 6 * NC;                // dense task rows of level 0 / 1
     static constexpr int EXTRA = 0;                            // policy scratch in the slab (doubles)
-    static constexpr bool STAGE_RECORD = TLIM;                 // see Slab::STAGE
-    static constexpr int KMAX = kmax_for(12, 3 * NC + (CONES ? 5 * NC : 0) + (TLIM ? NA : 0), N);
+    // Staging (see Slab::STAGE): shapes whose inequality scan re-reads M every iteration (torque-limit rows) keep
+    // the TAIL of the record [M | h | Jdqd | rhs | tau limits | cones | boxes] (one TMA bulk copy) plus the linear
+    // contact-Jacobian rows in shared memory; the task Jacobians (read once per level) stay in global memory.
+    // Policy functions get `rec` = staged tail (or the global record when nothing is staged) and `g` = global record.
+    static constexpr bool STAGE_RECORD = TLIM;
+    static constexpr bool EXT_IS_GLOBAL = true;                // the `ext` argument carries the global record pointer
+    static constexpr int STAGE_FROM = OFF_M_();                // first staged record offset (even => 16-byte aligned)
+    static constexpr int SB = STAGE_RECORD ? STAGE_FROM : 0;   // staged offset = record offset - SB
+    static constexpr int S_JCL = REC_() - STAGE_FROM;          // linear rows of J_c: (ci * 3 + k) * NV + col
+    static constexpr int STAGED = S_JCL + 3 * NC * NV + ((S_JCL + 3 * NC * NV) & 1);
+    __device__ static __forceinline__ double jcl(const double* rec, const double* g, int ci, int k, int col)
+    {
+        return STAGE_RECORD ? rec[S_JCL + (ci * 3 + k) * NV + col] : g[OFF_JC + (ci * 6 + k) * NV + col];
+    }
+    static constexpr int KMAX_RAW = kmax_for(12, 3 * NC + (CONES ? 5 * NC : 0) + (TLIM ? NA : 0), N);
+    // 31 instead of 32 rows of capacity is what lets a fifth CTA of the 51-variable shape fit on an SM
+    static constexpr int KMAX = (KMAX_RAW == 32 && N > 48) ? 31 : KMAX_RAW;
     template <int TEAM> __device__ static __forceinline__ bool prepare(const double*, double*, int) { return true; }
     __device__ static __forceinline__ int n_eq(int level) { return level == 0 ? 6 : 12; }
     __device__ static __forceinline__ int eq_row(int level, int e) { return e < 6 ? ROW_DYN + e : ROW_OPT + (e - 6); }
@@ -207,20 +231,20 @@ struct ForceAcc {
     // weights / targets into dg, db (postural rows are unit rows -> kept as a diagonal).
     // Level 0: waist Cartesian (ForceAcc.cpp:118-122).  Level 1: postural + contact Cartesian (:131).
     template <int TEAM>
-    __device__ static int load_tasks(const double* rec, const double*, int level, double* Ad, double* dg, double* db, int tid)
+    __device__ static int load_tasks(const double* rec, const double* g, int level, double* Ad, double* dg, double* db, int tid)
     {
         constexpr int LDA = NB + 1;
         const int md = level == 0 ? 6 : 6 * NC;
-        const double* Jr = level == 0 ? rec + OFF_JW : rec + OFF_JC;
+        const double* Jr = level == 0 ? g + OFF_JW : g + OFF_JC;
         for (int e = tid; e < md * NV; e += TEAM) { const int r = e / NV, j = e - r * NV; Ad[r * LDA + j] = Jr[e]; }
         for (int r = tid; r < md; r += TEAM) {
             const int t = level == 0 ? r : 6 + r;            // task-row index into rhs / Jdqd
-            Ad[r * LDA + NB] = rec[OFF_RHS + t] - rec[OFF_JDQD + t];
+            Ad[r * LDA + NB] = rec[OFF_RHS - SB + t] - rec[OFF_JDQD - SB + t];
         }
         for (int j = tid; j < N; j += TEAM) {
             const bool post = level == 1 && j < NV;
             dg[j] = post ? 1.0 : 0.0;
-            db[j] = post ? rec[OFF_RHS + 6 * (1 + NC) + j] : 0.0;
+            db[j] = post ? rec[OFF_RHS - SB + 6 * (1 + NC) + j] : 0.0;
         }
         return md;
     }
@@ -228,7 +252,7 @@ struct ForceAcc {
     // Coefficients of constraint row `row` as a dense n-vector (smem av) + its two-sided bounds.
     // eopt: A0 x0* (level-1 optimality right-hand sides).
     template <int TEAM>
-    __device__ static void build_row(const double* rec, const double*, int row, const double* eopt,
+    __device__ static void build_row(const double* rec, const double* g, int row, const double* eopt,
                                      double* av, double& lo, double& hi, int tid)
     {
         if (row < ROW_BOX) {                                   // DynamicFeasibility (base rows of M qdd + h - J^T w)
@@ -236,18 +260,18 @@ struct ForceAcc {
             for (int j = tid; j < N; j += TEAM) {
                 double v;
                 if (j < NV) v = M(rec, r, j);
-                else { const int ci = (j - NV) / 3, k = (j - NV) % 3; v = -rec[OFF_JC + (ci * 6 + k) * NV + r]; }
+                else { const int ci = (j - NV) / 3, k = (j - NV) % 3; v = -jcl(rec, g, ci, k, r); }
                 av[j] = v;
             }
-            lo = hi = -rec[OFF_H + r];
+            lo = hi = -rec[OFF_H - SB + r];
         } else if (row < ROW_CONE) {                           // wrench box (GenericConstraint)
             const int ci = (row - ROW_BOX) / 6, k = (row - ROW_BOX) % 6;
             for (int j = tid; j < N; j += TEAM) av[j] = (k < 3 && j == NV + 3 * ci + k) ? 1.0 : 0.0;
-            if (k < 3) { lo = rec[OFF_FBOX + 6 * ci + k]; hi = rec[OFF_FBOX + 6 * ci + 3 + k]; }
+            if (k < 3) { lo = rec[OFF_FBOX - SB + 6 * ci + k]; hi = rec[OFF_FBOX - SB + 6 * ci + 3 + k]; }
             else { lo = -1.0; hi = 1.0; }
         } else if (CONES && row < ROW_TAU) {                   // friction pyramid on R^T f
             const int ci = (row - ROW_CONE) / 5, jr = (row - ROW_CONE) % 5;
-            const double* R = rec + OFF_CONE + 10 * ci;
+            const double* R = rec + OFF_CONE - SB + 10 * ci;
             const double mu = R[9] * 0.70710678118654752440;
             const double c0 = jr == 0 ? 1.0 : (jr == 1 ? -1.0 : 0.0);
             const double c1 = jr == 2 ? 1.0 : (jr == 3 ? -1.0 : 0.0);
@@ -264,31 +288,31 @@ struct ForceAcc {
             for (int j = tid; j < N; j += TEAM) {
                 double v;
                 if (j < NV) v = M(rec, 6 + a, j);
-                else { const int ci = (j - NV) / 3, k = (j - NV) % 3; v = -rec[OFF_JC + (ci * 6 + k) * NV + 6 + a]; }
+                else { const int ci = (j - NV) / 3, k = (j - NV) % 3; v = -jcl(rec, g, ci, k, 6 + a); }
                 av[j] = v;
             }
-            const double ha = rec[OFF_H + 6 + a];
-            lo = rec[OFF_TAULIM + a] - ha; hi = rec[OFF_TAULIM + NA + a] - ha;
+            const double ha = rec[OFF_H - SB + 6 + a];
+            lo = rec[OFF_TAULIM - SB + a] - ha; hi = rec[OFF_TAULIM - SB + NA + a] - ha;
         } else {                                               // optimality rows of level 0: J_waist x = J_waist x0*
             const int r = row - ROW_OPT;
-            for (int j = tid; j < N; j += TEAM) av[j] = j < NV ? rec[OFF_JW + r * NV + j] : 0.0;
+            for (int j = tid; j < N; j += TEAM) av[j] = j < NV ? g[OFF_JW + r * NV + j] : 0.0;
             lo = hi = eopt[r];
         }
     }
 
     // Inequality slot q -> (row id, value a.x, lo, hi).  One slot per thread.
-    __device__ static void eval_slot(const double* rec, int q, const double* x,
+    __device__ static void eval_slot(const double* rec, const double* g, int q, const double* x,
                                      int& row, double& val, double& lo, double& hi)
     {
         if (q < NI_BOX) {
             const int ci = q / 3, k = q % 3;
             row = ROW_BOX + 6 * ci + k;
             val = x[NV + q];
-            lo = rec[OFF_FBOX + 6 * ci + k]; hi = rec[OFF_FBOX + 6 * ci + 3 + k];
+            lo = rec[OFF_FBOX - SB + 6 * ci + k]; hi = rec[OFF_FBOX - SB + 6 * ci + 3 + k];
         } else if (CONES && q < NI_BOX + NI_CONE) {
             const int qq = q - NI_BOX, ci = qq / 5, jr = qq % 5;
             row = ROW_CONE + qq;
-            const double* R = rec + OFF_CONE + 10 * ci;
+            const double* R = rec + OFF_CONE - SB + 10 * ci;
             const double mu = R[9] * 0.70710678118654752440;
             const double c0 = jr == 0 ? 1.0 : (jr == 1 ? -1.0 : 0.0);
             const double c1 = jr == 2 ? 1.0 : (jr == 3 ? -1.0 : 0.0);
@@ -303,25 +327,25 @@ struct ForceAcc {
             row = ROW_TAU + a;
             double v0 = 0.0, v1 = 0.0;
             const int i = 6 + a;
-            const double* Mi = rec + OFF_M + i * (i + 1) / 2;
+            const double* Mi = rec + OFF_M - SB + i * (i + 1) / 2;
 #pragma unroll 2
             for (int j = 0; j <= i; ++j) v0 = fma(Mi[j], x[j], v0);
 #pragma unroll 2
-            for (int j = i + 1; j < NV; ++j) v1 = fma(rec[OFF_M + j * (j + 1) / 2 + i], x[j], v1);
+            for (int j = i + 1; j < NV; ++j) v1 = fma(rec[OFF_M - SB + j * (j + 1) / 2 + i], x[j], v1);
 #pragma unroll 1
-            for (int j = 0; j < 3 * NC; ++j) v0 = fma(-rec[OFF_JC + ((j / 3) * 6 + (j % 3)) * NV + i], x[NV + j], v0);
-            const double ha = rec[OFF_H + i];
-            val = v0 + v1; lo = rec[OFF_TAULIM + a] - ha; hi = rec[OFF_TAULIM + NA + a] - ha;
+            for (int j = 0; j < 3 * NC; ++j) v0 = fma(-jcl(rec, g, j / 3, j % 3, i), x[NV + j], v0);
+            const double ha = rec[OFF_H - SB + i];
+            val = v0 + v1; lo = rec[OFF_TAULIM - SB + a] - ha; hi = rec[OFF_TAULIM - SB + NA + a] - ha;
         }
     }
 
     // Level-0 task value A0 x0* (6 numbers) -> eopt.
     template <int TEAM>
-    __device__ static void task0_value(const double* rec, const double*, const double* x, double* eopt, int tid)
+    __device__ static void task0_value(const double*, const double* g, const double* x, double* eopt, int tid)
     {
         if (tid < QPPVM_M0) {
             double s0 = 0.0, s1 = 0.0;
-            const double* Jr = rec + OFF_JW + tid * NV;
+            const double* Jr = g + OFF_JW + tid * NV;
             int j = 0;
             for (; j + 1 < NV; j += 2) { s0 = fma(Jr[j], x[j], s0); s1 = fma(Jr[j + 1], x[j + 1], s1); }
             if (j < NV) s0 = fma(Jr[j], x[j], s0);
@@ -331,15 +355,15 @@ struct ForceAcc {
 
     // tau = (M qdd + h - sum J_c^T [f;0]) actuated rows  (ref:src/ForceAcc.cpp:206-219)
     template <int TEAM>
-    __device__ static void recover(const double* rec, const double* x, double* tau_out, bool ok, int tid)
+    __device__ static void recover(const double* rec, const double* g, const double* x, double* tau_out, bool ok, int tid)
     {
         for (int a = tid; a < NA; a += TEAM) {
             double v = 0.0;
             if (ok) {
                 const int i = 6 + a;
-                v = rec[OFF_H + i];
+                v = rec[OFF_H - SB + i];
                 for (int j = 0; j < NV; ++j) v = fma(M(rec, i, j), x[j], v);
-                for (int j = 0; j < 3 * NC; ++j) v = fma(-rec[OFF_JC + ((j / 3) * 6 + (j % 3)) * NV + i], x[NV + j], v);
+                for (int j = 0; j < 3 * NC; ++j) v = fma(-jcl(rec, g, j / 3, j % 3, i), x[NV + j], v);
             }
             tau_out[a] = v;     // failure: nothing is commanded (ForceAcc.cpp:189-193) -> zeros
         }
@@ -368,6 +392,8 @@ struct Torque {
     static constexpr int REC = REC_UNPADDED + (REC_UNPADDED & 1);
     static constexpr int LDM = NA | 1;
     static constexpr bool STAGE_RECORD = false;                // see Slab::STAGE
+    static constexpr bool EXT_IS_GLOBAL = false;               // `ext` is the policy scratch (M^-1, A0, T)
+    static constexpr int STAGE_FROM = 0, STAGED = 0, S_JCL = 0;
     static constexpr int KMAX = kmax_for(6, NA, N);
     static constexpr int O_A0 = NA * LDM, O_T = O_A0 + 6 * NA;
     static constexpr int EXTRA = O_T + NA * LDM + ((O_T + NA * LDM) & 1);
@@ -487,7 +513,7 @@ struct Torque {
             lo = hi = eopt[r];
         }
     }
-    __device__ static void eval_slot(const double* rec, int q, const double* x,
+    __device__ static void eval_slot(const double* rec, const double*, int q, const double* x,
                                      int& row, double& val, double& lo, double& hi)
     {
         row = q; val = x[q];
@@ -505,7 +531,7 @@ struct Torque {
     }
     // tau_d = tau_qp + h ; tau_qp = 0 on failure (ref:src/QPPVMPlugin.cpp:246-256)
     template <int TEAM>
-    __device__ static void recover(const double* rec, const double* x, double* tau_out, bool ok, int tid)
+    __device__ static void recover(const double* rec, const double*, const double* x, double* tau_out, bool ok, int tid)
     {
         for (int a = tid; a < NA; a += TEAM) tau_out[a] = (ok ? x[a] : 0.0) + rec[OFF_H + a];
     }
@@ -530,7 +556,7 @@ struct Slab {
     // per shape (profiles/README.md): shapes whose inequality scan re-reads M every iteration (torque-limit rows)
     // want it staged; for the others the 11-18 KB are worth more as 4 extra resident CTAs per SM.
     static constexpr bool STAGE = P::STAGE_RECORD;
-    static constexpr int O_J = O_REC + (STAGE ? P::REC : 2);
+    static constexpr int O_J = O_REC + (STAGE ? P::STAGED : 0) + 2;   // staged part | global record pointer slot
     // J (and R before it) packed upper-triangular: NB (NB + 1) / 2 doubles.  R is row-major packed
     // (R(i,l) at i NB - i (i - 1) / 2 + (l - i)), J column-major packed (J(i,j) at j (j + 1) / 2 + i): triangular
     // numbers are a permutation mod 16, so a half-warp walking 16 consecutive columns is bank-conflict free.
@@ -558,10 +584,14 @@ struct Solver {
     static constexpr int KMAX = S::KMAX, LDQ = S::LDQ, LDR = S::LDR, KP = S::KP;
 
 #define QP_SM(name, off) __device__ static __forceinline__ double* name##_() { return reinterpret_cast<double*>(g_smem) + (off); }
+    __device__ static __forceinline__ double* grec_()         // the record in global memory
+    {
+        return *reinterpret_cast<double**>(reinterpret_cast<double*>(g_smem) + S::O_J - 2);
+    }
     __device__ static __forceinline__ double* rec_()
     {
         if (S::STAGE) return reinterpret_cast<double*>(g_smem) + S::O_REC;
-        return *reinterpret_cast<double**>(g_smem);            // pointer to the record in global memory
+        return grec_();
     }
     QP_SM(Jm, S::O_J) QP_SM(Q1, S::O_Q) QP_SM(Ad, S::O_Q) QP_SM(RN, S::O_R)
     QP_SM(u0, S::O_VEC) QP_SM(u, S::O_VEC + S::VEC) QP_SM(x, S::O_VEC + 2 * S::VEC) QP_SM(w, S::O_VEC + 3 * S::VEC)
@@ -581,7 +611,7 @@ struct Solver {
     double* const w = w_(); double* const w2 = w2_(); double* const av = av_(); double* const dg = dg_();   \
     double* const db = db_(); double* const xp = xp_(); double* const jd = jd_(); double* const d1 = d1_(); \
     double* const rr = rr_(); double* const lam = lam_(); double* const eopt = eopt_(); double* const red = red_(); \
-    double* const ext = ext_(); (void)ext; double* const rdi = rdi_(); (void)rdi;                          \
+    double* const ext = P::EXT_IS_GLOBAL ? grec_() : ext_(); (void)ext; double* const rdi = rdi_(); (void)rdi; \
     int* const st = state_(); int* const act_row = st + 4; int* const act_sgn = st + 4 + KP;               \
     unsigned char* const cstate = cstate_(); const int tid = threadIdx.x;                                  \
     (void)rec; (void)Jm; (void)Q1; (void)Ad; (void)RN; (void)u0; (void)u; (void)x; (void)w; (void)w2; (void)av; \
@@ -915,7 +945,7 @@ struct Solver {
         double worst = 0.0; int widx = 0x7fffffff; int wsgn = 0; double wb = 0.0;
         for (int q = tid; q < P::NI; q += TEAM) {
             int r; double val, lo, hi;
-            P::eval_slot(rec, q, x, r, val, lo, hi);
+            P::eval_slot(rec, ext, q, x, r, val, lo, hi);
             // cstate: 0 inactive, 1 active at lA, 3 active at uA, 2 implied / weakly active.  The side opposite to an
             // active one is still checked: an empty box (lA > uA) must surface as infeasible, not be masked.
             const int cs = cstate[r];
@@ -1095,7 +1125,7 @@ struct Solver {
             double viol = 0.0, cm = 0.0;
             for (int q = tid; q < P::NI; q += TEAM) {
                 int r; double val, lo, hi;
-                P::eval_slot(rec, q, x, r, val, lo, hi);
+                P::eval_slot(rec, ext, q, x, r, val, lo, hi);
                 cm = fmax(cm, fabs(val));
                 if (!(cstate[r] & 1)) viol = fmax(viol, fmax(lo - val, val - hi));
             }
@@ -1160,9 +1190,10 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
             else { i = next_static; next_static += gridDim.x; }
             s_idx = i;
             if ((long long)i < batch) {
-                if (Slab<P>::STAGE)                            // one TMA bulk copy stages the whole record
-                    bulk_load(SV::rec_(), recs + i * (size_t)P::REC, (uint32_t)(P::REC * sizeof(double)), SV::mbar_());
-                else *reinterpret_cast<const double**>(g_smem) = recs + i * (size_t)P::REC;
+                const double* gr = recs + i * (size_t)P::REC;
+                *reinterpret_cast<const double**>(reinterpret_cast<double*>(g_smem) + Slab<P>::O_J - 2) = gr;
+                if (Slab<P>::STAGE)                            // one TMA bulk copy stages the tail of the record
+                    bulk_load(SV::rec_(), gr + P::STAGE_FROM, (uint32_t)((P::REC - P::STAGE_FROM) * sizeof(double)), SV::mbar_());
             }
         }
         __syncthreads();
@@ -1171,16 +1202,25 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
         double* xo = reinterpret_cast<double*>(out + idx * (size_t)OUT_BYTES);
         double* dg = diag ? diag + idx * (size_t)DIAG : nullptr;
         if (dg) for (int i = tid; i < DIAG; i += TEAM) dg[i] = 0.0;
-        if (Slab<P>::STAGE) { mbar_wait(SV::mbar_(), phase); phase ^= 1; }
+        if (Slab<P>::STAGE) {
+            // linear contact-Jacobian rows next to the staged tail (plain coalesced loads, overlapping the TMA copy)
+            const double* gr = recs + idx * (size_t)P::REC;
+            for (int t = tid; t < 3 * P::NC * P::NV; t += TEAM) {
+                const int rowl = t / P::NV, col = t - rowl * P::NV;
+                SV::rec_()[P::S_JCL + t] = gr[P::NV * 6 + ((rowl / 3) * 6 + (rowl % 3)) * P::NV + col];
+            }
+            mbar_wait(SV::mbar_(), phase); phase ^= 1;
+            __syncthreads();
+        }
         float kkt0 = __int_as_float(0x7f800000), kkt1 = kkt0;
         int it0 = 0, it1 = 0;
-        int status = P::template prepare<TEAM>(SV::rec_(), SV::ext_(), tid) ? QPPVM_STATUS_OK : QPPVM_STATUS_NUMERIC;
+        int status = P::template prepare<TEAM>(SV::rec_(), P::EXT_IS_GLOBAL ? SV::grec_() : SV::ext_(), tid) ? QPPVM_STATUS_OK : QPPVM_STATUS_NUMERIC;
         if (status == QPPVM_STATUS_OK)
             status = SV::solve_level(0, prm.eps_reg, prm.n_reg_steps, prm.max_iter, dg ? dg + N : nullptr);
         it0 = SV::state_()[2];
         if (status == QPPVM_STATUS_OK) kkt0 = (float)SV::red_()[12];
         if (status == QPPVM_STATUS_OK) {
-            P::template task0_value<TEAM>(SV::rec_(), SV::ext_(), SV::x_(), SV::eopt_(), tid);
+            P::template task0_value<TEAM>(SV::rec_(), P::EXT_IS_GLOBAL ? SV::grec_() : SV::ext_(), SV::x_(), SV::eopt_(), tid);
             Team<TEAM>::sync();
             if (dg) {
                 for (int i = tid; i < N; i += TEAM) dg[i] = SV::x_()[i];
@@ -1194,7 +1234,7 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
         const bool ok = status == QPPVM_STATUS_OK;
         if (dg && !ok && tid < 3) dg[N + 2 * P::NROWS + 3 + tid] = SV::red_()[13 + tid];   // slack, |bound|, k at failure
         for (int i = tid; i < N; i += TEAM) xo[i] = ok ? SV::x_()[i] : 0.0;
-        P::template recover<TEAM>(SV::rec_(), SV::x_(), xo + N, ok, tid);
+        P::template recover<TEAM>(SV::rec_(), P::EXT_IS_GLOBAL ? SV::grec_() : SV::ext_(), SV::x_(), xo + N, ok, tid);
         // trailer: status, iters, 128-bit active mask of level 1, kkt[2]
         uint32_t* tr = reinterpret_cast<uint32_t*>(xo + N + P::NA);
         if (tid < 4) {
