@@ -56,6 +56,7 @@ struct qppvm_handle {
     double* d_rec[HOST_STREAMS];
     unsigned char* d_out[HOST_STREAMS];
     int64_t chunk;                         // records per host-path chunk
+    int64_t chunk_states;                  // states per chunk of the state front end (transfers are 10x smaller)
     double* d_state[HOST_STREAMS];         // host-path staging for the state front end
     RobotTables rob; RbdShape rsh; void* rob_blob; bool has_robot;
     double* d_one_rec; unsigned char* d_one_out;
@@ -223,10 +224,11 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
     // host path: records per pipelined chunk (H2D of chunk i+1 overlaps the solve of chunk i); QPPVM_CHUNK overrides
     h->chunk = 1024;
     if (const char* e = getenv("QPPVM_CHUNK")) { const long c = atol(e); if (c >= 64 && c <= (1 << 20)) h->chunk = c; }
+    h->chunk_states = 4 * h->chunk;
     for (int i = 0; i < HOST_STREAMS; ++i) {
         CUC(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
-        CUC(cudaMalloc(&h->d_rec[i], sizeof(double) * L.rec_doubles * h->chunk));
-        CUC(cudaMalloc(&h->d_out[i], (size_t)L.out_bytes * h->chunk));
+        CUC(cudaMalloc(&h->d_rec[i], sizeof(double) * L.rec_doubles * h->chunk_states));
+        CUC(cudaMalloc(&h->d_out[i], (size_t)L.out_bytes * h->chunk_states));
     }
     CUC(cudaStreamCreateWithFlags(&h->one_stream, cudaStreamNonBlocking));
     CUC(cudaMalloc(&h->d_one_rec, sizeof(double) * L.rec_doubles));
@@ -371,7 +373,7 @@ int qppvm_set_robot(qppvm_handle* h, const qppvm_robot* r)
     h->rob.anc = reinterpret_cast<const unsigned long long*>((const unsigned char*)h->rob_blob + nd * 8);
     h->rob.parent = di; h->rob.depth = di + nb; h->rob.contact_body = di + 2 * nb;
     for (int i = 0; i < HOST_STREAMS; ++i)
-        if (!h->d_state[i]) CU(h, cudaMalloc(&h->d_state[i], sizeof(double) * h->rsh.state_doubles * h->chunk));
+        if (!h->d_state[i]) CU(h, cudaMalloc(&h->d_state[i], sizeof(double) * h->rsh.state_doubles * h->chunk_states));
     h->has_robot = true;
     return QPPVM_OK;
 }
@@ -403,8 +405,13 @@ int qppvm_solve_states_host(qppvm_handle* h, const double* states, void* out, in
     CU(h, cudaSetDevice(h->desc.device));
     const size_t sb = sizeof(double) * h->rsh.state_doubles, ob = (size_t)h->L.out_bytes;
     int s = 0;
-    for (int64_t c0 = 0; c0 < batch; c0 += h->chunk, s = (s + 1) % HOST_STREAMS) {
-        const int64_t n = batch - c0 < h->chunk ? batch - c0 : h->chunk;
+    // chunk: a quarter of the batch (so that the four streams overlap copy / front end / solve), between the record
+    // path's chunk and four times that (large batches: fewer, fuller launches)
+    int64_t cs = (batch / 4 + 255) / 256 * 256;
+    if (cs < h->chunk) cs = h->chunk;
+    if (cs > h->chunk_states) cs = h->chunk_states;
+    for (int64_t c0 = 0; c0 < batch; c0 += cs, s = (s + 1) % HOST_STREAMS) {
+        const int64_t n = batch - c0 < cs ? batch - c0 : cs;
         cudaStream_t st = h->streams[s];
         CU(h, cudaMemcpyAsync(h->d_state[s], (const char*)states + c0 * sb, n * sb, cudaMemcpyHostToDevice, st));
         int rc = launch_rbd(h, h->d_state[s], h->d_rec[s], n, st);
