@@ -6,10 +6,11 @@
 //   ref:src/ForceAcc.cpp:184-219, ref:src/QPPVMPlugin.cpp:203-256  (SURVEY.md 8(a) a3-a16).
 //
 // B200 design (not the reference's: qpOASES is a sequential null-space homotopy method):
-//   * one team (TEAM = 32 or 64 threads = one CTA) owns one QP; the whole solve lives in the
-//     CTA's shared-memory slab: no H, C or KKT matrix ever touches HBM.  The record is pulled
-//     from HBM once by a single TMA bulk copy (cp.async.bulk + mbarrier) and every later read
-//     of J / M / bounds hits shared memory; outputs are written once, coalesced.
+//   * one team (TEAM = 64 threads = one CTA) owns one QP; the whole solve lives in the CTA's
+//     shared-memory slab: no H, C or KKT matrix ever touches HBM.  Shapes whose inequality scan
+//     re-reads M every iteration keep the re-read part of the record in shared memory (one TMA
+//     bulk copy, cp.async.bulk + mbarrier); the others read the record through L1/L2 and spend
+//     the shared memory on more resident CTAs.  Outputs are written once, coalesced.
 //   * whitening instead of normal equations: R from a Householder QR of the stacked task
 //     matrix [sqrt(D+eps) ; A_dense] (never forms A^T A, so the eps-regularised directions keep
 //     full relative accuracy); only the leading NB x NB block that has dense task columns is
