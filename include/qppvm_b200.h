@@ -144,6 +144,12 @@ int qppvm_solve_batch_diag(qppvm_handle* h, const double* records_dev, void* out
  * streams; returns after the outputs are in `out_host`. */
 int qppvm_solve_batch_host(qppvm_handle* h, const double* records_host, void* out_host,
                            int64_t batch);
+/* Pipelined form of qppvm_solve_batch_host: enqueues the chunked H2D / solve / D2H work and returns; consecutive
+ * calls overlap (the copies of batch i+1 run under the solve of batch i).  `records_host` must stay valid and
+ * `out_host` must not be read until qppvm_host_sync() returns; use pinned buffers.  Calls on one handle are
+ * executed in order. */
+int qppvm_solve_batch_host_async(qppvm_handle* h, const double* records_host, void* out_host, int64_t batch);
+int qppvm_host_sync(qppvm_handle* h);
 /* Latency mode: one record, host in / host out, synchronous (one control tick). */
 int qppvm_solve_one(qppvm_handle* h, const double* record_host, void* out_host);
 
@@ -172,6 +178,8 @@ int qppvm_records_from_states(qppvm_handle* h, const double* states_dev, double*
                               int64_t batch, void* cuda_stream);
 /* states (host) -> records (device, never leave it) -> solve -> outputs (host); chunked and overlapped. */
 int qppvm_solve_states_host(qppvm_handle* h, const double* states_host, void* out_host, int64_t batch);
+/* Pipelined form (see qppvm_solve_batch_host_async); completed by qppvm_host_sync(). */
+int qppvm_solve_states_host_async(qppvm_handle* h, const double* states_host, void* out_host, int64_t batch);
 
 /* Number of kernel launches issued through this handle so far. */
 int64_t qppvm_kernel_launches(const qppvm_handle* h);

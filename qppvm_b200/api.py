@@ -37,7 +37,8 @@ class CRobot(C.Structure):
 EXPORTS = ("qppvm_get_layout", "qppvm_create", "qppvm_destroy", "qppvm_last_error", "qppvm_solve_batch",
            "qppvm_solve_batch_diag", "qppvm_solve_batch_host", "qppvm_solve_one", "qppvm_kernel_launches",
            "qppvm_fp64_peak", "qppvm_supported_shapes", "qppvm_state_doubles", "qppvm_set_robot",
-           "qppvm_records_from_states", "qppvm_solve_states_host")
+           "qppvm_records_from_states", "qppvm_solve_states_host", "qppvm_solve_batch_host_async", "qppvm_host_sync",
+           "qppvm_solve_states_host_async")
 
 _lib = None
 
@@ -60,6 +61,9 @@ def load_library():
         lib.qppvm_solve_batch_diag.argtypes = [P, P, P, P, C.c_int64, P]
         lib.qppvm_solve_batch_host.argtypes = [P, P, P, C.c_int64]
         lib.qppvm_solve_one.argtypes = [P, P, P]
+        lib.qppvm_solve_batch_host_async.argtypes = [P, P, P, C.c_int64]
+        lib.qppvm_host_sync.argtypes = [P]
+        lib.qppvm_solve_states_host_async.argtypes = [P, P, P, C.c_int64]
         lib.qppvm_kernel_launches.argtypes = [P]
         lib.qppvm_kernel_launches.restype = C.c_int64
         lib.qppvm_fp64_peak.argtypes = [P, C.POINTER(C.c_double)]
@@ -155,6 +159,13 @@ class Solver:
     def solve_batch_host_ptr(self, rec_ptr: int, out_ptr: int, batch: int):
         self._check(self._lib.qppvm_solve_batch_host(self._h, rec_ptr, out_ptr, batch))
 
+    def solve_batch_host_async_ptr(self, rec_ptr: int, out_ptr: int, batch: int):
+        """Pipelined host path (pinned buffers): returns after enqueueing; read `out` only after host_sync()."""
+        self._check(self._lib.qppvm_solve_batch_host_async(self._h, rec_ptr, out_ptr, batch))
+
+    def host_sync(self):
+        self._check(self._lib.qppvm_host_sync(self._h))
+
     def solve_one(self, record: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         L = self.layout
         assert record.dtype == np.float64 and record.flags.c_contiguous and record.size == L.rec_doubles
@@ -194,6 +205,9 @@ class Solver:
 
     def solve_states_host_ptr(self, states_ptr: int, out_ptr: int, batch: int):
         self._check(self._lib.qppvm_solve_states_host(self._h, states_ptr, out_ptr, batch))
+
+    def solve_states_host_async_ptr(self, states_ptr: int, out_ptr: int, batch: int):
+        self._check(self._lib.qppvm_solve_states_host_async(self._h, states_ptr, out_ptr, batch))
 
     def solve_states_host(self, states: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         assert states.dtype == np.float64 and states.flags.c_contiguous and states.shape[1] == self.state_doubles

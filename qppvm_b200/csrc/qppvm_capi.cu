@@ -276,6 +276,20 @@ int qppvm_solve_batch(qppvm_handle* h, const double* rec, void* out, int64_t bat
 
 int qppvm_solve_batch_host(qppvm_handle* h, const double* rec, void* out, int64_t batch)
 {
+    const int rc = qppvm_solve_batch_host_async(h, rec, out, batch);
+    return rc ? rc : qppvm_host_sync(h);
+}
+
+int qppvm_host_sync(qppvm_handle* h)
+{
+    if (!h) return QPPVM_ERR_ARG;
+    CU(h, cudaSetDevice(h->desc.device));
+    for (int i = 0; i < HOST_STREAMS; ++i) CU(h, cudaStreamSynchronize(h->streams[i]));
+    return QPPVM_OK;
+}
+
+int qppvm_solve_batch_host_async(qppvm_handle* h, const double* rec, void* out, int64_t batch)
+{
     if (!h) return QPPVM_ERR_ARG;
     if (batch < 0 || (batch > 0 && (!rec || !out))) return fail(h, QPPVM_ERR_ARG, "bad batch arguments");
     CU(h, cudaSetDevice(h->desc.device));
@@ -289,8 +303,7 @@ int qppvm_solve_batch_host(qppvm_handle* h, const double* rec, void* out, int64_
         if (rc) return rc;
         CU(h, cudaMemcpyAsync((char*)out + c0 * ob, h->d_out[s], n * ob, cudaMemcpyDeviceToHost, st));
     }
-    for (int i = 0; i < HOST_STREAMS; ++i) CU(h, cudaStreamSynchronize(h->streams[i]));
-    return QPPVM_OK;
+    return QPPVM_OK;                     // per-stream staging buffers are reused in stream order: safe across calls
 }
 
 int qppvm_solve_one(qppvm_handle* h, const double* rec, void* out)
@@ -398,6 +411,12 @@ int qppvm_records_from_states(qppvm_handle* h, const double* states, double* rec
 
 int qppvm_solve_states_host(qppvm_handle* h, const double* states, void* out, int64_t batch)
 {
+    const int rc = qppvm_solve_states_host_async(h, states, out, batch);
+    return rc ? rc : qppvm_host_sync(h);
+}
+
+int qppvm_solve_states_host_async(qppvm_handle* h, const double* states, void* out, int64_t batch)
+{
     if (!h) return QPPVM_ERR_ARG;
     if (!h->has_robot) return fail(h, QPPVM_ERR_ARG, "qppvm_set_robot has not been called");
     if (batch < 0 || (batch > 0 && (!states || !out))) return fail(h, QPPVM_ERR_ARG, "bad batch arguments");
@@ -419,7 +438,6 @@ int qppvm_solve_states_host(qppvm_handle* h, const double* states, void* out, in
         if (rc) return rc;
         CU(h, cudaMemcpyAsync((char*)out + c0 * ob, h->d_out[s], n * ob, cudaMemcpyDeviceToHost, st));
     }
-    for (int i = 0; i < HOST_STREAMS; ++i) CU(h, cudaStreamSynchronize(h->streams[i]));
     return QPPVM_OK;
 }
 

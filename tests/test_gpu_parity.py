@@ -108,6 +108,15 @@ def test_host_and_single_tick_entry_points_match_device_path(torch_mod):
     assert np.array_equal(host, dev)                       # bitwise: problems are independent
     for i in (0, 17, 4999):
         assert np.array_equal(s.solve_one(recs[i]), dev[i])
+    # pipelined form: three overlapping calls, one sync
+    pin = torch.from_numpy(recs).pin_memory()
+    outs = [torch.empty((n, L.out_doubles), dtype=torch.float64).pin_memory() for n in (5000, 1234, 5000)]
+    s.solve_batch_host_async_ptr(pin.data_ptr(), outs[0].data_ptr(), 5000)
+    s.solve_batch_host_async_ptr(pin[100:].data_ptr(), outs[1].data_ptr(), 1234)
+    s.solve_batch_host_async_ptr(pin.data_ptr(), outs[2].data_ptr(), 5000)
+    s.host_sync()
+    assert np.array_equal(outs[0].numpy(), dev) and np.array_equal(outs[2].numpy(), dev)
+    assert np.array_equal(outs[1].numpy(), dev[100:1334])
 
 
 def test_shard_invariance(torch_mod):
