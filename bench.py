@@ -326,6 +326,32 @@ def main():
         sp_ok = float(((gsp["status"] == 0) & (gsp["kkt"].max(axis=1) <= 1e-6)).mean())
         e2e_states["pipelined_value"] = world * e2e_steps * batch * sp_ok / t_sp.item()
 
+    # ---- closed-loop rollout on the device: front end -> solve -> integrate per control period,
+    # nothing crossing PCIe.  Rollouts of ROLL_T periods restart from the pristine states (a 4 MB device copy, timed).
+    rollout = None
+    if desc.kind == 1:
+        ROLL_T, dt = 10, 1e-3
+        d_st0 = torch.from_numpy(h_states_all[:batch]).to(dev)
+        d_st = d_st0.clone()
+        n_roll = max(1, min(args.steps, 200) // ROLL_T)
+        solver.rollout_states(d_st, 3, dt, out=d_out[0])
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(stream)
+        for i in range(n_roll):
+            d_st.copy_(d_st0)
+            solver.rollout_states(d_st, ROLL_T, dt, out=d_out[0])
+        r1.record(stream)
+        barrier()
+        t_roll = torch.tensor([r0.elapsed_time(r1) * 1e-3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_roll, op=dist.ReduceOp.MAX)
+        gr = api.split_out(L, d_out[0].cpu().numpy())
+        rollout = {"value": world * n_roll * ROLL_T * batch / t_roll.item(), "unit": "state-ticks/s",
+                   "ticks_per_rollout": ROLL_T, "rollouts": n_roll, "dt": dt,
+                   "last_tick_converged_frac": float(((gr["status"] == 0) & (gr["kkt"].max(axis=1) <= 1e-6)).mean()),
+                   "api": "qppvm_rollout_states (device-resident states; 3 kernels per tick and lane, 4 lanes)"}
+
     # ---- N > 1: the same shards fed from rank 0 over NCCL (scatter records, gather outputs), device to device
     sg = None
     if world > 1:
@@ -388,6 +414,8 @@ def main():
     if sg:
         line["scatter_gather"] = sg
     line["e2e_pipelined"] = e2e_pipe
+    if rollout:
+        line["rollout"] = rollout
     if e2e_states:
         line["e2e_states"] = e2e_states
 

@@ -181,6 +181,15 @@ int qppvm_solve_states_host(qppvm_handle* h, const double* states_host, void* ou
 /* Pipelined form (see qppvm_solve_batch_host_async); completed by qppvm_host_sync(). */
 int qppvm_solve_states_host_async(qppvm_handle* h, const double* states_host, void* out_host, int64_t batch);
 
+/* ---- command side: integrate the solved accelerations, closed-loop rollouts on the device ----
+ * qppvm_integrate_states: states (device, in/out) advance by one period dt with the q-ddot of `out` (device, the block
+ * qppvm_solve_batch wrote for the same states): q += dt*qd + dt^2/2*qdd, qd += dt*qdd, floating base likewise
+ * (ref:src/ForceAcc.cpp:225-226).  A state whose solve failed is left as it is (ref:src/ForceAcc.cpp:189-193).
+ * qppvm_rollout_states: `ticks` control periods of front end -> 2-level solve -> integrate, all on `stream`, nothing
+ * crossing PCIe; `out` holds the last tick's solutions.  Task references stay those stored in the states. */
+int qppvm_integrate_states(qppvm_handle* h, double* states_dev, const void* out_dev, double dt, int64_t batch, void* stream);
+int qppvm_rollout_states(qppvm_handle* h, double* states_dev, void* out_dev, int ticks, double dt, int64_t batch, void* stream);
+
 /* Number of kernel launches issued through this handle so far. */
 int64_t qppvm_kernel_launches(const qppvm_handle* h);
 /* Measures the FP64 FMA peak of the device (TFLOP/s) with a register-resident DFMA

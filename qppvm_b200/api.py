@@ -38,7 +38,7 @@ EXPORTS = ("qppvm_get_layout", "qppvm_create", "qppvm_destroy", "qppvm_last_erro
            "qppvm_solve_batch_diag", "qppvm_solve_batch_host", "qppvm_solve_one", "qppvm_kernel_launches",
            "qppvm_fp64_peak", "qppvm_supported_shapes", "qppvm_state_doubles", "qppvm_set_robot",
            "qppvm_records_from_states", "qppvm_solve_states_host", "qppvm_solve_batch_host_async", "qppvm_host_sync",
-           "qppvm_solve_states_host_async")
+           "qppvm_solve_states_host_async", "qppvm_integrate_states", "qppvm_rollout_states")
 
 _lib = None
 
@@ -64,6 +64,8 @@ def load_library():
         lib.qppvm_solve_batch_host_async.argtypes = [P, P, P, C.c_int64]
         lib.qppvm_host_sync.argtypes = [P]
         lib.qppvm_solve_states_host_async.argtypes = [P, P, P, C.c_int64]
+        lib.qppvm_integrate_states.argtypes = [P, P, P, C.c_double, C.c_int64, P]
+        lib.qppvm_rollout_states.argtypes = [P, P, P, C.c_int, C.c_double, C.c_int64, P]
         lib.qppvm_kernel_launches.argtypes = [P]
         lib.qppvm_kernel_launches.restype = C.c_int64
         lib.qppvm_fp64_peak.argtypes = [P, C.POINTER(C.c_double)]
@@ -202,6 +204,27 @@ class Solver:
         st = torch.cuda.current_stream(states.device) if stream is None else stream
         self._check(self._lib.qppvm_records_from_states(self._h, states.data_ptr(), records.data_ptr(), B, st.cuda_stream))
         return records
+
+    def integrate_states(self, states, out, dt: float, stream=None):
+        """In place: advance `states` (cuda float64) by dt with the accelerations in `out` (solve_batch's block)."""
+        import torch
+        assert states.is_cuda and states.dtype == torch.float64 and states.is_contiguous() and out.is_contiguous()
+        assert states.shape[1] == self.state_doubles and out.shape == (states.shape[0], self.layout.out_doubles)
+        st = torch.cuda.current_stream(states.device) if stream is None else stream
+        self._check(self._lib.qppvm_integrate_states(self._h, states.data_ptr(), out.data_ptr(), dt, states.shape[0], st.cuda_stream))
+        return states
+
+    def rollout_states(self, states, ticks: int, dt: float, out=None, stream=None):
+        """`ticks` control periods of front end -> solve -> integrate on the device; `states` is updated in place,
+        the returned block holds the last tick's solutions."""
+        import torch
+        assert states.is_cuda and states.dtype == torch.float64 and states.is_contiguous()
+        assert states.shape[1] == self.state_doubles
+        if out is None:
+            out = torch.empty((states.shape[0], self.layout.out_doubles), dtype=torch.float64, device=states.device)
+        st = torch.cuda.current_stream(states.device) if stream is None else stream
+        self._check(self._lib.qppvm_rollout_states(self._h, states.data_ptr(), out.data_ptr(), ticks, dt, states.shape[0], st.cuda_stream))
+        return out
 
     def solve_states_host_ptr(self, states_ptr: int, out_ptr: int, batch: int):
         self._check(self._lib.qppvm_solve_states_host(self._h, states_ptr, out_ptr, batch))

@@ -41,6 +41,7 @@ const ShapeEntry g_shapes[] = {
 constexpr int N_SHAPES = sizeof(g_shapes) / sizeof(g_shapes[0]);
 
 constexpr int HOST_STREAMS = 4;
+constexpr int64_t ROLL_LANE = 16384;       // states per lane of the on-device rollout (record scratch <= 4 x 0.3 GB)
 
 }  // namespace
 
@@ -59,6 +60,8 @@ struct qppvm_handle {
     int64_t chunk_states;                  // states per chunk of the state front end (transfers are 10x smaller)
     double* d_state[HOST_STREAMS];         // host-path staging for the state front end
     RobotTables rob; RbdShape rsh; void* rob_blob; bool has_robot;
+    double* d_roll; int64_t roll_cap;      // record scratch of the on-device rollout: HOST_STREAMS lanes of roll_cap
+    cudaEvent_t ev_fork, ev_join[HOST_STREAMS];
     double* d_one_rec; unsigned char* d_one_out;
     double* h_one_rec; unsigned char* h_one_out;   // pinned staging for latency mode
     cudaStream_t one_stream;
@@ -249,7 +252,8 @@ int qppvm_destroy(qppvm_handle* h)
     }
     if (h->one_stream) cudaStreamDestroy(h->one_stream);
     for (int i = 0; i < HOST_STREAMS; ++i) cudaFree(h->d_state[i]);
-    cudaFree(h->rob_blob);
+    cudaFree(h->rob_blob); cudaFree(h->d_roll);
+    if (h->ev_fork) { cudaEventDestroy(h->ev_fork); for (int i = 0; i < HOST_STREAMS; ++i) cudaEventDestroy(h->ev_join[i]); }
     cudaFree(h->d_one_rec); cudaFree(h->d_one_out);
     cudaFreeHost(h->h_one_rec); cudaFreeHost(h->h_one_out);
     cudaFree(h->counters);
@@ -407,6 +411,76 @@ int qppvm_records_from_states(qppvm_handle* h, const double* states, double* rec
     if (batch < 0 || (batch > 0 && (!states || !recs))) return fail(h, QPPVM_ERR_ARG, "bad batch arguments");
     CU(h, cudaSetDevice(h->desc.device));
     return launch_rbd(h, states, recs, batch, (cudaStream_t)stream);
+}
+
+static int launch_integrate(qppvm_handle* h, double* states, const void* out, double dt, int64_t batch, cudaStream_t st)
+{
+    if (batch <= 0) return QPPVM_OK;
+    const int threads = 128, grid = (int)((batch + threads - 1) / threads);
+    integrate_states_kernel<<<grid, threads, 0, st>>>(h->rsh, states, (const double*)out, h->L.out_bytes / 8,
+                                                      h->L.n_x + h->L.n_a, dt, (long long)batch);
+    CU(h, cudaGetLastError());
+    h->launches += 1;
+    return QPPVM_OK;
+}
+
+int qppvm_integrate_states(qppvm_handle* h, double* states, const void* out, double dt, int64_t batch, void* stream)
+{
+    if (!h) return QPPVM_ERR_ARG;
+    if (!h->has_robot) return fail(h, QPPVM_ERR_ARG, "qppvm_set_robot has not been called");
+    if (batch < 0 || (batch > 0 && (!states || !out)) || !(dt > 0.0)) return fail(h, QPPVM_ERR_ARG, "bad arguments");
+    CU(h, cudaSetDevice(h->desc.device));
+    return launch_integrate(h, states, out, dt, batch, (cudaStream_t)stream);
+}
+
+int qppvm_rollout_states(qppvm_handle* h, double* states, void* out, int ticks, double dt, int64_t batch, void* stream)
+{
+    if (!h) return QPPVM_ERR_ARG;
+    if (!h->has_robot) return fail(h, QPPVM_ERR_ARG, "qppvm_set_robot has not been called");
+    if (batch < 0 || ticks < 0 || (batch > 0 && (!states || !out)) || !(dt > 0.0)) return fail(h, QPPVM_ERR_ARG, "bad arguments");
+    if (batch == 0 || ticks == 0) return QPPVM_OK;
+    CU(h, cudaSetDevice(h->desc.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // States are independent, so the batch is cut into lanes that run all their ticks back to back on the handle's
+    // worker streams: the tail of one lane's solve overlaps the front end / solve of the others (a single stream
+    // leaves the SMs idle in every kernel's tail: 4.0 M -> state-ticks/s measured in profiles/README.md).
+    int64_t lane = ((batch + HOST_STREAMS - 1) / HOST_STREAMS + 63) / 64 * 64;
+    if (lane < 512) lane = 512;
+    if (lane > ROLL_LANE) lane = ROLL_LANE;
+    if (lane > h->roll_cap) {
+        CU(h, cudaDeviceSynchronize());
+        cudaFree(h->d_roll); h->d_roll = nullptr; h->roll_cap = 0;
+        CU(h, cudaMalloc(&h->d_roll, sizeof(double) * (size_t)h->L.rec_doubles * lane * HOST_STREAMS));
+        h->roll_cap = lane;
+    }
+    if (!h->ev_fork) {
+        CU(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        for (int i = 0; i < HOST_STREAMS; ++i) CU(h, cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+    }
+    const size_t sd = h->rsh.state_doubles, ob = (size_t)h->L.out_bytes;
+    CU(h, cudaEventRecord(h->ev_fork, st));
+    int used = 0, w = 0;
+    for (int64_t c0 = 0; c0 < batch; c0 += lane, w = (w + 1) % HOST_STREAMS) {
+        const int64_t n = batch - c0 < lane ? batch - c0 : lane;
+        cudaStream_t ws = h->streams[w];
+        if (used < HOST_STREAMS && w == used) { CU(h, cudaStreamWaitEvent(ws, h->ev_fork, 0)); ++used; }
+        double* s = states + c0 * sd;
+        double* rec = h->d_roll + (size_t)w * h->roll_cap * h->L.rec_doubles;
+        unsigned char* o = (unsigned char*)out + c0 * ob;
+        for (int t = 0; t < ticks; ++t) {
+            int rc = launch_rbd(h, s, rec, n, ws);
+            if (rc) return rc;
+            rc = launch(h, rec, o, nullptr, n, ws, h->counters + w);
+            if (rc) return rc;
+            rc = launch_integrate(h, s, o, dt, n, ws);
+            if (rc) return rc;
+        }
+    }
+    for (int i = 0; i < used; ++i) {
+        CU(h, cudaEventRecord(h->ev_join[i], h->streams[i]));
+        CU(h, cudaStreamWaitEvent(st, h->ev_join[i], 0));
+    }
+    return QPPVM_OK;
 }
 
 int qppvm_solve_states_host(qppvm_handle* h, const double* states, void* out, int64_t batch)

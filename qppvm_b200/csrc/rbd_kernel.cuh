@@ -291,4 +291,53 @@ rbd_records_kernel(RobotTables rob, RbdShape sh, const double* __restrict__ stat
     }
 }
 
+// Command side: advance every state by one control period with the solved generalised
+// acceleration -- the integration ref:src/ForceAcc.cpp:225-226 carries (commented out there; the plugin sends the
+// model state as the position reference instead): q += dt*qd + dt^2/2*qdd, qd += dt*qdd; the floating base the same
+// way in the world-aligned convention of the front end (position; rotation through the exponential of the world
+// rotation vector dt*w + dt^2/2*alpha).  A state whose solve failed is left untouched (nothing is commanded,
+// ref:src/ForceAcc.cpp:189-193).  One thread per state; 2 x state bytes + n_v doubles of traffic.
+__global__ void __launch_bounds__(128)
+integrate_states_kernel(RbdShape sh, double* __restrict__ states, const double* __restrict__ out, int out_doubles,
+                        int trailer_off, double dt, long long batch)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= batch) return;
+    double* st = states + idx * (size_t)sh.state_doubles;
+    const double* x = out + idx * (size_t)out_doubles;
+    if (reinterpret_cast<const int*>(x + trailer_off)[0] != 0) return;
+    const double h2 = 0.5 * dt * dt;
+    double* tw = st + sh.s_tw;
+    double th[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        st[sh.s_p0 + k] += dt * tw[k] + h2 * x[k];
+        th[k] = dt * tw[3 + k] + h2 * x[3 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) tw[k] += dt * x[k];
+    // R0 <- exp([th]x) R0  (Rodrigues; series for tiny angles)
+    const double a2 = th[0] * th[0] + th[1] * th[1] + th[2] * th[2], ang = sqrt(a2);
+    const double A = a2 > 1e-12 ? sin(ang) / ang : 1.0 - a2 / 6.0;
+    const double Bc = a2 > 1e-12 ? (1.0 - cos(ang)) / a2 : 0.5 - a2 / 24.0;
+    double R[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = st[sh.s_R0 + k];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double v[3] = {R[c], R[3 + c], R[6 + c]};
+        double k1[3], k2[3];
+        cross3(th, v, k1); cross3(th, k1, k2);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) st[sh.s_R0 + 3 * r + c] = v[r] + A * k1[r] + Bc * k2[r];
+    }
+    const double* qdd = x + 6;
+#pragma unroll 1
+    for (int a = 0; a < sh.n_a; ++a) {
+        const double v = st[sh.s_qd + a], acc = qdd[a];
+        st[sh.s_q + a] += dt * v + h2 * acc;
+        st[sh.s_qd + a] = v + dt * acc;
+    }
+}
+
 }  // namespace qppvm

@@ -355,3 +355,40 @@ def records_from_states(desc: Desc, states: np.ndarray) -> np.ndarray:
 
 def config_seed(config_index: int) -> int:
     return BASE_SEED + 1000 * config_index
+
+
+def integrate_states(desc: Desc, states: np.ndarray, out: np.ndarray, dt: float) -> np.ndarray:
+    """Numpy mirror of integrate_states_kernel (the integration ref:src/ForceAcc.cpp:225-226
+    carries): one control period with the solved acceleration; failed solves leave their state untouched.
+    `out` is the solver's output block viewed as float64 (B, out_doubles)."""
+    from .layout import layout
+    L, o = layout(desc), state_offsets(desc)
+    nv, na = L.n_v, desc.n_a
+    st = states.copy()
+    trailer = (L.n_x + na)
+    ok = out[:, trailer:trailer + 1].copy().view(np.int32)[:, 0] == 0
+    x = out[:, :nv]
+    h2 = 0.5 * dt * dt
+    tw = states[:, o["tw"][0]:o["tw"][1]]
+    p0 = states[:, o["p0"][0]:o["p0"][1]] + dt * tw[:, :3] + h2 * x[:, :3]
+    th = dt * tw[:, 3:] + h2 * x[:, 3:6]
+    a2 = (th * th).sum(axis=1)
+    ang = np.sqrt(a2)
+    big = a2 > 1e-12
+    safe = np.where(big, ang, 1.0)
+    A = np.where(big, np.sin(safe) / safe, 1.0 - a2 / 6.0)
+    Bc = np.where(big, (1.0 - np.cos(safe)) / np.where(big, a2, 1.0), 0.5 - a2 / 24.0)
+    R = states[:, o["R0"][0]:o["R0"][1]].reshape(-1, 3, 3)
+    thb = np.broadcast_to(th[:, None, :], R.shape)
+    Rc = R.transpose(0, 2, 1)                                  # rows = columns of R
+    k1 = np.cross(thb, Rc); k2 = np.cross(thb, k1)
+    Rn = (Rc + A[:, None, None] * k1 + Bc[:, None, None] * k2).transpose(0, 2, 1)
+    q = states[:, o["q"][0]:o["q"][1]]; qd = states[:, o["qd"][0]:o["qd"][1]]
+    new = states.copy()
+    new[:, o["p0"][0]:o["p0"][1]] = p0
+    new[:, o["tw"][0]:o["tw"][1]] = tw + dt * x[:, :6]
+    new[:, o["R0"][0]:o["R0"][1]] = Rn.reshape(-1, 9)
+    new[:, o["q"][0]:o["q"][1]] = q + dt * qd + h2 * x[:, 6:nv]
+    new[:, o["qd"][0]:o["qd"][1]] = qd + dt * x[:, 6:nv]
+    st[ok] = new[ok]
+    return st
