@@ -28,6 +28,9 @@
 #include <stdint.h>
 #include "../../include/qppvm_b200.h"
 
+#ifndef QPPVM_SPLIT
+#define QPPVM_SPLIT 1
+#endif
 namespace qppvm {
 
 // Active-set capacity KMAX (eq + ineq, <= 32 so one warp lane per active row), per problem shape.
@@ -206,6 +209,10 @@ struct ForceAcc {
     }
     static constexpr int MD0 = 6, MD1 = 6 * NC;                // dense task rows of level 0 / 1
     static constexpr int EXTRA = 0;                            // policy scratch in the slab (doubles)
+    // The two factorisations depend only on the record: for the unstaged shapes they run in their own kernel
+    // (qp_factor_kernel) and reach the solve through a workspace in global memory (L2-resident), which takes the
+    // 25 KB of unrolled factorisation code out of the instruction-fetch-bound solve kernel (profiles/README.md).
+    static constexpr bool SPLIT_FACTOR = QPPVM_SPLIT && !TLIM;
     // Staging (see Slab::STAGE): shapes whose inequality scan re-reads M every iteration (torque-limit rows) keep
     // the TAIL of the record [M | h | Jdqd | rhs | tau limits | cones | boxes] (one TMA bulk copy) plus the linear
     // contact-Jacobian rows in shared memory; the task Jacobians (read once per level) stay in global memory.
@@ -398,6 +405,7 @@ struct Torque {
     static constexpr int KMAX = kmax_for(6, NA, N);
     static constexpr int O_A0 = NA * LDM, O_T = O_A0 + 6 * NA;
     static constexpr int EXTRA = O_T + NA * LDM + ((O_T + NA * LDM) & 1);
+    static constexpr bool SPLIT_FACTOR = false;
 
     __device__ static __forceinline__ int n_eq(int level) { return level == 0 ? 0 : 6; }
     __device__ static __forceinline__ int eq_row(int, int e) { return ROW_OPT + e; }
@@ -572,6 +580,8 @@ struct Slab {
     static constexpr int O_CSTATE = O_STATE + 2 + KP;     // bytes
     static constexpr int O_EXT = O_CSTATE + ((P::NROWS + 15) & ~15) / 8;   // policy scratch
     static constexpr int DOUBLES = O_EXT + P::EXTRA;
+    static constexpr int WS_LEVEL = SZ_J + 2 * VEC;   // factor workspace per level: J | u0 | jd
+    static constexpr int WS = 2 * WS_LEVEL;
     static constexpr int BYTES = DOUBLES * 8;
 };
 
@@ -588,6 +598,10 @@ struct Solver {
     __device__ static __forceinline__ double* grec_()         // the record in global memory
     {
         return *reinterpret_cast<double**>(reinterpret_cast<double*>(g_smem) + S::O_J - 2);
+    }
+    __device__ static __forceinline__ double*& ws_()           // this problem's factor workspace (global memory)
+    {
+        return *reinterpret_cast<double**>(reinterpret_cast<double*>(g_smem) + S::O_J - 1);
     }
     __device__ static __forceinline__ double* rec_()
     {
@@ -994,16 +1008,10 @@ struct Solver {
         tm::sync();
     }
 
-    // One level: returns status.  On return x holds the level solution.
-    // The KKT residual of the level is left in red[12].
-    __device__ static __noinline__ int solve_level(int level, double eps_reg, int n_reg_steps, int max_iter, double* ydiag)
+    // Task rows of `level` -> J, u0, jd (xp must hold the proximal centre: zero at the start of a level).
+    __device__ static __forceinline__ int load_and_factor(int level, double eps)
     {
         QP_BIND
-        const double eps = P::regularised(level) ? eps_reg : 0.0;
-        const int steps = eps > 0.0 ? n_reg_steps : 0;
-        for (int i = tid; i < N; i += TEAM) xp[i] = 0.0;
-        if (tid == 0) st[2] = 0;
-        tm::sync();
         const int md = P::template load_tasks<TEAM>(rec, ext, level, Ad, dg, db, tid);
         tm::sync();
         // One instantiation serves both levels when level 1 is at most twice as tall (level 0 is padded with zero
@@ -1015,6 +1023,29 @@ struct Solver {
             tm::sync();
         }
         if (level == 0) factor<MDF0>(eps); else factor<P::MD1>(eps);   // Ad dead after this
+        return md;
+    }
+
+    // One level: returns status.  On return x holds the level solution.
+    // The KKT residual of the level is left in red[12].
+    __device__ static __noinline__ int solve_level(int level, double eps_reg, int n_reg_steps, int max_iter, double* ydiag)
+    {
+        QP_BIND
+        const double eps = P::regularised(level) ? eps_reg : 0.0;
+        const int steps = eps > 0.0 ? n_reg_steps : 0;
+        for (int i = tid; i < N; i += TEAM) xp[i] = 0.0;
+        if (tid == 0) st[2] = 0;
+        tm::sync();
+        int md;
+        if constexpr (P::SPLIT_FACTOR) {
+            md = level == 0 ? P::MD0 : P::MD1;
+            const double* wsl = ws_() + level * S::WS_LEVEL;
+            for (int i = tid; i < S::SZ_J; i += TEAM) Jm[i] = wsl[i];
+            for (int i = tid; i < N; i += TEAM) { u0[i] = wsl[S::SZ_J + i]; jd[i] = wsl[S::SZ_J + S::VEC + i]; }
+            tm::sync();
+        } else {
+            md = load_and_factor(level, eps);
+        }
         reset_active_set();
         // ---- equalities first (dyn-feas, then level-0 optimality rows), never dropped
         int status = add_equalities(level, max_iter);
@@ -1170,7 +1201,7 @@ struct Solver {
 template <class P, int TEAM>
 __global__ void __launch_bounds__(TEAM)
 qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out, double* __restrict__ diag,
-                long long batch, Params prm, unsigned long long* __restrict__ counter)
+                long long batch, Params prm, unsigned long long* __restrict__ counter, double* __restrict__ ws)
 {
     using SV = Solver<P, TEAM>;
     constexpr int N = P::N;
@@ -1193,6 +1224,7 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
             if ((long long)i < batch) {
                 const double* gr = recs + i * (size_t)P::REC;
                 *reinterpret_cast<const double**>(reinterpret_cast<double*>(g_smem) + Slab<P>::O_J - 2) = gr;
+                if (P::SPLIT_FACTOR) SV::ws_() = ws + i * (size_t)Slab<P>::WS;
                 if (Slab<P>::STAGE)                            // one TMA bulk copy stages the tail of the record
                     bulk_load(SV::rec_(), gr + P::STAGE_FROM, (uint32_t)((P::REC - P::STAGE_FROM) * sizeof(double)), SV::mbar_());
             }
@@ -1252,6 +1284,33 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
             tr[6] = __float_as_uint(kkt0); tr[7] = __float_as_uint(kkt1);
         }
         __syncthreads();                                       // slab (incl. s_idx, rec) is reused by the next problem
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Factor kernel (shapes with P::SPLIT_FACTOR): one CTA per (problem, level) pair, grid-stride.  Writes
+// J | u0 | jd of each level into the workspace the solve kernel reads.
+// ------------------------------------------------------------------------------------------
+template <class P, int TEAM>
+__global__ void __launch_bounds__(TEAM)
+qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long long batch, Params prm)
+{
+    using SV = Solver<P, TEAM>;
+    using S = Slab<P>;
+    constexpr int N = P::N;
+    const int tid = threadIdx.x;
+#pragma unroll 1
+    for (long long pair = blockIdx.x; pair < 2 * batch; pair += gridDim.x) {
+        const long long idx = pair >> 1;
+        const int level = (int)(pair & 1);
+        if (tid == 0) *reinterpret_cast<const double**>(reinterpret_cast<double*>(g_smem) + S::O_J - 2) = recs + idx * (size_t)P::REC;
+        for (int i = tid; i < N; i += TEAM) SV::xp_()[i] = 0.0;
+        __syncthreads();
+        SV::load_and_factor(level, P::regularised(level) ? prm.eps_reg : 0.0);
+        double* wsl = ws + idx * (size_t)S::WS + level * S::WS_LEVEL;
+        for (int i = tid; i < S::SZ_J; i += TEAM) wsl[i] = SV::Jm_()[i];
+        for (int i = tid; i < N; i += TEAM) { wsl[S::SZ_J + i] = SV::u0_()[i]; wsl[S::SZ_J + S::VEC + i] = SV::jd_()[i]; }
+        __syncthreads();
     }
 }
 

@@ -20,6 +20,8 @@ struct ShapeEntry {
     int kind, n_a, n_c, flags;
     const void* kernel;          // qp_solve_kernel<P, 64>: 64 threads (one CTA) per problem
     int slab_bytes;
+    const void* factor_kernel;   // qp_factor_kernel<P, 64> for shapes that factor in a separate launch, else null
+    int ws_doubles;              // factor workspace per problem (doubles)
 };
 
 // Instantiated problem shapes (BASELINE.json configs).
@@ -27,7 +29,8 @@ template <class P>
 constexpr ShapeEntry entry()
 {
     return ShapeEntry{P::KIND, P::NA, P::NC, P::FLAGS,
-                      (const void*)&qp_solve_kernel<P, 64>, Slab<P>::BYTES};
+                      (const void*)&qp_solve_kernel<P, 64>, Slab<P>::BYTES,
+                      P::SPLIT_FACTOR ? (const void*)&qp_factor_kernel<P, 64> : nullptr, Slab<P>::WS};
 }
 constexpr int F_ALL = QPPVM_FLAG_FRICTION_CONES | QPPVM_FLAG_TORQUE_LIMITS;
 const ShapeEntry g_shapes[] = {
@@ -41,6 +44,8 @@ const ShapeEntry g_shapes[] = {
 constexpr int N_SHAPES = sizeof(g_shapes) / sizeof(g_shapes[0]);
 
 constexpr int HOST_STREAMS = 4;
+constexpr int N_SLOTS = HOST_STREAMS + 2;  // launch slots: host / rollout streams, caller's stream, spare
+constexpr int64_t WS_CHUNK = 8192;         // problems per factor-workspace pass (94 MB for config [1]: L2-resident)
 constexpr int64_t ROLL_LANE = 16384;       // states per lane of the on-device rollout (record scratch <= 4 x 0.3 GB)
 
 }  // namespace
@@ -52,7 +57,9 @@ struct qppvm_handle {
     const void* kernel;
     int team;                              // threads per problem (= CTA size)
     int sm_count, ctas_per_sm;
-    unsigned long long* counters;          // HOST_STREAMS + 2 device counters
+    unsigned long long* counters;          // N_SLOTS device counters
+    double* ws[N_SLOTS]; int64_t ws_cap[N_SLOTS];   // factor workspaces, one per launch slot, allocated on first use
+    int factor_ctas_per_sm;
     cudaStream_t streams[HOST_STREAMS];
     double* d_rec[HOST_STREAMS];
     unsigned char* d_out[HOST_STREAMS];
@@ -88,18 +95,44 @@ int fail(qppvm_handle* h, int code, const char* fmt, ...)
     } while (0)
 
 int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t batch,
-           cudaStream_t st, unsigned long long* counter)
+           cudaStream_t st, int slot, bool dynamic = true)
 {
     if (batch <= 0) return QPPVM_OK;
-    if (counter) CU(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
-    long long want = batch;                                   // one warp (= one CTA) per problem in flight
-    long long cap = (long long)h->sm_count * h->ctas_per_sm;
-    int grid = (int)(want < cap ? want : cap);
+    unsigned long long* counter = dynamic ? h->counters + slot : nullptr;   // null: static round-robin schedule
+    const long long cap = (long long)h->sm_count * h->ctas_per_sm;
     Params prm{h->desc.eps_regularisation * QPPVM_QPOASES_EPS_REG, h->desc.n_reg_steps, h->desc.max_iter};
-    long long b = batch;
-    void* args[] = {(void*)&rec, (void*)&out, (void*)&diag, (void*)&b, (void*)&prm, (void*)&counter};
-    CU(h, cudaLaunchKernel(h->kernel, dim3(grid), dim3(h->team), args, (size_t)h->shape->slab_bytes, st));
-    h->launches += 1;
+    const bool split = h->shape->factor_kernel != nullptr;
+    const int64_t pass = split ? WS_CHUNK : batch;
+    if (split) {
+        const int64_t need = batch < WS_CHUNK ? batch : WS_CHUNK;
+        if (need > h->ws_cap[slot]) {
+            // growing a slot's workspace: earlier launches on this slot may still be reading the old one
+            CU(h, cudaStreamSynchronize(st));
+            cudaFree(h->ws[slot]); h->ws[slot] = nullptr; h->ws_cap[slot] = 0;
+            const int64_t capn = need < 1024 ? 1024 : need;
+            CU(h, cudaMalloc(&h->ws[slot], sizeof(double) * (size_t)h->shape->ws_doubles * capn));
+            h->ws_cap[slot] = capn;
+        }
+    }
+    for (int64_t c0 = 0; c0 < batch; c0 += pass) {
+        long long b = batch - c0 < pass ? batch - c0 : pass;
+        const double* r = rec + c0 * (size_t)h->L.rec_doubles;
+        unsigned char* o = (unsigned char*)out + c0 * (size_t)h->L.out_bytes;
+        double* dgp = diag ? diag + c0 * (size_t)h->L.diag_doubles : nullptr;
+        double* ws = split ? h->ws[slot] : nullptr;
+        if (split) {
+            const long long fcap = (long long)h->sm_count * h->factor_ctas_per_sm;
+            const int fgrid = (int)(2 * b < fcap ? 2 * b : fcap);
+            void* fargs[] = {(void*)&r, (void*)&ws, (void*)&b, (void*)&prm};
+            CU(h, cudaLaunchKernel(h->shape->factor_kernel, dim3(fgrid), dim3(h->team), fargs, (size_t)h->shape->slab_bytes, st));
+            h->launches += 1;
+        }
+        if (counter) CU(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+        const int grid = (int)(b < cap ? b : cap);
+        void* args[] = {(void*)&r, (void*)&o, (void*)&dgp, (void*)&b, (void*)&prm, (void*)&counter, (void*)&ws};
+        CU(h, cudaLaunchKernel(h->kernel, dim3(grid), dim3(h->team), args, (size_t)h->shape->slab_bytes, st));
+        h->launches += 1;
+    }
     return QPPVM_OK;
 }
 
@@ -222,7 +255,13 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->kernel, h->team, (size_t)sh->slab_bytes));
     if (occ < 1) { fail(nullptr, QPPVM_ERR_CUDA, "kernel does not fit on an SM (%d B smem)", sh->slab_bytes); delete h; return QPPVM_ERR_CUDA; }
     h->ctas_per_sm = occ;
-    CUC(cudaMalloc(&h->counters, sizeof(unsigned long long) * (HOST_STREAMS + 2)));
+    if (sh->factor_kernel) {
+        CUC(cudaFuncSetAttribute(sh->factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh->slab_bytes));
+        CUC(cudaFuncSetAttribute(sh->factor_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh->factor_kernel, h->team, (size_t)sh->slab_bytes));
+        h->factor_ctas_per_sm = occ < 1 ? 1 : occ;
+    }
+    CUC(cudaMalloc(&h->counters, sizeof(unsigned long long) * N_SLOTS));
     // host path: records per pipelined chunk (H2D of chunk i+1 overlaps the solve of chunk i); QPPVM_CHUNK overrides
     h->chunk = 1024;
     if (const char* e = getenv("QPPVM_CHUNK")) { const long c = atol(e); if (c >= 64 && c <= (1 << 20)) h->chunk = c; }
@@ -257,6 +296,7 @@ int qppvm_destroy(qppvm_handle* h)
     cudaFree(h->d_one_rec); cudaFree(h->d_one_out);
     cudaFreeHost(h->h_one_rec); cudaFreeHost(h->h_one_out);
     cudaFree(h->counters);
+    for (int i = 0; i < N_SLOTS; ++i) cudaFree(h->ws[i]);
     delete h;
     return QPPVM_OK;
 }
@@ -270,7 +310,7 @@ int qppvm_solve_batch_diag(qppvm_handle* h, const double* rec, void* out, double
     if (((uintptr_t)rec & 15) || ((uintptr_t)out & 7) || ((uintptr_t)diag & 7))
         return fail(h, QPPVM_ERR_ARG, "records must be 16-byte aligned (TMA bulk copy), outputs 8-byte aligned");
     CU(h, cudaSetDevice(h->desc.device));
-    return launch(h, rec, out, diag, batch, (cudaStream_t)stream, h->counters + HOST_STREAMS);
+    return launch(h, rec, out, diag, batch, (cudaStream_t)stream, HOST_STREAMS);
 }
 
 int qppvm_solve_batch(qppvm_handle* h, const double* rec, void* out, int64_t batch, void* stream)
@@ -303,7 +343,7 @@ int qppvm_solve_batch_host_async(qppvm_handle* h, const double* rec, void* out, 
         const int64_t n = batch - c0 < h->chunk ? batch - c0 : h->chunk;
         cudaStream_t st = h->streams[s];
         CU(h, cudaMemcpyAsync(h->d_rec[s], (const char*)rec + c0 * rb, n * rb, cudaMemcpyHostToDevice, st));
-        int rc = launch(h, h->d_rec[s], h->d_out[s], nullptr, n, st, h->counters + s);
+        int rc = launch(h, h->d_rec[s], h->d_out[s], nullptr, n, st, s);
         if (rc) return rc;
         CU(h, cudaMemcpyAsync((char*)out + c0 * ob, h->d_out[s], n * ob, cudaMemcpyDeviceToHost, st));
     }
@@ -319,7 +359,7 @@ int qppvm_solve_one(qppvm_handle* h, const double* rec, void* out)
     // addresses directly (UVA): the kernel's TMA bulk copy pulls it across PCIe and the outputs are stored straight
     // back into pinned host memory, so there is no memcpy / memset node before or after the kernel.
     memcpy(h->h_one_rec, rec, rb);
-    int rc = launch(h, h->h_one_rec, h->h_one_out, nullptr, 1, h->one_stream, nullptr);
+    int rc = launch(h, h->h_one_rec, h->h_one_out, nullptr, 1, h->one_stream, HOST_STREAMS + 1, false);
     if (rc) return rc;
     CU(h, cudaStreamSynchronize(h->one_stream));
     memcpy(out, h->h_one_out, ob);
@@ -470,7 +510,7 @@ int qppvm_rollout_states(qppvm_handle* h, double* states, void* out, int ticks, 
         for (int t = 0; t < ticks; ++t) {
             int rc = launch_rbd(h, s, rec, n, ws);
             if (rc) return rc;
-            rc = launch(h, rec, o, nullptr, n, ws, h->counters + w);
+            rc = launch(h, rec, o, nullptr, n, ws, w);
             if (rc) return rc;
             rc = launch_integrate(h, s, o, dt, n, ws);
             if (rc) return rc;
@@ -508,7 +548,7 @@ int qppvm_solve_states_host_async(qppvm_handle* h, const double* states, void* o
         CU(h, cudaMemcpyAsync(h->d_state[s], (const char*)states + c0 * sb, n * sb, cudaMemcpyHostToDevice, st));
         int rc = launch_rbd(h, h->d_state[s], h->d_rec[s], n, st);
         if (rc) return rc;
-        rc = launch(h, h->d_rec[s], h->d_out[s], nullptr, n, st, h->counters + s);
+        rc = launch(h, h->d_rec[s], h->d_out[s], nullptr, n, st, s);
         if (rc) return rc;
         CU(h, cudaMemcpyAsync((char*)out + c0 * ob, h->d_out[s], n * ob, cudaMemcpyDeviceToHost, st));
     }
