@@ -586,6 +586,102 @@ struct Slab {
 };
 
 // ------------------------------------------------------------------------------------------
+// Whitening factorisation, shared by the in-kernel path (one 64-thread team, lane = thread id) and the
+// lane-batched factor kernel (several factorisations side by side in one CTA, GS = NB + 1 lanes each).
+// R^T R = D + eps I + Ad^T Ad via Householder QR of the stacked matrix [sqrt(D+eps); Ad], then J = R^-1, on the
+// leading NB x NB block; columns >= NB carry no dense task entries and stay diagonal (jd).
+// u0 = R^-T (D db + Ad^T b) comes out as the transformed right-hand side (the proximal centre is zero whenever a
+// level is factorised).  Register blocking: lane j keeps column j of Ad (MD doubles; j == NB is the rhs column) in
+// registers for the whole QR, the pivot column is broadcast through a double-buffered smem vector (one barrier
+// per step); then lane j keeps column j of J in registers through a fully unrolled back substitution.
+// Every thread of the CTA must call it (barriers); lanes with j > NB only take part in the barriers and in the
+// strided loops, a group that has nothing to do passes j = -1.
+// ------------------------------------------------------------------------------------------
+template <int MD, int N, int NB, int GS>
+__device__ __noinline__ void factor_core(int j, double* Jm, const double* Ad, const double* dg, const double* db,
+                                            double* u0, double* jd, double* bc, double eps)
+{
+    constexpr int LDA = NB + 1;
+    constexpr int BC = MD + 4;
+    const bool live = j >= 0;
+    double* const rinv = jd;               // 1 / R(i,i) for i < NB (jd proper only uses i >= NB)
+    if (live) for (int i = j; i < NB * (NB + 1) / 2; i += GS) Jm[i] = 0.0;
+    double col[MD];
+#pragma unroll
+    for (int r = 0; r < MD; ++r) col[r] = (live && j <= NB) ? Ad[r * LDA + j] : 0.0;
+    if (live)
+        for (int i = j; i < N; i += GS) {
+            const double dd = dg[i] + eps;
+            const double rt = sqrt(dd);
+            if (i < NB) rinv[i] = 1.0 / rt; else jd[i] = 1.0 / rt;
+            u0[i] = dd > 0.0 ? (dg[i] * db[i]) / rt : 0.0;
+        }
+    __syncthreads();
+    double top = 0.0;                      // R(kc, j) before the step is zero except for the rhs column (u0[kc])
+#pragma unroll 1
+    for (int kc = 0; kc < NB; ++kc) {
+        double* const b = bc + (kc & 1) * BC;
+        if (j == kc) {                     // pivot owner: reflector of [alpha; col]
+            double sg0 = 0.0, sg1 = 0.0;
+#pragma unroll
+            for (int r = 0; r + 1 < MD; r += 2) { sg0 = fma(col[r], col[r], sg0); sg1 = fma(col[r + 1], col[r + 1], sg1); }
+            if (MD & 1) sg0 = fma(col[MD - 1], col[MD - 1], sg0);
+            const double sigma = sg0 + sg1;
+            const double alpha = sqrt(dg[kc] + eps);
+            double v1 = 0.0, tau = 0.0;
+            if (sigma != 0.0) {
+                const double nrm = sqrt(fma(alpha, alpha, sigma));
+                v1 = -sigma / (alpha + nrm);               // alpha - nrm, cancellation-free (alpha >= 0)
+                tau = 2.0 / fma(v1, v1, sigma);
+                rinv[kc] = 1.0 / nrm;
+            }
+#pragma unroll
+            for (int r = 0; r < MD; ++r) b[r] = col[r];
+            b[MD] = v1; b[MD + 1] = tau;
+        }
+        __syncthreads();
+        if (live) {
+            const double tau = b[MD + 1];
+            if (tau != 0.0 && j > kc && j <= NB) {             // tau == 0: empty pivot column, nothing to do
+                const double v1 = b[MD];
+                top = j == NB ? u0[kc] : 0.0;
+                double s0 = v1 * top, s1 = 0.0;
+#pragma unroll
+                for (int r = 0; r + 1 < MD; r += 2) { s0 = fma(b[r], col[r], s0); s1 = fma(b[r + 1], col[r + 1], s1); }
+                if (MD & 1) s0 = fma(b[MD - 1], col[MD - 1], s0);
+                const double sc = (s0 + s1) * tau;
+                if (j == NB) u0[kc] = top - sc * v1; else Jm[kc * NB - kc * (kc - 1) / 2 + (j - kc)] = -sc * v1;   // R(kc, j)
+#pragma unroll
+                for (int r = 0; r < MD; ++r) col[r] = fma(-sc, b[r], col[r]);
+            }
+        }
+    }
+    __syncthreads();
+    // back substitution, lane j holds column j of J: J(i,j) = (d_ij - sum_{l>i} R(i,l) J(l,j)) / R(i,i).
+    // Uniform over lanes: Jc[l] stays 0 for l > j.  Row i of R is a broadcast read.
+    double Jc[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) Jc[i] = 0.0;
+    // (lanes without a column run it too, on zeros: a guard here makes ptxas keep Jc in local memory)
+#pragma unroll
+    for (int i = NB - 1; i >= 0; --i) {
+        double a0 = (j == i) ? 1.0 : 0.0, a1 = 0.0;
+#pragma unroll
+        for (int l = i + 1; l < NB; ++l) {
+            const double ril = Jm[i * NB - i * (i - 1) / 2 + (l - i)];
+            if ((l - i) & 1) a0 = fma(-ril, Jc[l], a0); else a1 = fma(-ril, Jc[l], a1);
+        }
+        Jc[i] = (a0 + a1) * rinv[i];
+    }
+    __syncthreads();                       // every row of R has been consumed: overwrite with J (packed columns)
+    if (live && j < NB) {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) if (i <= j) Jm[j * (j + 1) / 2 + i] = Jc[i];
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
 // The solver
 // ------------------------------------------------------------------------------------------
 template <class P, int TEAM>
@@ -644,82 +740,10 @@ struct Solver {
     __device__ static __noinline__ void factor(double eps)
     {
         static_assert(NB + 1 <= TEAM, "one task column per thread");
+        static_assert(2 * (MD + 4) <= 3 * S::VEC, "broadcast buffer fits in w|w2|av");
         QP_BIND
-        double* const bc = w;                  // 2 x (MD + 4) broadcast slots (w, w2, av are contiguous and dead here)
-        double* const rinv = jd;               // 1 / R(i,i) for i < NB (jd proper only uses i >= NB)
-        constexpr int BC = MD + 4;
-        static_assert(2 * BC <= 3 * S::VEC, "broadcast buffer fits in w|w2|av");
-        for (int i = tid; i < NB * (NB + 1) / 2; i += TEAM) Jm[i] = 0.0;
-        double col[MD];
-        const int j = tid;                     // my column (NB = rhs)
-#pragma unroll
-        for (int r = 0; r < MD; ++r) col[r] = j <= NB ? Ad[r * LDA + j] : 0.0;
-        for (int i = tid; i < N; i += TEAM) {
-            const double dd = dg[i] + eps;
-            const double rt = sqrt(dd);
-            if (i < NB) rinv[i] = 1.0 / rt; else jd[i] = 1.0 / rt;
-            u0[i] = dd > 0.0 ? (dg[i] * db[i] + eps * xp[i]) / rt : 0.0;
-        }
-        tm::sync();
-        double top = j == NB ? 0.0 : 0.0;      // R(kc, j) before the step is zero except for the rhs column (u0[kc])
-#pragma unroll 1
-        for (int kc = 0; kc < NB; ++kc) {
-            double* const b = bc + (kc & 1) * BC;
-            if (j == kc) {                     // pivot owner: reflector of [alpha; col]
-                double sg0 = 0.0, sg1 = 0.0;
-#pragma unroll
-                for (int r = 0; r + 1 < MD; r += 2) { sg0 = fma(col[r], col[r], sg0); sg1 = fma(col[r + 1], col[r + 1], sg1); }
-                if (MD & 1) sg0 = fma(col[MD - 1], col[MD - 1], sg0);
-                const double sigma = sg0 + sg1;
-                const double alpha = sqrt(dg[kc] + eps);
-                double v1 = 0.0, tau = 0.0;
-                if (sigma != 0.0) {
-                    const double nrm = sqrt(fma(alpha, alpha, sigma));
-                    v1 = -sigma / (alpha + nrm);               // alpha - nrm, cancellation-free (alpha >= 0)
-                    tau = 2.0 / fma(v1, v1, sigma);
-                    rinv[kc] = 1.0 / nrm;
-                }
-#pragma unroll
-                for (int r = 0; r < MD; ++r) b[r] = col[r];
-                b[MD] = v1; b[MD + 1] = tau;
-            }
-            tm::sync();
-            const double tau = b[MD + 1];
-            if (tau != 0.0 && j > kc && j <= NB) {             // tau == 0: empty pivot column, nothing to do
-                const double v1 = b[MD];
-                top = j == NB ? u0[kc] : 0.0;
-                double s0 = v1 * top, s1 = 0.0;
-#pragma unroll
-                for (int r = 0; r + 1 < MD; r += 2) { s0 = fma(b[r], col[r], s0); s1 = fma(b[r + 1], col[r + 1], s1); }
-                if (MD & 1) s0 = fma(b[MD - 1], col[MD - 1], s0);
-                const double sc = (s0 + s1) * tau;
-                if (j == NB) u0[kc] = top - sc * v1; else Jm[kc * NB - kc * (kc - 1) / 2 + (j - kc)] = -sc * v1;   // R(kc, j)
-#pragma unroll
-                for (int r = 0; r < MD; ++r) col[r] = fma(-sc, b[r], col[r]);
-            }
-        }
-        tm::sync();
-        // back substitution, thread j holds column j of J: J(i,j) = (d_ij - sum_{l>i} R(i,l) J(l,j)) / R(i,i).
-        // Uniform over threads: Jc[l] stays 0 for l > j.  Row i of R is a broadcast read.
-        double Jc[NB];
-#pragma unroll
-        for (int i = 0; i < NB; ++i) Jc[i] = 0.0;
-#pragma unroll
-        for (int i = NB - 1; i >= 0; --i) {
-            double a0 = (j == i) ? 1.0 : 0.0, a1 = 0.0;
-#pragma unroll
-            for (int l = i + 1; l < NB; ++l) {
-                const double ril = Jm[i * NB - i * (i - 1) / 2 + (l - i)];
-                if ((l - i) & 1) a0 = fma(-ril, Jc[l], a0); else a1 = fma(-ril, Jc[l], a1);
-            }
-            Jc[i] = (a0 + a1) * rinv[i];
-        }
-        tm::sync();                            // every row of R has been consumed: overwrite with J (packed columns)
-        if (j < NB) {
-#pragma unroll
-            for (int i = 0; i < NB; ++i) if (i <= j) Jm[j * (j + 1) / 2 + i] = Jc[i];
-        }
-        tm::sync();
+        // w, w2, av are contiguous and dead here: 2 x (MD + 4) broadcast slots
+        factor_core<MD, N, NB, TEAM>(tid, Jm, Ad, dg, db, u0, jd, w, eps);
     }
 
     // out = sgn * J^T a   (thread j: column j of J is contiguous in i)
@@ -1288,28 +1312,57 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
 }
 
 // ------------------------------------------------------------------------------------------
-// Factor kernel (shapes with P::SPLIT_FACTOR): one CTA per (problem, level) pair, grid-stride.  Writes
-// J | u0 | jd of each level into the workspace the solve kernel reads.
+// Factor kernel (shapes with P::SPLIT_FACTOR).  The factorisation has no data-dependent control flow, so several
+// (problem, level) pairs run side by side in one CTA: NB + 1 lanes per pair (one per task column + the rhs column),
+// FactorShape::FPC pairs per CTA -- 7 x 36 = 252 of 256 lanes for the 29-DoF shape, where a 64-thread team leaves
+// 28 lanes (and almost all of its second warp) idle.  Grid-stride over groups of FPC pairs.  Writes J | u0 | jd of
+// each level into the workspace the solve kernel reads.
 // ------------------------------------------------------------------------------------------
-template <class P, int TEAM>
-__global__ void __launch_bounds__(TEAM)
+template <class P>
+struct FactorShape {
+    static constexpr int N = P::N, NB = P::NB, GS = NB + 1, MD = P::MD1 > P::MD0 ? P::MD1 : P::MD0;
+    static constexpr int THREADS = 256;
+    static constexpr int FPC = THREADS / GS;
+    static constexpr int VEC = Slab<P>::VEC, SZ_J = Slab<P>::SZ_J, LDA = NB + 1;
+    // per-pair block (doubles): J | Ad | dg | db | u0 | jd | broadcast
+    static constexpr int O_AD = SZ_J, O_DG = O_AD + MD * LDA + ((MD * LDA) & 1), O_DB = O_DG + VEC, O_U0 = O_DB + VEC;
+    static constexpr int O_JD = O_U0 + VEC, O_BC = O_JD + VEC, BLOCK = O_BC + 2 * (MD + 4);
+    static constexpr int BYTES = FPC * BLOCK * 8;
+};
+
+template <class P>
+__global__ void __launch_bounds__(FactorShape<P>::THREADS)
 qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long long batch, Params prm)
 {
-    using SV = Solver<P, TEAM>;
+    using F = FactorShape<P>;
     using S = Slab<P>;
+    static_assert(!P::STAGE_RECORD, "the factor kernel reads the record from global memory");
     constexpr int N = P::N;
-    const int tid = threadIdx.x;
+    const int t = threadIdx.x;
+    const int f = t / F::GS, lane = t - f * F::GS;
+    double* const blk = reinterpret_cast<double*>(g_smem) + (f < F::FPC ? f : 0) * F::BLOCK;
+    double* const Jm = blk; double* const Ad = blk + F::O_AD; double* const dg = blk + F::O_DG;
+    double* const db = blk + F::O_DB; double* const u0 = blk + F::O_U0; double* const jd = blk + F::O_JD;
+    double* const bc = blk + F::O_BC;
 #pragma unroll 1
-    for (long long pair = blockIdx.x; pair < 2 * batch; pair += gridDim.x) {
+    for (long long base = (long long)blockIdx.x * F::FPC; base < 2 * batch; base += (long long)gridDim.x * F::FPC) {
+        const long long pair = base + f;
+        const bool live = f < F::FPC && pair < 2 * batch;
         const long long idx = pair >> 1;
         const int level = (int)(pair & 1);
-        if (tid == 0) *reinterpret_cast<const double**>(reinterpret_cast<double*>(g_smem) + S::O_J - 2) = recs + idx * (size_t)P::REC;
-        for (int i = tid; i < N; i += TEAM) SV::xp_()[i] = 0.0;
+        if (live) {
+            const double* gr = recs + idx * (size_t)P::REC;
+            const int md = P::template load_tasks<F::GS>(gr, gr, level, Ad, dg, db, lane);
+            for (int e = md * F::LDA + lane; e < F::MD * F::LDA; e += F::GS) Ad[e] = 0.0;   // pad to the common height
+        }
         __syncthreads();
-        SV::load_and_factor(level, P::regularised(level) ? prm.eps_reg : 0.0);
-        double* wsl = ws + idx * (size_t)S::WS + level * S::WS_LEVEL;
-        for (int i = tid; i < S::SZ_J; i += TEAM) wsl[i] = SV::Jm_()[i];
-        for (int i = tid; i < N; i += TEAM) { wsl[S::SZ_J + i] = SV::u0_()[i]; wsl[S::SZ_J + S::VEC + i] = SV::jd_()[i]; }
+        const double eps = P::regularised(level) ? prm.eps_reg : 0.0;
+        factor_core<F::MD, N, P::NB, F::GS>(live ? lane : -1, Jm, Ad, dg, db, u0, jd, bc, eps);
+        if (live) {
+            double* wsl = ws + idx * (size_t)S::WS + level * S::WS_LEVEL;
+            for (int i = lane; i < S::SZ_J; i += F::GS) wsl[i] = Jm[i];
+            for (int i = lane; i < N; i += F::GS) { wsl[S::SZ_J + i] = u0[i]; wsl[S::SZ_J + S::VEC + i] = jd[i]; }
+        }
         __syncthreads();
     }
 }

@@ -20,17 +20,25 @@ struct ShapeEntry {
     int kind, n_a, n_c, flags;
     const void* kernel;          // qp_solve_kernel<P, 64>: 64 threads (one CTA) per problem
     int slab_bytes;
-    const void* factor_kernel;   // qp_factor_kernel<P, 64> for shapes that factor in a separate launch, else null
+    const void* factor_kernel;   // qp_factor_kernel<P> for shapes that factor in a separate launch, else null
     int ws_doubles;              // factor workspace per problem (doubles)
+    int factor_threads, factor_pairs, factor_bytes;   // CTA size, (problem, level) pairs per CTA, dynamic smem
 };
 
 // Instantiated problem shapes (BASELINE.json configs).
+template <class P>
+constexpr const void* factor_entry()
+{
+    if constexpr (P::SPLIT_FACTOR) return (const void*)&qp_factor_kernel<P>;
+    else return nullptr;
+}
 template <class P>
 constexpr ShapeEntry entry()
 {
     return ShapeEntry{P::KIND, P::NA, P::NC, P::FLAGS,
                       (const void*)&qp_solve_kernel<P, 64>, Slab<P>::BYTES,
-                      P::SPLIT_FACTOR ? (const void*)&qp_factor_kernel<P, 64> : nullptr, Slab<P>::WS};
+                      factor_entry<P>(), Slab<P>::WS,
+                      FactorShape<P>::THREADS, FactorShape<P>::FPC, FactorShape<P>::BYTES};
 }
 constexpr int F_ALL = QPPVM_FLAG_FRICTION_CONES | QPPVM_FLAG_TORQUE_LIMITS;
 const ShapeEntry g_shapes[] = {
@@ -122,9 +130,11 @@ int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t 
         double* ws = split ? h->ws[slot] : nullptr;
         if (split) {
             const long long fcap = (long long)h->sm_count * h->factor_ctas_per_sm;
-            const int fgrid = (int)(2 * b < fcap ? 2 * b : fcap);
+            const long long fneed = (2 * b + h->shape->factor_pairs - 1) / h->shape->factor_pairs;
+            const int fgrid = (int)(fneed < fcap ? fneed : fcap);
             void* fargs[] = {(void*)&r, (void*)&ws, (void*)&b, (void*)&prm};
-            CU(h, cudaLaunchKernel(h->shape->factor_kernel, dim3(fgrid), dim3(h->team), fargs, (size_t)h->shape->slab_bytes, st));
+            CU(h, cudaLaunchKernel(h->shape->factor_kernel, dim3(fgrid), dim3(h->shape->factor_threads), fargs,
+                                   (size_t)h->shape->factor_bytes, st));
             h->launches += 1;
         }
         if (counter) CU(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
@@ -256,9 +266,9 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
     if (occ < 1) { fail(nullptr, QPPVM_ERR_CUDA, "kernel does not fit on an SM (%d B smem)", sh->slab_bytes); delete h; return QPPVM_ERR_CUDA; }
     h->ctas_per_sm = occ;
     if (sh->factor_kernel) {
-        CUC(cudaFuncSetAttribute(sh->factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh->slab_bytes));
+        CUC(cudaFuncSetAttribute(sh->factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh->factor_bytes));
         CUC(cudaFuncSetAttribute(sh->factor_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh->factor_kernel, h->team, (size_t)sh->slab_bytes));
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh->factor_kernel, sh->factor_threads, (size_t)sh->factor_bytes));
         h->factor_ctas_per_sm = occ < 1 ? 1 : occ;
     }
     CUC(cudaMalloc(&h->counters, sizeof(unsigned long long) * N_SLOTS));
