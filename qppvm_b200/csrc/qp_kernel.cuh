@@ -234,6 +234,21 @@ struct ForceAcc {
     __device__ static __forceinline__ int n_eq(int level) { return level == 0 ? 6 : 12; }
     __device__ static __forceinline__ int eq_row(int level, int e) { return e < 6 ? ROW_DYN + e : ROW_OPT + (e - 6); }
     __device__ static __forceinline__ bool regularised(int) { return true; }   // Cartesian/postural: HST_SEMIDEF
+    // Coefficient jc of equality row e as (record offset, sign), -1: zero.  Same rows as build_row (dyn-feas base
+    // rows, then the level-0 task rows); used by the prepare kernel of the unstaged shapes.
+    __device__ static __forceinline__ int eq_coef(int, int e, int jc, double& sg)
+    {
+        if (e < 6) {
+            if (jc < NV) { sg = 1.0; return OFF_M + (e >= jc ? e * (e + 1) / 2 + jc : jc * (jc + 1) / 2 + e); }
+            const int ci = (jc - NV) / 3, k = (jc - NV) % 3;
+            sg = -1.0;
+            return OFF_JC + (ci * 6 + k) * NV + e;
+        }
+        sg = 1.0;
+        return jc < NV ? OFF_JW + (e - 6) * NV + jc : -1;
+    }
+    // right-hand side of equality row e when it depends on the record alone (dyn-feas rows)
+    __device__ static __forceinline__ double eq_rhs(const double* g, int, int e) { return e < 6 ? -g[OFF_H + e] : 0.0; }
 
     // Dense task rows of a level into Ad (row-major, ld = NB+1, last column = b); diagonal task
     // weights / targets into dg, db (postural rows are unit rows -> kept as a diagonal).
@@ -580,7 +595,12 @@ struct Slab {
     static constexpr int O_CSTATE = O_STATE + 2 + KP;     // bytes
     static constexpr int O_EXT = O_CSTATE + ((P::NROWS + 15) & ~15) / 8;   // policy scratch
     static constexpr int DOUBLES = O_EXT + P::EXTRA;
-    static constexpr int WS_LEVEL = SZ_J + 2 * VEC;   // factor workspace per level: J | u0 | jd
+    // prepare workspace per level: J | u0 | jd | Q columns [c][i] of the equality normals | RN [c][r] | 1/diag |
+    // point after the equalities whose right-hand side is known | fallback flag
+    static constexpr int NEQ_MAX = 12;
+    static constexpr int WS_Q = SZ_J + 2 * VEC, WS_RN = WS_Q + NEQ_MAX * N, WS_RDI = WS_RN + NEQ_MAX * NEQ_MAX;
+    static constexpr int WS_U = WS_RDI + NEQ_MAX, WS_FLAG = WS_U + VEC;
+    static constexpr int WS_LEVEL = WS_FLAG + 2 + ((WS_FLAG + 2) & 1);
     static constexpr int WS = 2 * WS_LEVEL;
     static constexpr int BYTES = DOUBLES * 8;
 };
@@ -1032,6 +1052,55 @@ struct Solver {
         tm::sync();
     }
 
+    // Split shapes: the prepare kernel has orthogonalised the level's equality normals (Q1 columns, RN) and moved the
+    // point onto the rows whose right-hand side depends on the record alone.  Adopt that working set; for level 1
+    // finish the six optimality rows (right-hand side = level-0 task value) with their stored factors:
+    // slack_e = sum_{c<=e} RN(c,e) (q_c . u) - b_e, u += -(slack_e / RN(e,e)) q_e, the q_c being orthonormal.
+    __device__ static __forceinline__ void load_equalities(int level)
+    {
+        QP_BIND
+        const int neq = P::n_eq(level);
+        const double* wsl = ws_() + level * S::WS_LEVEL;
+        for (int t = tid; t < neq * N; t += TEAM) { const int c = t / N, i = t - c * N; Q1[i * LDQ + c] = wsl[S::WS_Q + t]; }
+        for (int t = tid; t < neq * S::NEQ_MAX; t += TEAM) {
+            const int c = t / S::NEQ_MAX, r = t - c * S::NEQ_MAX;
+            if (r <= c) RN[c * LDR + r] = wsl[S::WS_RN + t];
+        }
+        for (int i = tid; i < N; i += TEAM) u[i] = wsl[S::WS_U + i];
+        if (tid < neq) {
+            const int row = P::eq_row(level, tid);
+            rdi[tid] = wsl[S::WS_RDI + tid]; lam[tid] = 0.0; act_row[tid] = row; act_sgn[tid] = 2; cstate[row] = 1;
+        }
+        if (tid == 0) { st[0] = neq; st[1] = 0; st[2] += neq; }
+        tm::sync();
+        if (neq > 6) {
+            if (tid < neq) {
+                double s0 = 0.0, s1 = 0.0;
+                int i = 0;
+                for (; i + 1 < N; i += 2) { s0 = fma(Q1[i * LDQ + tid], u[i], s0); s1 = fma(Q1[(i + 1) * LDQ + tid], u[i + 1], s1); }
+                if (i < N) s0 = fma(Q1[i * LDQ + tid], u[i], s0);
+                d1[tid] = s0 + s1;
+            }
+            tm::sync();
+            if (tid == 0) {
+#pragma unroll 1
+                for (int e = 6; e < neq; ++e) {
+                    double sl = -eopt[e - 6];
+                    for (int c = 0; c <= e; ++c) sl = fma(RN[e * LDR + c], d1[c], sl);
+                    const double dl = -sl * rdi[e];
+                    d1[e] += dl; rr[e] = dl;
+                }
+            }
+            tm::sync();
+            for (int i = tid; i < N; i += TEAM) {
+                double v = u[i];
+                for (int e = 6; e < neq; ++e) v = fma(rr[e], Q1[i * LDQ + e], v);
+                u[i] = v;
+            }
+            tm::sync();
+        }
+    }
+
     // Task rows of `level` -> J, u0, jd (xp must hold the proximal centre: zero at the start of a level).
     __device__ static __forceinline__ int load_and_factor(int level, double eps)
     {
@@ -1072,7 +1141,12 @@ struct Solver {
         }
         reset_active_set();
         // ---- equalities first (dyn-feas, then level-0 optimality rows), never dropped
-        int status = add_equalities(level, max_iter);
+        int status = QPPVM_STATUS_OK;
+        bool prepared = false;
+        if constexpr (P::SPLIT_FACTOR) prepared = ws_()[level * S::WS_LEVEL + S::WS_FLAG] == 0.0;
+        if (prepared && P::n_eq(level) > max_iter) status = QPPVM_STATUS_MAX_ITER;      // as the row-by-row path would
+        else if (prepared) load_equalities(level);
+        else status = add_equalities(level, max_iter);
         // ---- inequalities + proximal regularisation steps
 #pragma unroll 1
         for (int step = 0; status == QPPVM_STATUS_OK; ++step) {
@@ -1324,9 +1398,15 @@ struct FactorShape {
     static constexpr int THREADS = 256;
     static constexpr int FPC = THREADS / GS;
     static constexpr int VEC = Slab<P>::VEC, SZ_J = Slab<P>::SZ_J, LDA = NB + 1;
-    // per-pair block (doubles): J | Ad | dg | db | u0 | jd | broadcast
+    // per-pair block (doubles): J | Ad | dg | db | u0 | jd | broadcast | normals -> Q | RN | 1/diag.
+    // After the factorisation Ad|dg|db hold the equality rows [e][i] and the broadcast slots their right-hand sides.
+    static constexpr int NEQ = Slab<P>::NEQ_MAX;
     static constexpr int O_AD = SZ_J, O_DG = O_AD + MD * LDA + ((MD * LDA) & 1), O_DB = O_DG + VEC, O_U0 = O_DB + VEC;
-    static constexpr int O_JD = O_U0 + VEC, O_BC = O_JD + VEC, BLOCK = O_BC + 2 * (MD + 4);
+    static constexpr int O_JD = O_U0 + VEC, O_BC = O_JD + VEC, O_WQ = O_BC + 2 * (MD + 4);
+    static constexpr int O_RN = O_WQ + NEQ * N + ((NEQ * N) & 1), O_RDI = O_RN + NEQ * NEQ, BLOCK = O_RDI + NEQ;
+    static_assert(O_U0 - O_AD >= NEQ * N, "equality rows fit over Ad | dg | db");
+    static_assert(2 * (MD + 4) >= NEQ, "right-hand sides fit in the broadcast slots");
+    static_assert(FPC <= THREADS / 32, "one warp per pair in the orthogonalisation phase");
     static constexpr int BYTES = FPC * BLOCK * 8;
 };
 
@@ -1346,10 +1426,12 @@ qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long 
     double* const bc = blk + F::O_BC;
 #pragma unroll 1
     for (long long base = (long long)blockIdx.x * F::FPC; base < 2 * batch; base += (long long)gridDim.x * F::FPC) {
+        // pairs are ordered level-major ([0, batch): level 0, [batch, 2 batch): level 1) so that the pairs sharing a
+        // CTA pass have the same number of equality rows (the orthogonalisation phase is 4x longer for level 1)
         const long long pair = base + f;
         const bool live = f < F::FPC && pair < 2 * batch;
-        const long long idx = pair >> 1;
-        const int level = (int)(pair & 1);
+        const int level = pair >= batch ? 1 : 0;
+        const long long idx = pair - (level ? batch : 0);
         if (live) {
             const double* gr = recs + idx * (size_t)P::REC;
             const int md = P::template load_tasks<F::GS>(gr, gr, level, Ad, dg, db, lane);
@@ -1358,10 +1440,132 @@ qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long 
         __syncthreads();
         const double eps = P::regularised(level) ? prm.eps_reg : 0.0;
         factor_core<F::MD, N, P::NB, F::GS>(live ? lane : -1, Jm, Ad, dg, db, u0, jd, bc, eps);
+        double* const wsl = ws + idx * (size_t)S::WS + level * S::WS_LEVEL;
+        double* const Aeq = blk + F::O_AD; double* const lo_eq = bc;
+        double* const WQ = blk + F::O_WQ; double* const RNb = blk + F::O_RN; double* const rdib = blk + F::O_RDI;
+        const int neq = live ? P::n_eq(level) : 0;
         if (live) {
-            double* wsl = ws + idx * (size_t)S::WS + level * S::WS_LEVEL;
             for (int i = lane; i < S::SZ_J; i += F::GS) wsl[i] = Jm[i];
             for (int i = lane; i < N; i += F::GS) { wsl[S::SZ_J + i] = u0[i]; wsl[S::SZ_J + S::VEC + i] = jd[i]; }
+            // equality rows of the level: each lane fetches its column of all rows before storing any of them, so
+            // the global loads of a pass are in flight together
+            const double* gr = recs + idx * (size_t)P::REC;
+            for (int jc = lane; jc < N; jc += F::GS) {
+                double v[F::NEQ];
+#pragma unroll
+                for (int e = 0; e < F::NEQ; ++e) {
+                    double sg;
+                    const int off = e < neq ? P::eq_coef(level, e, jc, sg) : -1;
+                    v[e] = off >= 0 ? sg * gr[off] : 0.0;
+                }
+#pragma unroll
+                for (int e = 0; e < F::NEQ; ++e) Aeq[e * N + jc] = v[e];
+            }
+            if (lane < neq) lo_eq[lane] = P::eq_rhs(gr, level, lane);
+        }
+        __syncthreads();
+        // whitened normals w_e = J^T a_e, all rows at once (lane j: column j of J against every row)
+        if (live) {
+            if (lane < P::NB) {
+                double acc[F::NEQ];
+#pragma unroll
+                for (int e = 0; e < F::NEQ; ++e) acc[e] = 0.0;
+                const double* col = Jm + lane * (lane + 1) / 2;
+#pragma unroll 1
+                for (int i = 0; i <= lane; ++i) {
+                    const double jv = col[i];
+#pragma unroll
+                    for (int e = 0; e < F::NEQ; ++e) acc[e] = fma(jv, Aeq[e * N + i], acc[e]);
+                }
+#pragma unroll
+                for (int e = 0; e < F::NEQ; ++e) WQ[e * N + lane] = acc[e];
+            }
+            for (int jj = P::NB + lane; jj < N; jj += F::GS) {
+                const double dj = jd[jj];
+#pragma unroll
+                for (int e = 0; e < F::NEQ; ++e) WQ[e * N + jj] = dj * Aeq[e * N + jj];
+            }
+        }
+        __syncthreads();
+        // Orthogonalisation (classical Gram-Schmidt, two passes) and the moves onto the rows whose right-hand side
+        // is known: one warp per pair, rows i = l and l + 32 per lane, Q overwrites the normals column by column.
+        // The same arithmetic as Solver::add_constraint for an equality; a dependent row (or non-finite data)
+        // raises the flag and the solve kernel takes the row-by-row path for that problem.
+        {
+            const int wq = t >> 5, l = t & 31;
+            const long long wpair = base + wq;
+            if (wq < F::FPC && wpair < 2 * batch) {
+                double* const bw = reinterpret_cast<double*>(g_smem) + wq * F::BLOCK;
+                double* const Wq = bw + F::O_WQ; double* const Rq = bw + F::O_RN; double* const rdq = bw + F::O_RDI;
+                const double* const u0q = bw + F::O_U0; const double* const loq = bw + F::O_BC;
+                const int wlevel = wpair >= batch ? 1 : 0, wneq = P::n_eq(wlevel);
+                const int nknown = wlevel == 0 ? wneq : 6;       // level 1: rows >= 6 wait for the level-0 task value
+                double* const wso = ws + (wpair - (wlevel ? batch : 0)) * (size_t)S::WS + wlevel * S::WS_LEVEL;
+                const int i0 = l, i1 = l + 32;
+                const bool has1 = i1 < N;
+                double ua = u0q[i0], ub = has1 ? u0q[i1] : 0.0;
+                double flag = 0.0;
+#pragma unroll 1
+                for (int e = 0; e < wneq; ++e) {
+                    const double wa = Wq[e * N + i0], wb = has1 ? Wq[e * N + i1] : 0.0;
+                    const double ww = warp_sum(fma(wa, wa, wb * wb));
+                    double va = wa, vb = wb, dacc = 0.0;
+#pragma unroll 1
+                    for (int pass = 0; pass < 2; ++pass) {
+                        double dmine = 0.0;
+#pragma unroll 1
+                        for (int c = 0; c < e; c += 4) {            // four independent reductions in flight
+                            double sd[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int cc = c + q < e ? c + q : c;
+                                const double qa = Wq[cc * N + i0], qb = has1 ? Wq[cc * N + i1] : 0.0;
+                                sd[q] = fma(qa, va, qb * vb);
+                            }
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) sd[q] += __shfl_xor_sync(0xffffffffu, sd[q], o);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) if (l == c + q) dmine = sd[q];
+                        }
+                        double na = va, nb = vb, na2 = 0.0, nb2 = 0.0;
+#pragma unroll 1
+                        for (int c = 0; c + 1 < e; c += 2) {
+                            const double dc0 = __shfl_sync(0xffffffffu, dmine, c), dc1 = __shfl_sync(0xffffffffu, dmine, c + 1);
+                            na = fma(-dc0, Wq[c * N + i0], na); na2 = fma(-dc1, Wq[(c + 1) * N + i0], na2);
+                            if (has1) { nb = fma(-dc0, Wq[c * N + i1], nb); nb2 = fma(-dc1, Wq[(c + 1) * N + i1], nb2); }
+                        }
+                        if (e & 1) {
+                            const double dc = __shfl_sync(0xffffffffu, dmine, e - 1);
+                            na = fma(-dc, Wq[(e - 1) * N + i0], na);
+                            if (has1) nb = fma(-dc, Wq[(e - 1) * N + i1], nb);
+                        }
+                        va = na + na2; vb = nb + nb2; dacc += dmine;
+                    }
+                    const double nrm2 = warp_sum(fma(va, va, vb * vb));
+                    if (!(nrm2 > 1e-22 * ww)) { flag = 1.0; break; }
+                    const double nr = sqrt(nrm2), inv = 1.0 / nr;
+                    __syncwarp();
+                    Wq[e * N + i0] = va * inv;
+                    if (has1) Wq[e * N + i1] = vb * inv;
+                    if (l < e) Rq[e * F::NEQ + l] = dacc;
+                    if (l == e) { Rq[e * F::NEQ + e] = nr; rdq[e] = inv; }
+                    if (e < nknown) {
+                        const double sl = warp_sum(fma(wa, ua, wb * ub)) - loq[e];
+                        const double tstep = -sl / nrm2;
+                        ua = fma(tstep, va, ua); ub = fma(tstep, vb, ub);
+                    }
+                    __syncwarp();
+                }
+                for (int i = l; i < wneq * N; i += 32) wso[S::WS_Q + i] = Wq[i];
+                for (int i = l; i < wneq * F::NEQ; i += 32) wso[S::WS_RN + i] = Rq[i];
+                if (l < wneq) wso[S::WS_RDI + l] = rdq[l];
+                wso[S::WS_U + i0] = ua;
+                if (has1) wso[S::WS_U + i1] = ub;
+                if (l == 0) wso[S::WS_FLAG] = flag;
+            }
         }
         __syncthreads();
     }
