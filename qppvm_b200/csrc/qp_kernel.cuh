@@ -1392,6 +1392,43 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
 // 28 lanes (and almost all of its second warp) idle.  Grid-stride over groups of FPC pairs.  Writes J | u0 | jd of
 // each level into the workspace the solve kernel reads.
 // ------------------------------------------------------------------------------------------
+// Sums NV per-lane values across the warp with NV - 1 + (5 - log2 NV) shuffles instead of 5 NV: at each of the
+// first log2 NV steps a lane keeps the half of its values selected by one lane-id bit and sends the other half.
+// Returns, in every lane l, the full sum of value l >> (5 - log2 NV).
+template <int NV>
+__device__ __forceinline__ double warp_sum_transposed(double (&p)[NV], int l)
+{
+    int off = 16;
+#pragma unroll
+    for (int half = NV / 2; half >= 1; half /= 2, off /= 2) {
+        const bool up = l & off;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const double send = up ? p[i] : p[i + half], keep = up ? p[i + half] : p[i];
+            p[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    double v = p[0];
+#pragma unroll
+    for (; off >= 1; off /= 2) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// dmine (lane c) = q_c . v for c < e, the e dot products of one Gram-Schmidt pass (rows i0, i1 of this lane)
+template <int NV, int N>
+__device__ __forceinline__ double gs_dots(const double* Wq, int e, int i0, int i1, bool has1, double va, double vb, int l)
+{
+    double p[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+        const int cc = c < e ? c : 0;
+        const double qa = Wq[cc * N + i0], qb = has1 ? Wq[cc * N + i1] : 0.0;
+        p[c] = fma(qa, va, qb * vb);
+    }
+    const double v = warp_sum_transposed<NV>(p, l);
+    return __shfl_sync(0xffffffffu, v, (l * (32 / NV)) & 31);      // lane c <- the lanes holding value c
+}
+
 template <class P>
 struct FactorShape {
     static constexpr int N = P::N, NB = P::NB, GS = NB + 1, MD = P::MD1 > P::MD0 ? P::MD1 : P::MD0;
@@ -1513,23 +1550,9 @@ qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long 
 #pragma unroll 1
                     for (int pass = 0; pass < 2; ++pass) {
                         double dmine = 0.0;
-#pragma unroll 1
-                        for (int c = 0; c < e; c += 4) {            // four independent reductions in flight
-                            double sd[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int cc = c + q < e ? c + q : c;
-                                const double qa = Wq[cc * N + i0], qb = has1 ? Wq[cc * N + i1] : 0.0;
-                                sd[q] = fma(qa, va, qb * vb);
-                            }
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) sd[q] += __shfl_xor_sync(0xffffffffu, sd[q], o);
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) if (l == c + q) dmine = sd[q];
-                        }
+                        if (e > 8) dmine = gs_dots<16, N>(Wq, e, i0, i1, has1, va, vb, l);
+                        else if (e > 4) dmine = gs_dots<8, N>(Wq, e, i0, i1, has1, va, vb, l);
+                        else if (e > 0) dmine = gs_dots<4, N>(Wq, e, i0, i1, has1, va, vb, l);
                         double na = va, nb = vb, na2 = 0.0, nb2 = 0.0;
 #pragma unroll 1
                         for (int c = 0; c + 1 < e; c += 2) {
