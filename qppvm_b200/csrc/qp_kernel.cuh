@@ -150,6 +150,23 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
 }
+// one instruction: pull `bytes` (multiple of 16) at gsrc (16-byte aligned) into L2
+__device__ __forceinline__ void l2_prefetch(const void* gsrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+// the two halves of bulk_load, for several copies completing on one barrier phase
+__device__ __forceinline__ void bulk_expect(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes),
+                   "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
@@ -586,7 +603,8 @@ struct Slab {
     // numbers are a permutation mod 16, so a half-warp walking 16 consecutive columns is bank-conflict free.
     static constexpr int SZ_J = NB * (NB + 1) / 2 + ((NB * (NB + 1) / 2) & 1);
     static constexpr int O_Q = O_J + SZ_J;            // Q1, aliased by Ad during the factorisation
-    static constexpr int SZ_Q = (N * LDQ > P::MD_MAX * LDA) ? N * LDQ : P::MD_MAX * LDA;
+    static constexpr int SZ_Q_RAW = (N * LDQ > P::MD_MAX * LDA) ? N * LDQ : P::MD_MAX * LDA;
+    static constexpr int SZ_Q = SZ_Q_RAW + (SZ_Q_RAW & 1);     // even: RN and the vectors stay 16-byte aligned
     static constexpr int O_R = O_Q + SZ_Q;
     static constexpr int O_VEC = O_R + KMAX * LDR + ((KMAX * LDR) & 1);    // u0 u x w w2 av dg db xp jd
     static constexpr int O_SMALL = O_VEC + 10 * VEC;  // d1 rr lam (KP each) | eopt 8 | red 16
@@ -595,12 +613,16 @@ struct Slab {
     static constexpr int O_CSTATE = O_STATE + 2 + KP;     // bytes
     static constexpr int O_EXT = O_CSTATE + ((P::NROWS + 15) & ~15) / 8;   // policy scratch
     static constexpr int DOUBLES = O_EXT + P::EXTRA;
-    // prepare workspace per level: J | u0 | jd | Q columns [c][i] of the equality normals | RN [c][r] | 1/diag |
-    // point after the equalities whose right-hand side is known | fallback flag
+    // prepare workspace per level, every piece in the layout (and 16-byte alignment) of its shared-memory home so
+    // that the solve kernel fetches it with bulk copies: J | u0 | jd | Q1 rows [i][LDQ] (first n_eq columns
+    // filled) | RN columns [c][LDR] | 1/diag + fallback flag | point after the equalities with a known rhs
     static constexpr int NEQ_MAX = 12;
-    static constexpr int WS_Q = SZ_J + 2 * VEC, WS_RN = WS_Q + NEQ_MAX * N, WS_RDI = WS_RN + NEQ_MAX * NEQ_MAX;
-    static constexpr int WS_U = WS_RDI + NEQ_MAX, WS_FLAG = WS_U + VEC;
-    static constexpr int WS_LEVEL = WS_FLAG + 2 + ((WS_FLAG + 2) & 1);
+    static constexpr int WS_U0 = SZ_J, WS_JD = WS_U0 + VEC, WS_Q = WS_JD + VEC;
+    static constexpr int WSZ_Q = N * LDQ + ((N * LDQ) & 1), WS_RN = WS_Q + WSZ_Q;
+    static constexpr int WSZ_RN = NEQ_MAX * LDR + ((NEQ_MAX * LDR) & 1), WS_RDI = WS_RN + WSZ_RN;
+    static constexpr int WSZ_RDI = NEQ_MAX + 2, WS_FLAG = WS_RDI + NEQ_MAX, WS_U = WS_RDI + WSZ_RDI;
+    static constexpr int WS_LEVEL = WS_U + VEC;
+    static_assert((SZ_J % 2 == 0) && (VEC % 2 == 0) && (WSZ_RDI % 2 == 0) && (KP >= WSZ_RDI), "bulk-copy alignment");
     static constexpr int WS = 2 * WS_LEVEL;
     static constexpr int BYTES = DOUBLES * 8;
 };
@@ -1053,23 +1075,17 @@ struct Solver {
     }
 
     // Split shapes: the prepare kernel has orthogonalised the level's equality normals (Q1 columns, RN) and moved the
-    // point onto the rows whose right-hand side depends on the record alone.  Adopt that working set; for level 1
+    // point onto the rows whose right-hand side depends on the record alone (all of it already sits in Q1, RN, rdi
+    // and u: solve_level's bulk copies).  Adopt that working set; for level 1
     // finish the six optimality rows (right-hand side = level-0 task value) with their stored factors:
     // slack_e = sum_{c<=e} RN(c,e) (q_c . u) - b_e, u += -(slack_e / RN(e,e)) q_e, the q_c being orthonormal.
-    __device__ static __forceinline__ void load_equalities(int level)
+    __device__ static __forceinline__ void adopt_equalities(int level)
     {
         QP_BIND
         const int neq = P::n_eq(level);
-        const double* wsl = ws_() + level * S::WS_LEVEL;
-        for (int t = tid; t < neq * N; t += TEAM) { const int c = t / N, i = t - c * N; Q1[i * LDQ + c] = wsl[S::WS_Q + t]; }
-        for (int t = tid; t < neq * S::NEQ_MAX; t += TEAM) {
-            const int c = t / S::NEQ_MAX, r = t - c * S::NEQ_MAX;
-            if (r <= c) RN[c * LDR + r] = wsl[S::WS_RN + t];
-        }
-        for (int i = tid; i < N; i += TEAM) u[i] = wsl[S::WS_U + i];
         if (tid < neq) {
             const int row = P::eq_row(level, tid);
-            rdi[tid] = wsl[S::WS_RDI + tid]; lam[tid] = 0.0; act_row[tid] = row; act_sgn[tid] = 2; cstate[row] = 1;
+            lam[tid] = 0.0; act_row[tid] = row; act_sgn[tid] = 2; cstate[row] = 1;
         }
         if (tid == 0) { st[0] = neq; st[1] = 0; st[2] += neq; }
         tm::sync();
@@ -1130,23 +1146,42 @@ struct Solver {
         if (tid == 0) st[2] = 0;
         tm::sync();
         int md;
+        int status = QPPVM_STATUS_OK;
         if constexpr (P::SPLIT_FACTOR) {
+            // everything the prepare kernel produced for this level lands in its shared-memory home through seven
+            // bulk copies on one mbarrier (the previous level / problem is done with the slab: barrier above)
             md = level == 0 ? P::MD0 : P::MD1;
-            const double* wsl = ws_() + level * S::WS_LEVEL;
-            for (int i = tid; i < S::SZ_J; i += TEAM) Jm[i] = wsl[i];
-            for (int i = tid; i < N; i += TEAM) { u0[i] = wsl[S::SZ_J + i]; jd[i] = wsl[S::SZ_J + S::VEC + i]; }
+            if (tid == 0) {
+                const double* wsl = ws_() + level * S::WS_LEVEL;
+                constexpr uint32_t B_J = S::SZ_J * 8, B_V = S::VEC * 8, B_Q = S::WSZ_Q * 8, B_RN = S::WSZ_RN * 8, B_RDI = S::WSZ_RDI * 8;
+                bulk_expect(mbar_(), B_J + 3 * B_V + B_Q + B_RN + B_RDI);
+                bulk_copy(Jm, wsl, B_J, mbar_());
+                bulk_copy(u0, wsl + S::WS_U0, B_V, mbar_());
+                bulk_copy(jd, wsl + S::WS_JD, B_V, mbar_());
+                bulk_copy(Q1, wsl + S::WS_Q, B_Q, mbar_());
+                bulk_copy(RN, wsl + S::WS_RN, B_RN, mbar_());
+                bulk_copy(rdi, wsl + S::WS_RDI, B_RDI, mbar_());
+                bulk_copy(u, wsl + S::WS_U, B_V, mbar_());
+            }
+            for (int i = tid; i < P::NROWS; i += TEAM) cstate[i] = 0;
+            mbar_wait(mbar_(), (uint32_t)st[3]);
             tm::sync();
+            const bool prepared = rdi[S::NEQ_MAX] == 0.0;
+            tm::sync();
+            if (tid == 0) { st[3] ^= 1; st[0] = 0; st[1] = 0; }
+            if (prepared && P::n_eq(level) > max_iter) status = QPPVM_STATUS_MAX_ITER;   // as the row-by-row path would
+            else if (prepared) adopt_equalities(level);
+            else {
+                for (int i = tid; i < N; i += TEAM) u[i] = u0[i];
+                tm::sync();
+                status = add_equalities(level, max_iter);
+            }
         } else {
             md = load_and_factor(level, eps);
+            reset_active_set();
+            // ---- equalities first (dyn-feas, then level-0 optimality rows), never dropped
+            status = add_equalities(level, max_iter);
         }
-        reset_active_set();
-        // ---- equalities first (dyn-feas, then level-0 optimality rows), never dropped
-        int status = QPPVM_STATUS_OK;
-        bool prepared = false;
-        if constexpr (P::SPLIT_FACTOR) prepared = ws_()[level * S::WS_LEVEL + S::WS_FLAG] == 0.0;
-        if (prepared && P::n_eq(level) > max_iter) status = QPPVM_STATUS_MAX_ITER;      // as the row-by-row path would
-        else if (prepared) load_equalities(level);
-        else status = add_equalities(level, max_iter);
         // ---- inequalities + proximal regularisation steps
 #pragma unroll 1
         for (int step = 0; status == QPPVM_STATUS_OK; ++step) {
@@ -1307,7 +1342,7 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
     constexpr int OUT_BYTES = 8 * (N + P::NA) + 32;
     constexpr int DIAG = N + 2 * P::NROWS + QPPVM_M0;
     __shared__ unsigned long long s_idx;
-    if (tid == 0) mbar_init(SV::mbar_(), 1);
+    if (tid == 0) { mbar_init(SV::mbar_(), 1); SV::state_()[3] = 0; }   // state[3]: barrier phase of the workspace copies
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     uint32_t phase = 0;
@@ -1322,7 +1357,11 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
             if ((long long)i < batch) {
                 const double* gr = recs + i * (size_t)P::REC;
                 *reinterpret_cast<const double**>(reinterpret_cast<double*>(g_smem) + Slab<P>::O_J - 2) = gr;
-                if (P::SPLIT_FACTOR) SV::ws_() = ws + i * (size_t)Slab<P>::WS;
+                if (P::SPLIT_FACTOR) {
+                    SV::ws_() = ws + i * (size_t)Slab<P>::WS;
+                    // level 1's share of the workspace is needed ~100 us from now: have it in L2 by then
+                    l2_prefetch(ws + i * (size_t)Slab<P>::WS + Slab<P>::WS_LEVEL, (uint32_t)(Slab<P>::WS_LEVEL * 8));
+                }
                 if (Slab<P>::STAGE)                            // one TMA bulk copy stages the tail of the record
                     bulk_load(SV::rec_(), gr + P::STAGE_FROM, (uint32_t)((P::REC - P::STAGE_FROM) * sizeof(double)), SV::mbar_());
             }
@@ -1483,7 +1522,7 @@ qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long 
         const int neq = live ? P::n_eq(level) : 0;
         if (live) {
             for (int i = lane; i < S::SZ_J; i += F::GS) wsl[i] = Jm[i];
-            for (int i = lane; i < N; i += F::GS) { wsl[S::SZ_J + i] = u0[i]; wsl[S::SZ_J + S::VEC + i] = jd[i]; }
+            for (int i = lane; i < N; i += F::GS) { wsl[S::WS_U0 + i] = u0[i]; wsl[S::WS_JD + i] = jd[i]; }
             // equality rows of the level: each lane fetches its column of all rows before storing any of them, so
             // the global loads of a pass are in flight together
             const double* gr = recs + idx * (size_t)P::REC;
@@ -1582,8 +1621,14 @@ qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long 
                     }
                     __syncwarp();
                 }
-                for (int i = l; i < wneq * N; i += 32) wso[S::WS_Q + i] = Wq[i];
-                for (int i = l; i < wneq * F::NEQ; i += 32) wso[S::WS_RN + i] = Rq[i];
+                for (int t2 = l; t2 < wneq * N; t2 += 32) {      // Q1's row-major home: (i, c) -> i LDQ + c
+                    const int i = t2 / wneq, c = t2 - i * wneq;
+                    wso[S::WS_Q + i * S::LDQ + c] = Wq[c * N + i];
+                }
+                for (int t2 = l; t2 < wneq * F::NEQ; t2 += 32) {
+                    const int c = t2 / F::NEQ, r = t2 - c * F::NEQ;
+                    if (r <= c) wso[S::WS_RN + c * S::LDR + r] = Rq[t2];
+                }
                 if (l < wneq) wso[S::WS_RDI + l] = rdq[l];
                 wso[S::WS_U + i0] = ua;
                 if (has1) wso[S::WS_U + i1] = ub;
