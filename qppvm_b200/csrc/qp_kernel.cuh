@@ -1361,6 +1361,9 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
                     SV::ws_() = ws + i * (size_t)Slab<P>::WS;
                     // level 1's share of the workspace is needed ~100 us from now: have it in L2 by then
                     l2_prefetch(ws + i * (size_t)Slab<P>::WS + Slab<P>::WS_LEVEL, (uint32_t)(Slab<P>::WS_LEVEL * 8));
+                    // the record was pushed out of L2 by the workspace writes of the prepare kernel; the row / task
+                    // reads of the inequality scan, the KKT check and the torque recovery all come from it
+                    l2_prefetch(gr, (uint32_t)(P::REC * sizeof(double)));
                 }
                 if (Slab<P>::STAGE)                            // one TMA bulk copy stages the tail of the record
                     bulk_load(SV::rec_(), gr + P::STAGE_FROM, (uint32_t)((P::REC - P::STAGE_FROM) * sizeof(double)), SV::mbar_());
