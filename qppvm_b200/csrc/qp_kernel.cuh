@@ -226,10 +226,10 @@ struct ForceAcc {
     }
     static constexpr int MD0 = 6, MD1 = 6 * NC;                // dense task rows of level 0 / 1
     static constexpr int EXTRA = 0;                            // policy scratch in the slab (doubles)
-    // The two factorisations depend only on the record: for the unstaged shapes they run in their own kernel
+    // The two factorisations depend only on the record: for the ForceAcc shapes they run in their own kernel
     // (qp_factor_kernel) and reach the solve through a workspace in global memory (L2-resident), which takes the
     // 25 KB of unrolled factorisation code out of the instruction-fetch-bound solve kernel (profiles/README.md).
-    static constexpr bool SPLIT_FACTOR = QPPVM_SPLIT && !TLIM;
+    static constexpr bool SPLIT_FACTOR = QPPVM_SPLIT;
     // Staging (see Slab::STAGE): shapes whose inequality scan re-reads M every iteration (torque-limit rows) keep
     // the TAIL of the record [M | h | Jdqd | rhs | tau limits | cones | boxes] (one TMA bulk copy) plus the linear
     // contact-Jacobian rows in shared memory; the task Jacobians (read once per level) stay in global memory.
@@ -608,8 +608,8 @@ struct Slab {
     static constexpr int O_R = O_Q + SZ_Q;
     static constexpr int O_VEC = O_R + KMAX * LDR + ((KMAX * LDR) & 1);    // u0 u x w w2 av dg db xp jd
     static constexpr int O_SMALL = O_VEC + 10 * VEC;  // d1 rr lam (KP each) | eopt 8 | red 16
-    static constexpr int O_MBAR = O_SMALL + 4 * KP + 8 + 16;   // d1 rr lam rdi
-    static constexpr int O_STATE = O_MBAR + 1;        // ints: k, n_act_ineq, iters, - | act_row[KP] | act_sgn[KP]
+    static constexpr int O_MBAR = O_SMALL + 4 * KP + 8 + 16;   // d1 rr lam rdi | 2 mbarriers: record staging, workspace copies
+    static constexpr int O_STATE = O_MBAR + 2;        // ints: k, n_act_ineq, iters, ws phase | act_row[KP] | act_sgn[KP]
     static constexpr int O_CSTATE = O_STATE + 2 + KP;     // bytes
     static constexpr int O_EXT = O_CSTATE + ((P::NROWS + 15) & ~15) / 8;   // policy scratch
     static constexpr int DOUBLES = O_EXT + P::EXTRA;
@@ -754,6 +754,7 @@ struct Solver {
     QP_SM(eopt, S::O_SMALL + 4 * KP) QP_SM(red, S::O_SMALL + 4 * KP + 8) QP_SM(ext, S::O_EXT)
 #undef QP_SM
     __device__ static __forceinline__ uint64_t* mbar_() { return reinterpret_cast<uint64_t*>(g_smem) + S::O_MBAR; }
+    __device__ static __forceinline__ uint64_t* mbar_ws_() { return reinterpret_cast<uint64_t*>(g_smem) + S::O_MBAR + 1; }
     __device__ static __forceinline__ int* state_() { return reinterpret_cast<int*>(reinterpret_cast<double*>(g_smem) + S::O_STATE); }
     __device__ static __forceinline__ unsigned char* cstate_() { return g_smem + 8 * S::O_CSTATE; }
     using tm = Team<TEAM>;
@@ -1154,17 +1155,17 @@ struct Solver {
             if (tid == 0) {
                 const double* wsl = ws_() + level * S::WS_LEVEL;
                 constexpr uint32_t B_J = S::SZ_J * 8, B_V = S::VEC * 8, B_Q = S::WSZ_Q * 8, B_RN = S::WSZ_RN * 8, B_RDI = S::WSZ_RDI * 8;
-                bulk_expect(mbar_(), B_J + 3 * B_V + B_Q + B_RN + B_RDI);
-                bulk_copy(Jm, wsl, B_J, mbar_());
-                bulk_copy(u0, wsl + S::WS_U0, B_V, mbar_());
-                bulk_copy(jd, wsl + S::WS_JD, B_V, mbar_());
-                bulk_copy(Q1, wsl + S::WS_Q, B_Q, mbar_());
-                bulk_copy(RN, wsl + S::WS_RN, B_RN, mbar_());
-                bulk_copy(rdi, wsl + S::WS_RDI, B_RDI, mbar_());
-                bulk_copy(u, wsl + S::WS_U, B_V, mbar_());
+                bulk_expect(mbar_ws_(), B_J + 3 * B_V + B_Q + B_RN + B_RDI);
+                bulk_copy(Jm, wsl, B_J, mbar_ws_());
+                bulk_copy(u0, wsl + S::WS_U0, B_V, mbar_ws_());
+                bulk_copy(jd, wsl + S::WS_JD, B_V, mbar_ws_());
+                bulk_copy(Q1, wsl + S::WS_Q, B_Q, mbar_ws_());
+                bulk_copy(RN, wsl + S::WS_RN, B_RN, mbar_ws_());
+                bulk_copy(rdi, wsl + S::WS_RDI, B_RDI, mbar_ws_());
+                bulk_copy(u, wsl + S::WS_U, B_V, mbar_ws_());
             }
             for (int i = tid; i < P::NROWS; i += TEAM) cstate[i] = 0;
-            mbar_wait(mbar_(), (uint32_t)st[3]);
+            mbar_wait(mbar_ws_(), (uint32_t)st[3]);
             tm::sync();
             const bool prepared = rdi[S::NEQ_MAX] == 0.0;
             tm::sync();
@@ -1342,7 +1343,7 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
     constexpr int OUT_BYTES = 8 * (N + P::NA) + 32;
     constexpr int DIAG = N + 2 * P::NROWS + QPPVM_M0;
     __shared__ unsigned long long s_idx;
-    if (tid == 0) { mbar_init(SV::mbar_(), 1); SV::state_()[3] = 0; }   // state[3]: barrier phase of the workspace copies
+    if (tid == 0) { mbar_init(SV::mbar_(), 1); mbar_init(SV::mbar_ws_(), 1); SV::state_()[3] = 0; }   // state[3]: phase of the workspace copies
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     uint32_t phase = 0;
@@ -1363,7 +1364,7 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
                     l2_prefetch(ws + i * (size_t)Slab<P>::WS + Slab<P>::WS_LEVEL, (uint32_t)(Slab<P>::WS_LEVEL * 8));
                     // the record was pushed out of L2 by the workspace writes of the prepare kernel; the row / task
                     // reads of the inequality scan, the KKT check and the torque recovery all come from it
-                    l2_prefetch(gr, (uint32_t)(P::REC * sizeof(double)));
+                    if (!Slab<P>::STAGE) l2_prefetch(gr, (uint32_t)(P::REC * sizeof(double)));
                 }
                 if (Slab<P>::STAGE)                            // one TMA bulk copy stages the tail of the record
                     bulk_load(SV::rec_(), gr + P::STAGE_FROM, (uint32_t)((P::REC - P::STAGE_FROM) * sizeof(double)), SV::mbar_());
@@ -1474,7 +1475,7 @@ __device__ __forceinline__ double gs_dots(const double* Wq, int e, int i0, int i
 template <class P>
 struct FactorShape {
     static constexpr int N = P::N, NB = P::NB, GS = NB + 1, MD = P::MD1 > P::MD0 ? P::MD1 : P::MD0;
-    static constexpr int THREADS = 256;
+    static constexpr int THREADS = GS <= 36 ? 256 : 128;        // the 51-variable shapes need 22 KB per pair: 3 pairs per CTA
     static constexpr int FPC = THREADS / GS;
     static constexpr int VEC = Slab<P>::VEC, SZ_J = Slab<P>::SZ_J, LDA = NB + 1;
     // per-pair block (doubles): J | Ad | dg | db | u0 | jd | broadcast | normals -> Q | RN | 1/diag.
@@ -1495,7 +1496,6 @@ qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long 
 {
     using F = FactorShape<P>;
     using S = Slab<P>;
-    static_assert(!P::STAGE_RECORD, "the factor kernel reads the record from global memory");
     constexpr int N = P::N;
     const int t = threadIdx.x;
     const int f = t / F::GS, lane = t - f * F::GS;
@@ -1513,7 +1513,8 @@ qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long 
         const long long idx = pair - (level ? batch : 0);
         if (live) {
             const double* gr = recs + idx * (size_t)P::REC;
-            const int md = P::template load_tasks<F::GS>(gr, gr, level, Ad, dg, db, lane);
+            // (policy functions address the staged tail as rec[OFF - SB]: hand them the global record shifted by SB)
+            const int md = P::template load_tasks<F::GS>(gr + P::SB, gr, level, Ad, dg, db, lane);
             for (int e = md * F::LDA + lane; e < F::MD * F::LDA; e += F::GS) Ad[e] = 0.0;   // pad to the common height
         }
         __syncthreads();
