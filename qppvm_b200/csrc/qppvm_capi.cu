@@ -119,6 +119,8 @@ int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t 
             cudaFree(h->ws[slot]); h->ws[slot] = nullptr; h->ws_cap[slot] = 0;
             const int64_t capn = need < 1024 ? 1024 : need;
             CU(h, cudaMalloc(&h->ws[slot], sizeof(double) * (size_t)h->shape->ws_doubles * capn));
+            // the bulk copies of the solve kernel also move the unused Q1 / RN entries: give them defined contents
+            CU(h, cudaMemsetAsync(h->ws[slot], 0, sizeof(double) * (size_t)h->shape->ws_doubles * capn, st));
             h->ws_cap[slot] = capn;
         }
     }
