@@ -264,6 +264,12 @@ struct ForceAcc {
         sg = 1.0;
         return jc < NV ? OFF_JW + (e - 6) * NV + jc : -1;
     }
+    static constexpr bool HAS_EQ_COEF = true;
+    // bound of equality row e as the solve kernel sees it (rec: staged tail or global record; eopt: level-0 task value)
+    __device__ static __forceinline__ double eq_bound(const double* rec, int e, const double* eopt)
+    {
+        return e < 6 ? -rec[OFF_H - SB + e] : eopt[e - 6];
+    }
     // right-hand side of equality row e when it depends on the record alone (dyn-feas rows)
     __device__ static __forceinline__ double eq_rhs(const double* g, int, int e) { return e < 6 ? -g[OFF_H + e] : 0.0; }
 
@@ -438,6 +444,7 @@ struct Torque {
     static constexpr int O_A0 = NA * LDM, O_T = O_A0 + 6 * NA;
     static constexpr int EXTRA = O_T + NA * LDM + ((O_T + NA * LDM) & 1);
     static constexpr bool SPLIT_FACTOR = false;
+    static constexpr bool HAS_EQ_COEF = false;
 
     __device__ static __forceinline__ int n_eq(int level) { return level == 0 ? 0 : 6; }
     __device__ static __forceinline__ int eq_row(int, int e) { return ROW_OPT + e; }
@@ -626,6 +633,28 @@ struct Slab {
     static constexpr int WS = 2 * WS_LEVEL;
     static constexpr int BYTES = DOUBLES * 8;
 };
+
+// Sums NV per-lane values across the warp with NV - 1 + (5 - log2 NV) shuffles instead of 5 NV: at each of the
+// first log2 NV steps a lane keeps the half of its values selected by one lane-id bit and sends the other half.
+// Returns, in every lane l, the full sum of value l >> (5 - log2 NV).
+template <int NV>
+__device__ __forceinline__ double warp_sum_transposed(double (&p)[NV], int l)
+{
+    int off = 16;
+#pragma unroll
+    for (int half = NV / 2; half >= 1; half /= 2, off /= 2) {
+        const bool up = l & off;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const double send = up ? p[i] : p[i + half], keep = up ? p[i + half] : p[i];
+            p[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    double v = p[0];
+#pragma unroll
+    for (; off >= 1; off /= 2) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
 
 // ------------------------------------------------------------------------------------------
 // Whitening factorisation, shared by the in-kernel path (one 64-thread team, lane = thread id) and the
@@ -1263,9 +1292,47 @@ struct Solver {
         // grad = D (x - db) + Ad^T (Ad x - b) + eps (x - xp) - sum_c y_c a_c ; constraint part first (w)
         for (int i = tid; i < N; i += TEAM) w[i] = 0.0;
         tm::sync();
-        double rprim = 0.0, rcomp = 0.0, cxmax = 0.0, ymax = 0.0;
+        double rprim = 0.0, rcomp = 0.0, cxmax = 0.0, ymax = 0.0;   // per-thread partial maxima, merged at the end
+        int c0 = 0;
+        if constexpr (P::HAS_EQ_COEF) {
+            // The equality rows sit at the head of the working set in row order (unless a dependent one was skipped):
+            // one sweep with every thread fetching its column of all of them (loads in flight together), the
+            // a_e . x through one transposed reduction, instead of a row build + reduction + barriers per row.
+            const int neq = P::n_eq(level);
+            bool fast = k >= neq;
+            for (int e = 0; e < neq && fast; ++e) fast = act_row[e] == P::eq_row(level, e) && !(act_sgn[e] & 1);
+            if (fast) {
+                static_assert(S::NEQ_MAX <= 16 && TEAM == 64, "one transposed reduction per warp");
+                double pe[16], wj = 0.0;
+                const double xj = tid < N ? x[tid] : 0.0;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    double a = 0.0;
+                    if (e < neq && tid < N) {
+                        double sg;
+                        const int off = P::eq_coef(level, e, tid, sg);
+                        if (off >= 0) a = sg * ext[off];
+                    }
+                    const double y = e < neq ? (act_sgn[e] > 0 ? 1.0 : -1.0) * rr[e] : 0.0;
+                    wj = fma(-y, a, wj);
+                    pe[e] = a * xj;
+                }
+                const double v = warp_sum_transposed<16>(pe, tid & 31);
+                if (!(tid & 1)) av[(tid >> 5) * 16 + ((tid & 31) >> 1)] = v;
+                if (tid < N) w[tid] = wj;
+                tm::sync();
+                if (tid < neq) {
+                    const double val = av[tid] + av[16 + tid];
+                    const double y = (act_sgn[tid] > 0 ? 1.0 : -1.0) * rr[tid];
+                    rprim = fabs(val - P::eq_bound(rec, tid, eopt)); cxmax = fabs(val); ymax = fabs(y);
+                    if (ydiag) ydiag[act_row[tid]] = y;
+                }
+                tm::sync();
+                c0 = neq;
+            }
+        }
 #pragma unroll 1
-        for (int c = 0; c < k; ++c) {
+        for (int c = c0; c < k; ++c) {
             const int row = act_row[c];
             const int sg = act_sgn[c];
             double lo, hi;
@@ -1295,7 +1362,7 @@ struct Solver {
                 cm = fmax(cm, fabs(val));
                 if (!(cstate[r] & 1)) viol = fmax(viol, fmax(lo - val, val - hi));
             }
-            rprim = fmax(rprim, tm::max(viol, red)); cxmax = fmax(cxmax, tm::max(cm, red));
+            rprim = fmax(rprim, viol); cxmax = fmax(cxmax, cm);
         }
         // task part (reload the dense task rows over the dead Q1 region); (A x)_r -> w2, b_r -> av
         tm::sync();
@@ -1320,7 +1387,26 @@ struct Solver {
             const double stn = hx + g + w[j];
             rs = fmax(rs, fabs(stn)); gmax = fmax(gmax, fabs(g)); hxmax = fmax(hxmax, fabs(hx)); xmax = fmax(xmax, fabs(x[j]));
         }
-        rs = tm::max(rs, red); gmax = tm::max(gmax, red); hxmax = tm::max(hxmax, red); xmax = tm::max(xmax, red);
+        {   // the eight maxima meet through one exchange (red: WARPS x 8)
+            static_assert(tm::WARPS * 8 <= 16, "red holds the exchange");
+            double m[8] = {rs, gmax, hxmax, xmax, rprim, rcomp, cxmax, ymax};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) m[q] = warp_max(m[q]);
+            tm::sync();
+            if ((tid & 31) == 0)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) red[(tid >> 5) * 8 + q] = m[q];
+            tm::sync();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                double v = red[q];
+#pragma unroll
+                for (int wv = 1; wv < tm::WARPS; ++wv) v = fmax(v, red[wv * 8 + q]);
+                m[q] = v;
+            }
+            tm::sync();
+            rs = m[0]; gmax = m[1]; hxmax = m[2]; xmax = m[3]; rprim = m[4]; rcomp = m[5]; cxmax = m[6]; ymax = m[7];
+        }
         rs /= fmax(1.0, fmax(gmax, hxmax));
         rprim /= fmax(1.0, fmax(xmax, cxmax));
         rcomp /= fmax(1.0, ymax) * fmax(1.0, cxmax);
@@ -1435,28 +1521,6 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
 // 28 lanes (and almost all of its second warp) idle.  Grid-stride over groups of FPC pairs.  Writes J | u0 | jd of
 // each level into the workspace the solve kernel reads.
 // ------------------------------------------------------------------------------------------
-// Sums NV per-lane values across the warp with NV - 1 + (5 - log2 NV) shuffles instead of 5 NV: at each of the
-// first log2 NV steps a lane keeps the half of its values selected by one lane-id bit and sends the other half.
-// Returns, in every lane l, the full sum of value l >> (5 - log2 NV).
-template <int NV>
-__device__ __forceinline__ double warp_sum_transposed(double (&p)[NV], int l)
-{
-    int off = 16;
-#pragma unroll
-    for (int half = NV / 2; half >= 1; half /= 2, off /= 2) {
-        const bool up = l & off;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-            const double send = up ? p[i] : p[i + half], keep = up ? p[i + half] : p[i];
-            p[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-    double v = p[0];
-#pragma unroll
-    for (; off >= 1; off /= 2) v += __shfl_xor_sync(0xffffffffu, v, off);
-    return v;
-}
-
 // dmine (lane c) = q_c . v for c < e, the e dot products of one Gram-Schmidt pass (rows i0, i1 of this lane)
 template <int NV, int N>
 __device__ __forceinline__ double gs_dots(const double* Wq, int e, int i0, int i1, bool has1, double va, double vb, int l)
