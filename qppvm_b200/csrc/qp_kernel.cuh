@@ -47,6 +47,8 @@ struct Params {
     double eps_reg;     // eps_regularisation * 2.221e-13
     int n_reg_steps;
     int max_iter;
+    int rowwise;        // test switch (QPPVM_ROWWISE_EQUALITIES=1 at create): the prepare kernel flags every problem for
+                        // the row-by-row equality path of the solve kernel, the one dependent rows fall back to
 };
 
 // ------------------------------------------------------------------------------------------
@@ -1648,9 +1650,9 @@ qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long 
                 const int i0 = l, i1 = l + 32;
                 const bool has1 = i1 < N;
                 double ua = u0q[i0], ub = has1 ? u0q[i1] : 0.0;
-                double flag = 0.0;
+                double flag = prm.rowwise ? 1.0 : 0.0;
 #pragma unroll 1
-                for (int e = 0; e < wneq; ++e) {
+                for (int e = 0; e < (prm.rowwise ? 0 : wneq); ++e) {
                     const double wa = Wq[e * N + i0], wb = has1 ? Wq[e * N + i1] : 0.0;
                     const double ww = warp_sum(fma(wa, wa, wb * wb));
                     double va = wa, vb = wb, dacc = 0.0;

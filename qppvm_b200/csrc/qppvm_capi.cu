@@ -68,6 +68,7 @@ struct qppvm_handle {
     unsigned long long* counters;          // N_SLOTS device counters
     double* ws[N_SLOTS]; int64_t ws_cap[N_SLOTS];   // factor workspaces, one per launch slot, allocated on first use
     int factor_ctas_per_sm;
+    int rowwise;                           // QPPVM_ROWWISE_EQUALITIES=1 at create (tests): see Params::rowwise
     cudaStream_t streams[HOST_STREAMS];
     double* d_rec[HOST_STREAMS];
     unsigned char* d_out[HOST_STREAMS];
@@ -108,7 +109,7 @@ int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t 
     if (batch <= 0) return QPPVM_OK;
     unsigned long long* counter = dynamic ? h->counters + slot : nullptr;   // null: static round-robin schedule
     const long long cap = (long long)h->sm_count * h->ctas_per_sm;
-    Params prm{h->desc.eps_regularisation * QPPVM_QPOASES_EPS_REG, h->desc.n_reg_steps, h->desc.max_iter};
+    Params prm{h->desc.eps_regularisation * QPPVM_QPOASES_EPS_REG, h->desc.n_reg_steps, h->desc.max_iter, h->rowwise};
     const bool split = h->shape->factor_kernel != nullptr;
     const int64_t pass = split ? WS_CHUNK : batch;
     if (split) {
@@ -275,6 +276,7 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
     }
     CUC(cudaMalloc(&h->counters, sizeof(unsigned long long) * N_SLOTS));
     // host path: records per pipelined chunk (H2D of chunk i+1 overlaps the solve of chunk i); QPPVM_CHUNK overrides
+    if (const char* e = getenv("QPPVM_ROWWISE_EQUALITIES")) h->rowwise = atoi(e) != 0;
     h->chunk = 1024;
     if (const char* e = getenv("QPPVM_CHUNK")) { const long c = atol(e); if (c >= 64 && c <= (1 << 20)) h->chunk = c; }
     h->chunk_states = 4 * h->chunk;

@@ -212,3 +212,27 @@ def test_full_size_properties(torch_mod, oracle_mod, ci):
     o = oracle_mod.split_out(desc, oracle_mod.solve_batch(desc, recs[idx])[0])
     assert rel_inf(g["x"][idx], o["x"]).max() <= PRIMAL_TOL
     assert np.array_equal(g["active"][idx], o["active"])
+
+
+@pytest.mark.parametrize("ci", (1, 0, 2))
+def test_prepared_and_row_by_row_equality_paths_agree(torch_mod, monkeypatch, ci):
+    """The solve kernel adopts the equality working set the prepare kernel orthogonalised; a dependent row (or
+    non-finite data) makes it fall back to adding the equality rows one by one.  QPPVM_ROWWISE_EQUALITIES=1 at
+    create forces that fallback for every problem: both paths must give the same solutions and active sets."""
+    from qppvm_b200 import api
+    torch = torch_mod
+    desc = CONFIGS[ci]["desc"]
+    L = layout(desc)
+    recs = torch.from_numpy(gen.generate(desc, 600, 1234 + ci)).cuda()
+    fast = api.Solver(desc)
+    monkeypatch.setenv("QPPVM_ROWWISE_EQUALITIES", "1")
+    slow = api.Solver(desc)
+    monkeypatch.delenv("QPPVM_ROWWISE_EQUALITIES")
+    a, _ = fast.solve_batch(recs)
+    b, _ = slow.solve_batch(recs)
+    torch.cuda.synchronize()
+    ga, gb = api.split_out(L, a.cpu().numpy()), api.split_out(L, b.cpu().numpy())
+    assert (ga["status"] == 0).all() and np.array_equal(ga["status"], gb["status"])
+    assert rel_inf(ga["x"], gb["x"]).max() <= 1e-9 and rel_inf(ga["tau"], gb["tau"]).max() <= 1e-9
+    assert np.array_equal(ga["active"], gb["active"]) and max(ga["kkt"].max(), gb["kkt"].max()) <= KKT_TOL
+    assert not torch.equal(a, b)                           # (the two paths really are different arithmetic)
