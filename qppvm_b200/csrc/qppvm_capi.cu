@@ -268,6 +268,7 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->kernel, h->team, (size_t)sh->slab_bytes));
     if (occ < 1) { fail(nullptr, QPPVM_ERR_CUDA, "kernel does not fit on an SM (%d B smem)", sh->slab_bytes); delete h; return QPPVM_ERR_CUDA; }
     h->ctas_per_sm = occ;
+    if (const char* e = getenv("QPPVM_CTAS_PER_SM")) { const int c = atoi(e); if (c >= 1 && c < occ) h->ctas_per_sm = c; }   // profiling aid
     if (sh->factor_kernel) {
         CUC(cudaFuncSetAttribute(sh->factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh->factor_bytes));
         CUC(cudaFuncSetAttribute(sh->factor_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
