@@ -820,50 +820,63 @@ struct Solver {
         factor_core<MD, N, NB, TEAM>(tid, Jm, Ad, dg, db, u0, jd, w, eps);
     }
 
-    // out = sgn * J^T a   (thread j: column j of J is contiguous in i)
+    // Triangular mat-vecs with J.  A warp executes as many iterations as its longest lane, and with one column
+    // (row) per thread the long ones sit next to idle lanes: the part of a column beyond HALF entries goes to a
+    // helper thread (tid >= NB), whose partial sum travels through d1 (scratch of gs_pass, free here).
+    static constexpr int HALF = (NB - 1) / 2;                  // main lanes: entries [0, HALF] of their column
+    static constexpr int NHELP = NB - 1 - HALF;                // columns HALF + 1 .. NB - 1 have a helper
+    static_assert(NB + NHELP <= TEAM && NHELP <= KP, "helper lanes and their exchange slots");
+
+    // out = sgn * J^T a   (column j of J is contiguous in i)
     __device__ static __noinline__ void whiten(const double* a, double sgn, double* out)
     {
         QP_BIND
-        for (int j = tid; j < N; j += TEAM) {
-            double r;
-            if (j < NB) {
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                const double* col = Jm + j * (j + 1) / 2;
-                int i = 0;
+        double r = 0.0;
+        if (tid < NB + NHELP) {
+            const bool helper = tid >= NB;
+            const int jc = helper ? HALF + 1 + (tid - NB) : tid;
+            const double* col = Jm + jc * (jc + 1) / 2;
+            int i = helper ? HALF + 1 : 0;
+            const int last = helper ? jc : (jc < HALF ? jc : HALF);
+            double s0 = 0.0, s1 = 0.0;
 #pragma unroll 2
-                for (; i + 3 <= j; i += 4) {
-                    s0 = fma(col[i], a[i], s0); s1 = fma(col[i + 1], a[i + 1], s1);
-                    s2 = fma(col[i + 2], a[i + 2], s2); s3 = fma(col[i + 3], a[i + 3], s3);
-                }
-#pragma unroll 1
-                for (; i <= j; ++i) s0 = fma(col[i], a[i], s0);
-                r = (s0 + s1) + (s2 + s3);
-            } else r = jd[j] * a[j];
-            out[j] = sgn * r;
+            for (; i + 1 <= last; i += 2) { s0 = fma(col[i], a[i], s0); s1 = fma(col[i + 1], a[i + 1], s1); }
+            if (i <= last) s0 = fma(col[i], a[i], s0);
+            r = s0 + s1;
+            if (helper) d1[tid - NB] = r;
         }
         tm::sync();
+        if (tid < NB) out[tid] = sgn * (tid > HALF ? r + d1[tid - HALF - 1] : r);
+        else if (tid < N) out[tid] = sgn * jd[tid] * a[tid];
+        for (int jj = TEAM + tid; jj < N; jj += TEAM) out[jj] = sgn * jd[jj] * a[jj];
+        tm::sync();
     }
-    // xx = J uu  (thread i: row i of J is strided by LDJ across j, consecutive across threads)
+    // xx = J uu  (row i of J: entries J(i, j), j >= i, at Jm[j (j + 1) / 2 + i]); main lanes take the last
+    // HALF + 1 columns of their row, the helper of row i < NHELP the columns before those
     __device__ static __noinline__ void unwhiten(const double* uu, double* xx)
     {
         QP_BIND
-        for (int i = tid; i < N; i += TEAM) {
-            double r;
-            if (i < NB) {
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                int j = i;
-                const double* Ji = Jm + i;
+        double r = 0.0;
+        if (tid < NB + NHELP) {
+            const bool helper = tid >= NB;
+            const int ir = helper ? tid - NB : tid;
+            int jx = helper ? ir : (ir > NHELP ? ir : NHELP);
+            const int last = helper ? NHELP - 1 : NB - 1;
+            const double* Ji = Jm + ir;
+            double s0 = 0.0, s1 = 0.0;
 #pragma unroll 2
-                for (; j + 3 < NB; j += 4) {
-                    s0 = fma(Ji[j * (j + 1) / 2], uu[j], s0); s1 = fma(Ji[(j + 1) * (j + 2) / 2], uu[j + 1], s1);
-                    s2 = fma(Ji[(j + 2) * (j + 3) / 2], uu[j + 2], s2); s3 = fma(Ji[(j + 3) * (j + 4) / 2], uu[j + 3], s3);
-                }
-#pragma unroll 1
-                for (; j < NB; ++j) s0 = fma(Ji[j * (j + 1) / 2], uu[j], s0);
-                r = (s0 + s1) + (s2 + s3);
-            } else r = jd[i] * uu[i];
-            xx[i] = r;
+            for (; jx + 1 <= last; jx += 2) {
+                s0 = fma(Ji[jx * (jx + 1) / 2], uu[jx], s0);
+                s1 = fma(Ji[(jx + 1) * (jx + 2) / 2], uu[jx + 1], s1);
+            }
+            if (jx <= last) s0 = fma(Ji[jx * (jx + 1) / 2], uu[jx], s0);
+            r = s0 + s1;
+            if (helper) d1[ir] = r;
         }
+        tm::sync();
+        if (tid < NB) xx[tid] = tid < NHELP ? r + d1[tid] : r;
+        else if (tid < N) xx[tid] = jd[tid] * uu[tid];
+        for (int jj = TEAM + tid; jj < N; jj += TEAM) xx[jj] = jd[jj] * uu[jj];
         tm::sync();
     }
     __device__ static __forceinline__ double dot(const double* a, const double* b)
