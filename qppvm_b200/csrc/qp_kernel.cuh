@@ -23,6 +23,11 @@
 //     n x n rotation sweep.  Equalities (dyn-feas, level-0 optimality rows) enter first.
 //   * both priority levels, the qpOASES proximal regularisation re-solve, the KKT certificate
 //     and tau = M qdd + h - J^T f run in the same kernel.
+//   * ForceAcc shapes: the part of the above without data-dependent control flow -- the two
+//     factorisations and the orthogonalisation of the equality rows -- runs in a separate, lane-batched
+//     kernel (qp_factor_kernel: several (problem, level) pairs per CTA) and reaches the solve kernel
+//     through a per-problem workspace in global memory that is laid out like the shared-memory slab and
+//     fetched with bulk copies.  The Torque kind runs everything in qp_solve_kernel.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
