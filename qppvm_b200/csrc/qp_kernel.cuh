@@ -740,7 +740,8 @@ __device__ __noinline__ void factor_core(int j, double* Jm, const double* Ad, co
     double Jc[NB];
 #pragma unroll
     for (int i = 0; i < NB; ++i) Jc[i] = 0.0;
-    // (lanes without a column run it too, on zeros: a guard here makes ptxas keep Jc in local memory)
+    // (lanes without a column run it too, on zeros; predicates around these unrolled rows have made ptxas demote Jc
+    // to local memory: profiles/README.md, skipped-back-substitution experiment)
 #pragma unroll
     for (int i = NB - 1; i >= 0; --i) {
         double a0 = (j == i) ? 1.0 : 0.0, a1 = 0.0;
