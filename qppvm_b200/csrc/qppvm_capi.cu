@@ -69,6 +69,7 @@ struct qppvm_handle {
     double* ws[N_SLOTS]; int64_t ws_cap[N_SLOTS];   // factor workspaces, one per launch slot, allocated on first use
     int factor_ctas_per_sm;
     int rowwise;                           // QPPVM_ROWWISE_EQUALITIES=1 at create (tests): see Params::rowwise
+    cudaStream_t dev_stream; bool dev_used; cudaEvent_t ev_dev;   // last stream the caller's-stream slot ran on
     cudaStream_t streams[HOST_STREAMS];
     double* d_rec[HOST_STREAMS];
     unsigned char* d_out[HOST_STREAMS];
@@ -312,6 +313,7 @@ int qppvm_destroy(qppvm_handle* h)
     cudaFreeHost(h->h_one_rec); cudaFreeHost(h->h_one_out);
     cudaFree(h->counters);
     for (int i = 0; i < N_SLOTS; ++i) cudaFree(h->ws[i]);
+    if (h->ev_dev) cudaEventDestroy(h->ev_dev);
     delete h;
     return QPPVM_OK;
 }
@@ -325,7 +327,16 @@ int qppvm_solve_batch_diag(qppvm_handle* h, const double* rec, void* out, double
     if (((uintptr_t)rec & 15) || ((uintptr_t)out & 7) || ((uintptr_t)diag & 7))
         return fail(h, QPPVM_ERR_ARG, "records must be 16-byte aligned (TMA bulk copy), outputs 8-byte aligned");
     CU(h, cudaSetDevice(h->desc.device));
-    return launch(h, rec, out, diag, batch, (cudaStream_t)stream, HOST_STREAMS);
+    // The caller's-stream slot (work counter, prepare workspace) is reused from call to call: when the caller moves
+    // to another stream, order the new stream after the work still queued on the previous one.
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->dev_used && st != h->dev_stream) {
+        if (!h->ev_dev) CU(h, cudaEventCreateWithFlags(&h->ev_dev, cudaEventDisableTiming));
+        if (cudaEventRecord(h->ev_dev, h->dev_stream) == cudaSuccess) CU(h, cudaStreamWaitEvent(st, h->ev_dev, 0));
+        else { cudaGetLastError(); CU(h, cudaDeviceSynchronize()); }      // the previous stream is gone
+    }
+    h->dev_stream = st; h->dev_used = true;
+    return launch(h, rec, out, diag, batch, st, HOST_STREAMS);
 }
 
 int qppvm_solve_batch(qppvm_handle* h, const double* rec, void* out, int64_t batch, void* stream)

@@ -236,3 +236,24 @@ def test_prepared_and_row_by_row_equality_paths_agree(torch_mod, monkeypatch, ci
     assert rel_inf(ga["x"], gb["x"]).max() <= 1e-9 and rel_inf(ga["tau"], gb["tau"]).max() <= 1e-9
     assert np.array_equal(ga["active"], gb["active"]) and max(ga["kkt"].max(), gb["kkt"].max()) <= KKT_TOL
     assert not torch.equal(a, b)                           # (the two paths really are different arithmetic)
+
+
+def test_one_handle_moved_between_streams(torch_mod):
+    """The caller's-stream launch slot (work counter, prepare workspace) is reused across calls: calls issued
+    back to back on different streams, without any synchronisation in between, must not disturb each other."""
+    from qppvm_b200 import api
+    torch = torch_mod
+    desc = CONFIGS[1]["desc"]
+    s = api.Solver(desc)
+    a = torch.from_numpy(gen.generate(desc, 3000, 501)).cuda()
+    b = torch.from_numpy(gen.generate(desc, 2000, 502)).cuda()
+    ref_a, ref_b = s.solve_batch(a)[0].clone(), s.solve_batch(b)[0].clone()
+    torch.cuda.synchronize()
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for rep in range(6):
+        st, rec = (sa, a) if rep % 2 == 0 else (sb, b)
+        outs.append(s.solve_batch(rec, stream=st)[0])
+    torch.cuda.synchronize()
+    for rep, o in enumerate(outs):
+        assert torch.equal(o, ref_a if rep % 2 == 0 else ref_b)
