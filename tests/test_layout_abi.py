@@ -91,3 +91,26 @@ def test_product_does_not_reference_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 src = open(os.path.join(dp, fn)).read()
                 assert "oracle" not in src.lower() or fn == "__init__.py" and False, os.path.join(dp, fn)
+
+
+def test_null_handle_is_an_argument_error_everywhere():
+    """No entry point dereferences a null handle (no GPU needed: each returns before touching the device)."""
+    raw = ctypes.CDLL(api.LIB_PATH)
+    P, I64, D = ctypes.c_void_p, ctypes.c_int64, ctypes.c_double
+    calls = {
+        "qppvm_destroy": (P,), "qppvm_solve_batch": (P, P, P, I64, P), "qppvm_solve_batch_diag": (P, P, P, P, I64, P),
+        "qppvm_solve_batch_host": (P, P, P, I64), "qppvm_solve_batch_host_async": (P, P, P, I64), "qppvm_host_sync": (P,),
+        "qppvm_solve_one": (P, P, P), "qppvm_set_robot": (P, P), "qppvm_records_from_states": (P, P, P, I64, P),
+        "qppvm_solve_states_host": (P, P, P, I64), "qppvm_solve_states_host_async": (P, P, P, I64),
+        "qppvm_integrate_states": (P, P, P, D, I64, P), "qppvm_rollout_states": (P, P, P, ctypes.c_int, D, I64, P),
+        "qppvm_fp64_peak": (P, P),
+    }
+    for name, sig in calls.items():
+        fn = getattr(raw, name)
+        fn.argtypes = list(sig); fn.restype = ctypes.c_int
+        args = [None if t is P else (1e-3 if t is D else 1) for t in sig]
+        assert fn(*args) == 1, name                      # QPPVM_ERR_ARG
+    raw.qppvm_kernel_launches.argtypes = [P]; raw.qppvm_kernel_launches.restype = I64
+    assert raw.qppvm_kernel_launches(None) == 0
+    raw.qppvm_last_error.argtypes = [P]; raw.qppvm_last_error.restype = ctypes.c_char_p
+    assert raw.qppvm_last_error(None) is not None
