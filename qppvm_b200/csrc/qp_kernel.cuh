@@ -1577,12 +1577,15 @@ struct FactorShape {
 
 template <class P>
 __global__ void __launch_bounds__(FactorShape<P>::THREADS)
-qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long long batch, Params prm)
+qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long long batch, Params prm,
+                 unsigned long long* __restrict__ counter)
 {
     using F = FactorShape<P>;
     using S = Slab<P>;
     constexpr int N = P::N;
     const int t = threadIdx.x;
+    // the work counter of the solve kernel that follows on this stream (the previous solve is complete: stream order)
+    if (counter && blockIdx.x == 0 && t == 0) *counter = 0ull;
     const int f = t / F::GS, lane = t - f * F::GS;
     double* const blk = reinterpret_cast<double*>(g_smem) + (f < F::FPC ? f : 0) * F::BLOCK;
     double* const Jm = blk; double* const Ad = blk + F::O_AD; double* const dg = blk + F::O_DG;

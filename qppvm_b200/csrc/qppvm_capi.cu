@@ -136,12 +136,12 @@ int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t 
             const long long fcap = (long long)h->sm_count * h->factor_ctas_per_sm;
             const long long fneed = (2 * b + h->shape->factor_pairs - 1) / h->shape->factor_pairs;
             const int fgrid = (int)(fneed < fcap ? fneed : fcap);
-            void* fargs[] = {(void*)&r, (void*)&ws, (void*)&b, (void*)&prm};
+            void* fargs[] = {(void*)&r, (void*)&ws, (void*)&b, (void*)&prm, (void*)&counter};   // also resets the counter
             CU(h, cudaLaunchKernel(h->shape->factor_kernel, dim3(fgrid), dim3(h->shape->factor_threads), fargs,
                                    (size_t)h->shape->factor_bytes, st));
             h->launches += 1;
         }
-        if (counter) CU(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+        if (counter && !split) CU(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
         const int grid = (int)(b < cap ? b : cap);
         void* args[] = {(void*)&r, (void*)&o, (void*)&dgp, (void*)&b, (void*)&prm, (void*)&counter, (void*)&ws};
         CU(h, cudaLaunchKernel(h->kernel, dim3(grid), dim3(h->team), args, (size_t)h->shape->slab_bytes, st));
