@@ -2,9 +2,12 @@
 """bench.py — whole-body QP solves/sec on N B200s (one process per GPU), next to the CPU path.
 
 A step = one pass of the hot path (2-level cascade + output recovery, what one control_loop tick
-does: ref:src/ForceAcc.cpp:184-219) over one batch of BASELINE.json configs[1]:
-"ForceAcc batched QP, 4096 synthetic states, 2 foot contacts" per GPU (weak scaling: every rank owns
-its own, differently seeded, batches; the path shards with no data-path collective).
+does: ref:src/ForceAcc.cpp:184-219) over one batch of synthetic states.  Workload (BASELINE.json):
+  * one GPU (no torchrun):  configs[2], "QPPVM batched, 65536 states, WALK-MAN-like 33-DoF, 4 contacts
+    (feet+hands)" with friction cones + torque limits: the largest single-GPU configuration;
+  * under torchrun (N > 1): configs[3], ONE batch of 2^20 such states split over the N ranks (strong scaling;
+    the path shards with no data-path collective).
+configs[0], [1], [4] are parity-test cases; `--config i` still runs any of them.
 
     python bench.py --gpus 1 --steps 1000 --warmup 10
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
@@ -34,10 +37,11 @@ F_ALG = {(29, 2): 182e3, (33, 4): 335e3}
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=1, help="BASELINE.json config index (default 1 = the metric's config)")
+    ap.add_argument("--config", type=int, default=-1,
+                    help="BASELINE.json config index (default: 2 on one GPU, 3 = 2^20 states sharded under torchrun)")
     ap.add_argument("--batch", type=int, default=0, help="override records per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
@@ -55,32 +59,54 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    """Samples SM clock and throttle reasons through NVML.  Started before the warm-up (NVML initialisation is
+    slower than a short timed region); one sample is taken synchronously when the timed region is armed, the thread
+    keeps sampling every 10 ms until it is disarmed."""
+
+    NAMES = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+             "hw_power_brake_slowdown": 0x80, "applications_clocks_setting": 0x2}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
-
-    def run(self):
+        self.index, self.stop_flag, self.armed = index, False, False
+        self.samples, self.reasons, self.max_mhz, self.nv, self.h = [], set(), None, None, None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
-                     "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80, "applications_clocks_setting": 0x2}
-            while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-                time.sleep(0.02)
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
         except Exception as e:  # NVML unavailable: report that rather than invent clocks
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def sample(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for k, bit in self.NAMES.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception as e:
+            self.reasons.add("nvml_error:%s" % type(e).__name__)
+
+    def arm(self):
+        self.sample()            # the GPU is busy with the warm-up's tail / idle-to-busy edge: kept as sample 0
+        self.armed = True
+
+    def disarm(self):
+        self.armed = False
+        self.stop_flag = True
+
+    def run(self):
+        while not self.stop_flag:
+            if self.armed:
+                self.sample()
+            time.sleep(0.01)
 
     def result(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
@@ -159,6 +185,8 @@ def run_reference(args, desc, L, cfg_name, batch):
 def main():
     args = parse()
     from qppvm_b200.layout import CONFIGS, layout
+    if args.config < 0:
+        args.config = 3 if max(args.gpus, int(os.environ.get("WORLD_SIZE", "1"))) > 1 else 2
     cfg = CONFIGS[args.config]
     desc = cfg["desc"]
     L = layout(desc)
@@ -223,10 +251,13 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- device-resident throughput ("value") ------------------------------------------------------
+    sampler = ClockSampler(local); sampler.start()
     for i in range(args.warmup):
         solver.solve_batch(d_recs[i % N_BUF], out=d_out[i % N_BUF])
     barrier()
-    sampler = ClockSampler(local); sampler.start()
+    # clocks: one NVML sample right here (GPU still busy with the warm-up's tail), then every 10 ms while the K timed
+    # steps run (a configs[2] step is tens of milliseconds)
+    sampler.arm()
     l0 = solver.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -234,7 +265,7 @@ def main():
         solver.solve_batch(d_recs[i % N_BUF], out=d_out[i % N_BUF])
     e1.record(stream)
     barrier()
-    sampler.stop_flag = True; sampler.join()
+    sampler.disarm(); sampler.join()
     launches = solver.kernel_launches - l0
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     # every counted solve must have converged with KKT <= 1e-6 (in-kernel certificate)
@@ -383,8 +414,8 @@ def main():
     launch_s = t_s / max(1, args.steps)
     per_step = max(1, int(round(launches / max(1, args.steps))))
     kname = "qp_solve_kernel<ForceAcc<%d,%d,%d>>" % (desc.n_a, desc.n_contacts, desc.flags) if desc.kind == 1 else "qp_solve_kernel<Torque<%d>>" % desc.n_a
-    if per_step == 2:
-        kname = "qp_factor_kernel + " + kname + " (2 launches per step, timed together)"
+    if per_step >= 2:
+        kname = "qp_factor_kernel + " + kname + " (%d launches per step: the batch runs in workspace-sized passes of one factor + one solve launch, timed together)" % per_step
     alg_bytes = L.algorithmic_bytes() * batch
     fp64_peak = solver.fp64_peak_tflops()
     f_alg = F_ALG.get((desc.n_a, desc.n_contacts))
@@ -396,16 +427,20 @@ def main():
             traffic = int(tj["dram_bytes_per_launch"] / tj["records_per_launch"] * batch)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "achieved": alg_bytes / launch_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": alg_bytes / launch_s / 1e9 / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                "kernel": kname, "launches_per_step": per_step,
-                "note": "path is FP64-pipe/latency bound (SURVEY 8(d)); see roofline_fp64 for the binding roof"}
-    roofline_fp64 = None
-    if f_alg:
-        ach = f_alg * batch / launch_s / 1e12
-        roofline_fp64 = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-                         "peak_source": "measured in this run (register-resident DFMA kernel)",
-                         "flop_per_solve": f_alg}
+    roofline_hbm = {"bound": "hbm", "achieved": alg_bytes / launch_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": alg_bytes / launch_s / 1e9 / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                    "bytes_per_solve": L.algorithmic_bytes(),
+                    "note": "not the binding roof: arithmetic intensity 15-18 FLOP/B vs an FP64 ridge of ~5.5 FLOP/B"}
+    f_alg = f_alg or 0.0
+    ach = f_alg * batch / launch_s / 1e12
+    # The binding roof of this path is the FP64 FMA pipe: algorithmic FLOPs per launch (minimum-work
+    # model) / launch time, against the FP64 peak measured in this run (MEASURED_PEAKS.json has no FP64
+    # figure).  `traffic` stays the ncu DRAM bytes of the same launch(es).
+    roofline = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": ach / fp64_peak if fp64_peak else None, "traffic": traffic,
+                "peak_source": "measured in this run (register-resident DFMA kernel; no FP64 figure in MEASURED_PEAKS.json)",
+                "flop_per_solve": f_alg, "kernel": kname, "launches_per_step": per_step,
+                "note": "FP64 CUDA-core path (tcgen05 has no FP64): `bound` names the binding roof; HBM roof in roofline_hbm"}
 
     line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_s / args.steps * 1e3, "higher_is_better": True,
@@ -416,7 +451,7 @@ def main():
                     "d2h_bytes_per_step": batch * L.out_bytes, "steps": e2e_steps,
                     "api": "qppvm_solve_batch_host (pinned host buffers in/out)"},
             "gpu_launches": int(launches),
-            "roofline": roofline, "roofline_fp64": roofline_fp64,
+            "roofline": roofline, "roofline_hbm": roofline_hbm,
             "converged_frac": frac.item(), "kkt_max": kkt_max}
     if sg:
         line["scatter_gather"] = sg

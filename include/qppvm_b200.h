@@ -140,6 +140,15 @@ int qppvm_solve_batch(qppvm_handle* h, const double* records_dev, void* out_dev,
 /* Same plus the diagnostic block (level-0 solution and the multipliers of both levels). */
 int qppvm_solve_batch_diag(qppvm_handle* h, const double* records_dev, void* out_dev,
                            double* diag_dev, int64_t batch, void* cuda_stream);
+/* Hot-started batched solve.  The reference keeps ONE QPOases_sot alive across control ticks
+ * (ref:include/QPPVM_RT_plugin/QPPVMPlugin.h:64, built once ref:src/QPPVMPlugin.cpp:188 / ref:src/ForceAcc.cpp:135-137,
+ * called every tick ref:src/QPPVMPlugin.cpp:246 / ref:src/ForceAcc.cpp:189), so qpOASES starts every tick from the
+ * previous tick's working set.  `warm_dev` is that state for a batch: QPPVM_WARM_WORDS uint32 per problem (active-row
+ * masks of level 0 | level 1, row ids as in qppvm_layout), read at the start of each problem and overwritten with the
+ * working set it converged to; all-zero words = cold start.  The result is the same unique minimiser either way. */
+#define QPPVM_WARM_WORDS 8
+int qppvm_solve_batch_warm(qppvm_handle* h, const double* records_dev, void* out_dev, uint32_t* warm_dev,
+                           int64_t batch, void* cuda_stream);
 /* Batched solve with HOST buffers: chunked H2D / solve / D2H overlapped on internal
  * streams; returns after the outputs are in `out_host`. */
 int qppvm_solve_batch_host(qppvm_handle* h, const double* records_host, void* out_host,
@@ -195,8 +204,9 @@ int64_t qppvm_kernel_launches(const qppvm_handle* h);
 /* Measures the FP64 FMA peak of the device (TFLOP/s) with a register-resident DFMA
  * kernel; the compute-roofline denominator (not in MEASURED_PEAKS.json). */
 int qppvm_fp64_peak(qppvm_handle* h, double* tflops);
-/* Shapes compiled into this library: writes up to `cap` (n_a, c, flags) triples, returns count. */
-int qppvm_supported_shapes(int32_t* triples, int cap);
+/* Shapes compiled into this library: writes up to `cap` QUADRUPLES (kind, n_a, n_contacts, flags), i.e. 4 * cap
+ * int32, and returns the number of shapes available (call with quads = NULL or cap = 0 to size the buffer). */
+int qppvm_supported_shapes(int32_t* quads, int cap);
 
 #ifdef __cplusplus
 }

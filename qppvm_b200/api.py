@@ -38,7 +38,7 @@ EXPORTS = ("qppvm_get_layout", "qppvm_create", "qppvm_destroy", "qppvm_last_erro
            "qppvm_solve_batch_diag", "qppvm_solve_batch_host", "qppvm_solve_one", "qppvm_kernel_launches",
            "qppvm_fp64_peak", "qppvm_supported_shapes", "qppvm_state_doubles", "qppvm_set_robot",
            "qppvm_records_from_states", "qppvm_solve_states_host", "qppvm_solve_batch_host_async", "qppvm_host_sync",
-           "qppvm_solve_states_host_async", "qppvm_integrate_states", "qppvm_rollout_states")
+           "qppvm_solve_states_host_async", "qppvm_integrate_states", "qppvm_rollout_states", "qppvm_solve_batch_warm")
 
 _lib = None
 
@@ -59,6 +59,7 @@ def load_library():
         lib.qppvm_last_error.restype = C.c_char_p
         lib.qppvm_solve_batch.argtypes = [P, P, P, C.c_int64, P]
         lib.qppvm_solve_batch_diag.argtypes = [P, P, P, P, C.c_int64, P]
+        lib.qppvm_solve_batch_warm.argtypes = [P, P, P, P, C.c_int64, P]
         lib.qppvm_solve_batch_host.argtypes = [P, P, P, C.c_int64]
         lib.qppvm_solve_one.argtypes = [P, P, P]
         lib.qppvm_solve_batch_host_async.argtypes = [P, P, P, C.c_int64]
@@ -147,6 +148,20 @@ class Solver:
             self._h, records.data_ptr(), out.data_ptr(), diag.data_ptr() if diag is not None else None,
             B, st.cuda_stream))
         return out, diag
+
+    def solve_batch_warm(self, records, warm, out=None, stream=None):
+        """Hot-started batched solve: `warm` is a CUDA int32 tensor (B, 8), the working sets of the previous tick
+        (in/out; zeros = cold start)."""
+        import torch
+        L = self.layout
+        assert records.is_cuda and records.dtype == torch.float64 and records.is_contiguous() and records.shape[1] == L.rec_doubles
+        B = records.shape[0]
+        assert warm.is_cuda and warm.dtype == torch.int32 and warm.is_contiguous() and warm.shape == (B, 8)
+        if out is None:
+            out = torch.empty((B, L.out_doubles), dtype=torch.float64, device=records.device)
+        st = torch.cuda.current_stream(records.device) if stream is None else stream
+        self._check(self._lib.qppvm_solve_batch_warm(self._h, records.data_ptr(), out.data_ptr(), warm.data_ptr(), B, st.cuda_stream))
+        return out
 
     # ---- host path: the reference-facing call (host buffers in, host buffers out) ----------
     def solve_batch_host(self, records: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:

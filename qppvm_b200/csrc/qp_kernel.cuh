@@ -36,6 +36,9 @@
 #ifndef QPPVM_SPLIT
 #define QPPVM_SPLIT 1
 #endif
+#ifndef QPPVM_SELECTIVE_GS
+#define QPPVM_SELECTIVE_GS 1     // second Gram-Schmidt pass only when the first one cancelled more than half of the norm
+#endif
 namespace qppvm {
 
 // Active-set capacity KMAX (eq + ineq, <= 32 so one warp lane per active row), per problem shape.
@@ -209,6 +212,14 @@ struct ForceAcc {
     // inequality slots scanned each iteration
     static constexpr int NI_BOX = 3 * NC, NI_CONE = CONES ? 5 * NC : 0, NI_TAU = TLIM ? NA : 0;
     static constexpr int NI = NI_BOX + NI_CONE + NI_TAU;
+    // Slots [0, NI_CHEAP) are rows over the force variables of ONE contact (box, friction pyramid).  The force columns
+    // carry no task entries, so they stay diagonal in the whitening (x_f = jd u_f): such a row is evaluated from u
+    // without the triangular product, and its whitened normal has three entries.  The torque-limit rows are dense.
+    static constexpr int NI_CHEAP = NI_BOX + NI_CONE;
+    // The loop over the working-set changes ends with a scan of the dense slots at the final x: their values
+    // (M_a qdd - J_a^T f) are kept and reused by the KKT check and the torque recovery.
+    static constexpr bool TAUVAL = TLIM;
+    static constexpr int NTV = TLIM ? NA + (NA & 1) : 0;
     // record offsets (doubles)
     __host__ __device__ static constexpr int OFF_M_() { return 6 * (NA_ + 6) + NC_ * 6 * (NA_ + 6); }
     __host__ __device__ static constexpr int REC_()
@@ -353,6 +364,31 @@ struct ForceAcc {
         }
     }
 
+    // Force-only row (box rows with k < 3, pyramid rows): first column and the three coefficients.
+    __device__ static __forceinline__ bool sparse_row(const double* rec, int row, int& j0, double& a0, double& a1, double& a2)
+    {
+        if (row >= ROW_BOX && row < ROW_CONE) {
+            const int ci = (row - ROW_BOX) / 6, k = (row - ROW_BOX) % 6;
+            j0 = NV + 3 * ci;
+            a0 = k == 0 ? 1.0 : 0.0; a1 = k == 1 ? 1.0 : 0.0; a2 = k == 2 ? 1.0 : 0.0;
+            return true;
+        }
+        if (CONES && row >= ROW_CONE && row < ROW_TAU) {
+            const int ci = (row - ROW_CONE) / 5, jr = (row - ROW_CONE) % 5;
+            const double* R = rec + OFF_CONE - SB + 10 * ci;
+            const double mu = R[9] * 0.70710678118654752440;
+            const double c0 = jr == 0 ? 1.0 : (jr == 1 ? -1.0 : 0.0);
+            const double c1 = jr == 2 ? 1.0 : (jr == 3 ? -1.0 : 0.0);
+            const double c2 = jr == 4 ? -1.0 : -mu;
+            j0 = NV + 3 * ci;
+            a0 = c0 * R[0] + c1 * R[1] + c2 * R[2];
+            a1 = c0 * R[3] + c1 * R[4] + c2 * R[5];
+            a2 = c0 * R[6] + c1 * R[7] + c2 * R[8];
+            return true;
+        }
+        return false;
+    }
+
     // Inequality slot q -> (row id, value a.x, lo, hi).  One slot per thread.
     __device__ static void eval_slot(const double* rec, const double* g, int q, const double* x,
                                      int& row, double& val, double& lo, double& hi)
@@ -392,6 +428,15 @@ struct ForceAcc {
         }
     }
 
+    // row id and bounds of a dense slot (q >= NI_CHEAP)
+    __device__ static __forceinline__ void dense_slot_bounds(const double* rec, int q, int& row, double& lo, double& hi)
+    {
+        const int a = q - NI_CHEAP;
+        row = ROW_TAU + a;
+        const double ha = rec[OFF_H - SB + 6 + a];
+        lo = rec[OFF_TAULIM - SB + a] - ha; hi = rec[OFF_TAULIM - SB + NA + a] - ha;
+    }
+
     // Level-0 task value A0 x0* (6 numbers) -> eopt.
     template <int TEAM>
     __device__ static void task0_value(const double*, const double* g, const double* x, double* eopt, int tid)
@@ -407,12 +452,14 @@ struct ForceAcc {
     }
 
     // tau = (M qdd + h - sum J_c^T [f;0]) actuated rows  (ref:src/ForceAcc.cpp:206-219)
+    // (tv: the values M_a qdd - J_a^T f left by the last scan of the torque-limit slots, shapes with TAUVAL)
     template <int TEAM>
-    __device__ static void recover(const double* rec, const double* g, const double* x, double* tau_out, bool ok, int tid)
+    __device__ static void recover(const double* rec, const double* g, const double* x, const double* tv, double* tau_out, bool ok, int tid)
     {
         for (int a = tid; a < NA; a += TEAM) {
             double v = 0.0;
-            if (ok) {
+            if (ok && TAUVAL) v = rec[OFF_H - SB + 6 + a] + tv[a];
+            else if (ok) {
                 const int i = 6 + a;
                 v = rec[OFF_H - SB + i];
                 for (int j = 0; j < NV; ++j) v = fma(M(rec, i, j), x[j], v);
@@ -438,7 +485,11 @@ struct Torque {
     static constexpr int NV = NA, N = NA, NB = NA;
     static constexpr int MD0 = 6, MD1 = NA, MD_MAX = NA;
     static constexpr int ROW_BOX = 0, ROW_OPT = NA, NROWS = NA + QPPVM_M0;
-    static constexpr int NI = NA;
+    static constexpr int NI = NA, NI_CHEAP = 0;              // every bound row is a (dense) row of J in whitened coordinates
+    static constexpr bool TAUVAL = false;
+    static constexpr int NTV = 0;
+    __device__ static __forceinline__ void dense_slot_bounds(const double*, int, int&, double&, double&) {}
+    __device__ static __forceinline__ bool sparse_row(const double*, int, int&, double&, double&, double&) { return false; }
     static constexpr int OFF_J = 0, OFF_M = 12 * NA, OFF_H = OFF_M + NA * (NA + 1) / 2, OFF_FEE = OFF_H + NA;
     static constexpr int OFF_TAUJ = OFF_FEE + 12, OFF_TAULIM = OFF_TAUJ + NA;
     static constexpr int REC_UNPADDED = OFF_TAULIM + 2 * NA;
@@ -586,7 +637,7 @@ struct Torque {
     }
     // tau_d = tau_qp + h ; tau_qp = 0 on failure (ref:src/QPPVMPlugin.cpp:246-256)
     template <int TEAM>
-    __device__ static void recover(const double* rec, const double*, const double* x, double* tau_out, bool ok, int tid)
+    __device__ static void recover(const double* rec, const double*, const double* x, const double*, double* tau_out, bool ok, int tid)
     {
         for (int a = tid; a < NA; a += TEAM) tau_out[a] = (ok ? x[a] : 0.0) + rec[OFF_H + a];
     }
@@ -621,7 +672,8 @@ struct Slab {
     static constexpr int SZ_Q = SZ_Q_RAW + (SZ_Q_RAW & 1);     // even: RN and the vectors stay 16-byte aligned
     static constexpr int O_R = O_Q + SZ_Q;
     static constexpr int O_VEC = O_R + KMAX * LDR + ((KMAX * LDR) & 1);    // u0 u x w w2 av dg db xp jd
-    static constexpr int O_SMALL = O_VEC + 10 * VEC;  // d1 rr lam (KP each) | eopt 8 | red 16
+    static constexpr int O_TV = O_VEC + 10 * VEC;     // values of the dense inequality slots at the last full scan
+    static constexpr int O_SMALL = O_TV + P::NTV;     // d1 rr lam (KP each) | eopt 8 | red 16
     static constexpr int O_MBAR = O_SMALL + 4 * KP + 8 + 16;   // d1 rr lam rdi | 2 mbarriers: record staging, workspace copies
     static constexpr int O_STATE = O_MBAR + 2;        // ints: k, n_act_ineq, iters, ws phase | act_row[KP] | act_sgn[KP]
     static constexpr int O_CSTATE = O_STATE + 2 + KP;     // bytes
@@ -788,7 +840,7 @@ struct Solver {
     QP_SM(w2, S::O_VEC + 4 * S::VEC) QP_SM(av, S::O_VEC + 5 * S::VEC) QP_SM(dg, S::O_VEC + 6 * S::VEC)
     QP_SM(db, S::O_VEC + 7 * S::VEC) QP_SM(xp, S::O_VEC + 8 * S::VEC) QP_SM(jd, S::O_VEC + 9 * S::VEC)
     QP_SM(d1, S::O_SMALL) QP_SM(rr, S::O_SMALL + KP) QP_SM(lam, S::O_SMALL + 2 * KP) QP_SM(rdi, S::O_SMALL + 3 * KP)
-    QP_SM(eopt, S::O_SMALL + 4 * KP) QP_SM(red, S::O_SMALL + 4 * KP + 8) QP_SM(ext, S::O_EXT)
+    QP_SM(eopt, S::O_SMALL + 4 * KP) QP_SM(red, S::O_SMALL + 4 * KP + 8) QP_SM(ext, S::O_EXT) QP_SM(tv, S::O_TV)
 #undef QP_SM
     __device__ static __forceinline__ uint64_t* mbar_() { return reinterpret_cast<uint64_t*>(g_smem) + S::O_MBAR; }
     __device__ static __forceinline__ uint64_t* mbar_ws_() { return reinterpret_cast<uint64_t*>(g_smem) + S::O_MBAR + 1; }
@@ -892,14 +944,17 @@ struct Solver {
         return tm::sum(s, red_());
     }
 
-    // d1 (+)= Q1^T v ; v -= Q1 d  (one Gram-Schmidt pass against the k active normals).
+    // One Gram-Schmidt pass against the k active normals, in two halves: gs_dots: rr = Q1^T v, d1 (+)= rr;
+    // gs_update: dst = src - Q1 rr.
     // The k dot products of length N are shared by all threads: column c is split over SEG = TEAM / CW threads
     // (CW = 16 or 32 columns wide), each walking every SEG-th row; the partial sums meet through a shuffle inside
-    // the warp and a small exchange buffer across warps (red[0 .. 2 * KMAX)).
-    __device__ static __noinline__ void gs_pass(double* v, bool accumulate, int k)
+    // the warp and a small exchange buffer across warps (`part`: WARPS x 32 doubles over av | dg, both dead during
+    // the active-set iterations: dg / db are reloaded by kkt()).
+    static_assert(2 * S::VEC >= Team<TEAM>::WARPS * 32, "the exchange buffer of gs_dots covers av | dg");
+    __device__ static __noinline__ void gs_dots(const double* v, bool accumulate, int k)
     {
         QP_BIND
-        double* const part = w2 == v ? av : w2;            // WARPS x 32 partial sums; never the vector being processed
+        double* const part = av;
         {
             const bool narrow = k <= 16;
             const int cw = narrow ? 16 : 32;
@@ -927,16 +982,35 @@ struct Solver {
             d1[tid] = accumulate ? d1[tid] + sacc : sacc;
         }
         tm::sync();
+    }
+    // The same for a normal with three entries (columns j0 .. j0 + 2: a force-only row): three products per column.
+    __device__ static __forceinline__ void gs_dots_sparse(const double* v, int j0, int k)
+    {
+        QP_BIND
+        if (tid < k) {
+            const double sacc = fma(Q1[j0 * LDQ + tid], v[j0], fma(Q1[(j0 + 1) * LDQ + tid], v[j0 + 1], Q1[(j0 + 2) * LDQ + tid] * v[j0 + 2]));
+            rr[tid] = sacc; d1[tid] = sacc;
+        }
+        tm::sync();
+    }
+    __device__ static __noinline__ void gs_update(const double* src, double* dst, int k)
+    {
+        QP_BIND
         for (int i = tid; i < N; i += TEAM) {
-            double s0 = v[i], s1 = 0.0;
+            double s0 = src[i], s1 = 0.0;
             const double* q = Q1 + i * LDQ;
             int c = 0;
 #pragma unroll 2
             for (; c + 1 < k; c += 2) { s0 = fma(-q[c], rr[c], s0); s1 = fma(-q[c + 1], rr[c + 1], s1); }
             if (c < k) s0 = fma(-q[c], rr[c], s0);
-            v[i] = s0 + s1;
+            dst[i] = s0 + s1;
         }
         tm::sync();
+    }
+    __device__ static __forceinline__ void gs_pass(double* v, bool accumulate, int k)
+    {
+        gs_dots(v, accumulate, k);
+        gs_update(v, v, k);
     }
 
     // rr = RN^-1 d1 (back substitution in warp 0; lane c holds component c)
@@ -962,7 +1036,7 @@ struct Solver {
         QP_BIND
         const int row = act_row[l];
         tm::sync();
-        if (tid == 0) { cstate[row] = 0; st[0] = k - 1; st[1] -= 1; }
+        if (tid == 0) { cstate[row] &= 4; st[0] = k - 1; st[1] -= 1; }
         // shift columns l+1.. of RN (and bookkeeping) one to the left; thread t only touches row t
         if (tid < KMAX)
             for (int c = l; c < k - 1; ++c)
@@ -998,24 +1072,33 @@ struct Solver {
         tm::sync();
     }
 
-    // Adds constraint `row` with sign sgn (normal sgn*a, already whitened into w), current slack sp <= 0.
+    // Adds constraint `row` with sign sgn (normal sgn*a, already whitened into w; ww = w.w), current slack sp <= 0.
+    // sj0 >= 0: w has three entries, columns sj0 .. sj0 + 2 (force-only row).
     // Returns status; handles partial steps (drops) per Goldfarb-Idnani.
-    __device__ static __noinline__ int add_constraint(int row, int sgn, bool is_eq, double sp, double bound_abs, int max_iter)
+    __device__ static __noinline__ int add_constraint(int row, int sgn, bool is_eq, double sp, double bound_abs, int max_iter,
+                                                      double ww, int sj0)
     {
         QP_BIND
         double up = 0.0;
-        const double ww = dot(w, w);
         int k = st[0], nai = st[1], iters = st[2];
 #pragma unroll 1
         for (;;) {
             if (iters >= max_iter) { tm::sync(); if (tid == 0) st[2] = iters; tm::sync(); return QPPVM_STATUS_MAX_ITER; }
-            for (int i = tid; i < N; i += TEAM) w2[i] = w[i];
-            tm::sync();
             double nrm2 = ww;
             if (k > 0) {
-                gs_pass(w2, false, k);
-                gs_pass(w2, true, k);                         // CGS2: "twice is enough"
+                if (sj0 >= 0) gs_dots_sparse(w, sj0, k); else gs_dots(w, false, k);
+                gs_update(w, w2, k);
                 nrm2 = dot(w2, w2);
+#if QPPVM_SELECTIVE_GS
+                if (nrm2 < 0.5 * ww)                          // Daniel-Gragg-Kaufman-Stewart: a second pass only after cancellation
+#endif
+                {
+                    gs_pass(w2, true, k);                     // CGS2: "twice is enough"
+                    nrm2 = dot(w2, w2);
+                }
+            } else {
+                for (int i = tid; i < N; i += TEAM) w2[i] = w[i];
+                tm::sync();
             }
             const bool dependent = !(nrm2 > 1e-22 * ww) || k >= N;
             const bool full = k >= KMAX;
@@ -1058,7 +1141,7 @@ struct Solver {
                 if (tid < k) RN[k * LDR + tid] = d1[tid];
                 if (tid == 0) {
                     RN[k * LDR + k] = nr; rdi[k] = inv; lam[k] = up; act_row[k] = row; act_sgn[k] = is_eq ? 2 * sgn : sgn;
-                    cstate[row] = (is_eq || sgn > 0) ? 1 : 3;
+                    cstate[row] = (cstate[row] & 4) | ((is_eq || sgn > 0) ? 1 : 3);
                     st[0] = k + 1; st[1] = nai + (is_eq ? 0 : 1); st[2] = iters;
                 }
                 tm::sync();
@@ -1069,29 +1152,45 @@ struct Solver {
         }
     }
 
-    // Scan all inactive inequality slots at x; returns the most violated row (-1: none) and publishes its
-    // slack (<0), sign and |bound| in red[8..10].
-    __device__ static __noinline__ int scan()
+    // Scan the inactive inequality slots [q0, q1) at x; returns the most violated row (-1: none) and publishes its
+    // slack (<0), sign and |bound| in red[8..10].  Rows flagged as candidates (cstate bit 2: the working set of the
+    // previous level / previous tick) go first: among violated candidates the most violated one, otherwise the most
+    // violated row -- any violated row is a valid Goldfarb-Idnani pivot, and the ones that ended up active in a
+    // neighbouring problem are rarely dropped again.
+    // TAUVAL: the values of the dense slots are kept (tv[q - q0]) for the KKT check and the output recovery.
+    template <bool TAUVAL>
+    __device__ static __noinline__ int scan(int q0, int q1, double* tv)
     {
         QP_BIND
-        double worst = 0.0; int widx = 0x7fffffff; int wsgn = 0; double wb = 0.0;
-        for (int q = tid; q < P::NI; q += TEAM) {
+        double worst = 0.0, wkey = 0.0; int widx = 0x7fffffff; int wsgn = 0; double wb = 0.0;
+        for (int q = q0 + tid; q < q1; q += TEAM) {
             int r; double val, lo, hi;
             P::eval_slot(rec, ext, q, x, r, val, lo, hi);
+            if (TAUVAL) tv[q - q0] = val;
             // cstate: 0 inactive, 1 active at lA, 3 active at uA, 2 implied / weakly active.  The side opposite to an
             // active one is still checked: an empty box (lA > uA) must surface as infeasible, not be masked.
-            const int cs = cstate[r];
+            const int cs = cstate[r] & 3;
+            const double pri = (cstate[r] & 4) ? 0x1p100 : 1.0;
             if (cs != 2) {
                 const double tol = 1e-9 * fmax(1.0, fabs(val));
                 const double sl = val - lo, su = hi - val;
-                if (cs != 1 && lo > -0.5 * QPPVM_INFTY && sl < -tol && sl < worst) { worst = sl; widx = r; wsgn = 1; wb = fabs(lo); }
-                if (cs != 3 && hi < 0.5 * QPPVM_INFTY && su < -tol && su < worst) { worst = su; widx = r; wsgn = -1; wb = fabs(hi); }
+                if (cs != 1 && lo > -0.5 * QPPVM_INFTY && sl < -tol && sl * pri < wkey) { worst = sl; wkey = sl * pri; widx = r; wsgn = 1; wb = fabs(lo); }
+                if (cs != 3 && hi < 0.5 * QPPVM_INFTY && su < -tol && su * pri < wkey) { worst = su; wkey = su * pri; widx = r; wsgn = -1; wb = fabs(hi); }
             }
         }
-        double v = worst; int idx = widx;
+        double v = wkey; int idx = widx;
+        if (q1 - q0 <= 32) {                                   // all slots live in warp 0: no exchange across warps
+            warp_argmin(v, idx);
+            if (tid < 32 && widx == idx && wkey == v && idx != 0x7fffffff) { red[8] = worst; red[9] = (double)wsgn; red[10] = wb; red[11] = (double)idx; }
+            if (tid == 0 && idx == 0x7fffffff) red[11] = -1.0;
+            tm::sync();
+            const int r = (int)red[11];
+            tm::sync();
+            return r;
+        }
         tm::argmin(v, idx, red);
         if (idx == 0x7fffffff) return -1;
-        if (widx == idx && worst == v) { red[8] = v; red[9] = (double)wsgn; red[10] = wb; }   // the owner publishes
+        if (widx == idx && wkey == v) { red[8] = worst; red[9] = (double)wsgn; red[10] = wb; }   // the owner publishes
         tm::sync();
         return idx;
     }
@@ -1111,7 +1210,8 @@ struct Solver {
             const double s = dot(w, u) - lo;
             const int sgn = s > 0.0 ? -1 : 1;
             if (sgn < 0) { for (int i = tid; i < N; i += TEAM) w[i] = -w[i]; tm::sync(); }
-            status = add_constraint(row, sgn, true, -fabs(s), fabs(lo), max_iter);
+            const double ww = dot(w, w);
+            status = add_constraint(row, sgn, true, -fabs(s), fabs(lo), max_iter, ww, -1);
         }
         return status;
     }
@@ -1119,10 +1219,21 @@ struct Solver {
     __device__ static __forceinline__ void reset_active_set()
     {
         QP_BIND
-        for (int i = tid; i < P::NROWS; i += TEAM) cstate[i] = 0;
+        for (int i = tid; i < P::NROWS; i += TEAM) cstate[i] &= 4;   // the candidate flags survive
         if (tid == 0) { st[0] = 0; st[1] = 0; }
         for (int i = tid; i < N; i += TEAM) u[i] = u0[i];
         tm::sync();
+    }
+    // Start of a level: every row inactive; candidates (bit 2) = the rows active at the end of the previous level of
+    // this problem (cstate still holds them) and / or the rows of `wmask` (the working set of the previous tick).
+    __device__ static __forceinline__ void init_cstate(int level, const uint32_t* wmask)
+    {
+        QP_BIND
+        for (int i = tid; i < P::NROWS; i += TEAM) {
+            bool cand = level > 0 && (cstate[i] & 1);
+            if (wmask) cand |= (wmask[i >> 5] >> (i & 31)) & 1u;
+            cstate[i] = cand ? 4 : 0;
+        }
     }
 
     // Split shapes: the prepare kernel has orthogonalised the level's equality normals (Q1 columns, RN) and moved the
@@ -1188,7 +1299,8 @@ struct Solver {
 
     // One level: returns status.  On return x holds the level solution.
     // The KKT residual of the level is left in red[12].
-    __device__ static __noinline__ int solve_level(int level, double eps_reg, int n_reg_steps, int max_iter, double* ydiag)
+    __device__ static __noinline__ int solve_level(int level, double eps_reg, int n_reg_steps, int max_iter, double* ydiag,
+                                                   const uint32_t* wmask)
     {
         QP_BIND
         const double eps = P::regularised(level) ? eps_reg : 0.0;
@@ -1214,7 +1326,7 @@ struct Solver {
                 bulk_copy(rdi, wsl + S::WS_RDI, B_RDI, mbar_ws_());
                 bulk_copy(u, wsl + S::WS_U, B_V, mbar_ws_());
             }
-            for (int i = tid; i < P::NROWS; i += TEAM) cstate[i] = 0;
+            init_cstate(level, wmask);
             mbar_wait(mbar_ws_(), (uint32_t)st[3]);
             tm::sync();
             const bool prepared = rdi[S::NEQ_MAX] == 0.0;
@@ -1229,6 +1341,7 @@ struct Solver {
             }
         } else {
             md = load_and_factor(level, eps);
+            init_cstate(level, wmask);
             reset_active_set();
             // ---- equalities first (dyn-feas, then level-0 optimality rows), never dropped
             status = add_equalities(level, max_iter);
@@ -1238,18 +1351,39 @@ struct Solver {
         for (int step = 0; status == QPPVM_STATUS_OK; ++step) {
 #pragma unroll 1
             for (;;) {
-                unwhiten(u, x);
-                const int row = scan();
-                if (row < 0) break;
+                // Force-only slots first, from u alone (x_f = jd u_f); the triangular product for the full x and the
+                // dense (torque-limit) slots only when none of those is violated.  The loop is left with the full x.
+                int row = -1;
+                if (P::NI_CHEAP > 0) {
+                    for (int j = NB + tid; j < N; j += TEAM) x[j] = jd[j] * u[j];
+                    tm::sync();
+                    row = scan<false>(0, P::NI_CHEAP, nullptr);
+                }
+                if (row < 0) {
+                    unwhiten(u, x);
+                    if (P::NI > P::NI_CHEAP) row = scan<P::TAUVAL>(P::NI_CHEAP, P::NI, tv_());
+                    if (row < 0) break;
+                }
                 const double sp = red[8], babs = red[10];
                 const int sgn = (int)red[9];
-                double lo, hi;
-                P::template build_row<TEAM>(rec, ext, row, eopt, av, lo, hi, tid);
-                tm::sync();
-                whiten(av, (double)sgn, w);
-                status = add_constraint(row, sgn, false, sp, babs, max_iter);
+                int sj0 = -1;
+                double ww, a0, a1, a2;
+                if (P::sparse_row(rec, row, sj0, a0, a1, a2)) {    // whitened normal: three entries
+                    const double w0 = sgn * jd[sj0] * a0, w1 = sgn * jd[sj0 + 1] * a1, w2v = sgn * jd[sj0 + 2] * a2;
+                    for (int i = tid; i < N; i += TEAM) w[i] = i == sj0 ? w0 : (i == sj0 + 1 ? w1 : (i == sj0 + 2 ? w2v : 0.0));
+                    tm::sync();
+                    ww = fma(w0, w0, fma(w1, w1, w2v * w2v));
+                } else {
+                    sj0 = -1;
+                    double lo, hi;
+                    P::template build_row<TEAM>(rec, ext, row, eopt, av, lo, hi, tid);
+                    tm::sync();
+                    whiten(av, (double)sgn, w);
+                    ww = dot(w, w);
+                }
+                status = add_constraint(row, sgn, false, sp, babs, max_iter, ww, sj0);
                 if (status == STATUS_IMPLIED) {               // not added; excluded from further scans
-                    if (tid == 0) cstate[row] = 2;
+                    if (tid == 0) cstate[row] = (cstate[row] & 4) | 2;
                     tm::sync();
                     status = QPPVM_STATUS_OK;
                 }
@@ -1291,6 +1425,17 @@ struct Solver {
         if (tid == 0) red[12] = kv;
         tm::sync();
         return status;
+    }
+
+    // bits [32 wd, 32 wd + 32) of the active-row mask (rows whose multiplier is non-zero)
+    __device__ static __forceinline__ uint32_t active_word(int wd)
+    {
+        uint32_t mask = 0;
+        for (int b = 0; b < 32; ++b) {
+            const int r = wd * 32 + b;
+            if (r < P::NROWS && (cstate_()[r] & 1)) mask |= 1u << b;
+        }
+        return mask;
     }
 
     // KKT certificate of the solved (regularised, proximal-shifted) level problem, SURVEY.md 8(c).
@@ -1369,7 +1514,7 @@ struct Solver {
                 rprim = fmax(rprim, fmax(0.0, fmax(lo - val, val - hi)));
                 rcomp = fmax(rcomp, y > 0.0 ? y * fabs(val - lo) : -y * fabs(hi - val));
                 if (sg * y < 0.0) rcomp = fmax(rcomp, fabs(y));        // wrong-signed multiplier
-                if (y == 0.0 && tid == 0) cstate[row] = 2;             // weakly active: not reported in the mask
+                if (y == 0.0 && tid == 0) cstate[row] = (cstate[row] & 4) | 2;   // weakly active: not reported in the mask
             }
             if (ydiag && tid == 0) ydiag[row] = y;
             tm::sync();
@@ -1379,7 +1524,8 @@ struct Solver {
             double viol = 0.0, cm = 0.0;
             for (int q = tid; q < P::NI; q += TEAM) {
                 int r; double val, lo, hi;
-                P::eval_slot(rec, ext, q, x, r, val, lo, hi);
+                if (P::TAUVAL && q >= P::NI_CHEAP) { P::dense_slot_bounds(rec, q, r, lo, hi); val = tv_()[q - P::NI_CHEAP]; }
+                else P::eval_slot(rec, ext, q, x, r, val, lo, hi);
                 cm = fmax(cm, fabs(val));
                 if (!(cstate[r] & 1)) viol = fmax(viol, fmax(lo - val, val - hi));
             }
@@ -1442,8 +1588,13 @@ struct Solver {
 template <class P, int TEAM>
 __global__ void __launch_bounds__(TEAM)
 qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out, double* __restrict__ diag,
-                long long batch, Params prm, unsigned long long* __restrict__ counter, double* __restrict__ ws)
+                long long batch, Params prm, unsigned long long* __restrict__ counter, double* __restrict__ ws,
+                uint32_t* __restrict__ warm)
 {
+    // warm (optional, in/out): 8 words per problem, the active rows of level 0 | level 1 at the end of the previous
+    // solve of this problem (previous control tick; zeros = cold).  They are tried first (scan()), which is what
+    // the reference gets from keeping one QPOases_sot alive across ticks (ref:include/QPPVM_RT_plugin/QPPVMPlugin.h:64,
+    // ref:src/QPPVMPlugin.cpp:246: qpOASES hot start).
     using SV = Solver<P, TEAM>;
     constexpr int N = P::N;
     const int tid = threadIdx.x;
@@ -1482,6 +1633,7 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
         if ((long long)idx >= batch) break;
         double* xo = reinterpret_cast<double*>(out + idx * (size_t)OUT_BYTES);
         double* dg = diag ? diag + idx * (size_t)DIAG : nullptr;
+        uint32_t* const wm = warm ? warm + idx * 8 : nullptr;
         if (dg) for (int i = tid; i < DIAG; i += TEAM) dg[i] = 0.0;
         if (Slab<P>::STAGE) {
             // linear contact-Jacobian rows next to the staged tail (plain coalesced loads, overlapping the TMA copy)
@@ -1497,8 +1649,9 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
         int it0 = 0, it1 = 0;
         int status = P::template prepare<TEAM>(SV::rec_(), P::EXT_IS_GLOBAL ? SV::grec_() : SV::ext_(), tid) ? QPPVM_STATUS_OK : QPPVM_STATUS_NUMERIC;
         if (status == QPPVM_STATUS_OK)
-            status = SV::solve_level(0, prm.eps_reg, prm.n_reg_steps, prm.max_iter, dg ? dg + N : nullptr);
+            status = SV::solve_level(0, prm.eps_reg, prm.n_reg_steps, prm.max_iter, dg ? dg + N : nullptr, wm);
         it0 = SV::state_()[2];
+        if (wm && status == QPPVM_STATUS_OK && tid < 4) wm[tid] = SV::active_word(tid);
         if (status == QPPVM_STATUS_OK) kkt0 = (float)SV::red_()[12];
         if (status == QPPVM_STATUS_OK) {
             P::template task0_value<TEAM>(SV::rec_(), P::EXT_IS_GLOBAL ? SV::grec_() : SV::ext_(), SV::x_(), SV::eopt_(), tid);
@@ -1508,24 +1661,20 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
                 if (tid < QPPVM_M0) dg[N + 2 * P::NROWS + tid] = SV::eopt_()[tid];
             }
             Team<TEAM>::sync();
-            status = SV::solve_level(1, prm.eps_reg, prm.n_reg_steps, prm.max_iter, dg ? dg + N + P::NROWS : nullptr);
+            status = SV::solve_level(1, prm.eps_reg, prm.n_reg_steps, prm.max_iter, dg ? dg + N + P::NROWS : nullptr, wm ? wm + 4 : nullptr);
             it1 = SV::state_()[2];
             if (status == QPPVM_STATUS_OK) kkt1 = (float)SV::red_()[12];
         }
         const bool ok = status == QPPVM_STATUS_OK;
         if (dg && !ok && tid < 3) dg[N + 2 * P::NROWS + 3 + tid] = SV::red_()[13 + tid];   // slack, |bound|, k at failure
         for (int i = tid; i < N; i += TEAM) xo[i] = ok ? SV::x_()[i] : 0.0;
-        P::template recover<TEAM>(SV::rec_(), P::EXT_IS_GLOBAL ? SV::grec_() : SV::ext_(), SV::x_(), xo + N, ok, tid);
+        P::template recover<TEAM>(SV::rec_(), P::EXT_IS_GLOBAL ? SV::grec_() : SV::ext_(), SV::x_(), SV::tv_(), xo + N, ok, tid);
         // trailer: status, iters, 128-bit active mask of level 1, kkt[2]
         uint32_t* tr = reinterpret_cast<uint32_t*>(xo + N + P::NA);
         if (tid < 4) {
-            uint32_t mask = 0;
-            if (ok)
-                for (int b = 0; b < 32; ++b) {
-                    const int r = tid * 32 + b;
-                    if (r < P::NROWS && (SV::cstate_()[r] & 1)) mask |= 1u << b;
-                }
+            const uint32_t mask = ok ? SV::active_word(tid) : 0u;
             tr[2 + tid] = mask;
+            if (wm && ok) wm[4 + tid] = mask;
         }
         if (tid == 0) {
             tr[0] = (uint32_t)status; tr[1] = (uint32_t)((it0 & 0xffff) | (it1 << 16));

@@ -53,7 +53,11 @@ constexpr int N_SHAPES = sizeof(g_shapes) / sizeof(g_shapes[0]);
 
 constexpr int HOST_STREAMS = 4;
 constexpr int N_SLOTS = HOST_STREAMS + 2;  // launch slots: host / rollout streams, caller's stream, spare
-constexpr int64_t WS_CHUNK = 8192;         // problems per factor-workspace pass (94 MB for config [1]: L2-resident)
+// Problems per prepare-workspace pass on the caller's stream.  The workspace is 28.5 - 46.5 KB per problem, i.e.
+// 0.9 - 1.5 GB per pass: it does NOT stay in the 126 MB L2 (ncu: the solve kernel reads it back from DRAM, < 8 % of the
+// HBM bandwidth).  Passes are sized for throughput instead: tens of waves of resident CTAs, so that the idle tail of
+// a pass (the last problems of a dynamic schedule) is a few per cent of it.
+constexpr int64_t WS_CHUNK = 32768;
 constexpr int64_t ROLL_LANE = 16384;       // states per lane of the on-device rollout (record scratch <= 4 x 0.3 GB)
 
 }  // namespace
@@ -97,6 +101,21 @@ int fail(qppvm_handle* h, int code, const char* fmt, ...)
     return code;
 }
 
+// Entry points run on the handle's device and leave the caller's current device as they found it.
+struct DeviceGuard {
+    int prev = -1; bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess; else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+#define ENTER(h)                                                                                         \
+    DeviceGuard guard_((h)->desc.device);                                                                \
+    if (!guard_.ok) return fail(h, QPPVM_ERR_CUDA, "cudaSetDevice(%d) failed", (h)->desc.device)
+
 #define CU(h, call)                                                                        \
     do {                                                                                   \
         cudaError_t e_ = (call);                                                           \
@@ -105,27 +124,14 @@ int fail(qppvm_handle* h, int code, const char* fmt, ...)
     } while (0)
 
 int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t batch,
-           cudaStream_t st, int slot, bool dynamic = true)
+           cudaStream_t st, int slot, bool dynamic = true, uint32_t* warm = nullptr)
 {
     if (batch <= 0) return QPPVM_OK;
     unsigned long long* counter = dynamic ? h->counters + slot : nullptr;   // null: static round-robin schedule
     const long long cap = (long long)h->sm_count * h->ctas_per_sm;
     Params prm{h->desc.eps_regularisation * QPPVM_QPOASES_EPS_REG, h->desc.n_reg_steps, h->desc.max_iter, h->rowwise};
     const bool split = h->shape->factor_kernel != nullptr;
-    const int64_t pass = split ? WS_CHUNK : batch;
-    if (split) {
-        const int64_t need = batch < WS_CHUNK ? batch : WS_CHUNK;
-        if (need > h->ws_cap[slot]) {
-            // growing a slot's workspace: earlier launches on this slot may still be reading the old one
-            CU(h, cudaStreamSynchronize(st));
-            cudaFree(h->ws[slot]); h->ws[slot] = nullptr; h->ws_cap[slot] = 0;
-            const int64_t capn = need < 1024 ? 1024 : need;
-            CU(h, cudaMalloc(&h->ws[slot], sizeof(double) * (size_t)h->shape->ws_doubles * capn));
-            // the bulk copies of the solve kernel also move the unused Q1 / RN entries: give them defined contents
-            CU(h, cudaMemsetAsync(h->ws[slot], 0, sizeof(double) * (size_t)h->shape->ws_doubles * capn, st));
-            h->ws_cap[slot] = capn;
-        }
-    }
+    const int64_t pass = split ? h->ws_cap[slot] : batch;   // problems per prepare-workspace pass (allocated at create)
     for (int64_t c0 = 0; c0 < batch; c0 += pass) {
         long long b = batch - c0 < pass ? batch - c0 : pass;
         const double* r = rec + c0 * (size_t)h->L.rec_doubles;
@@ -143,10 +149,30 @@ int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t 
         }
         if (counter && !split) CU(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
         const int grid = (int)(b < cap ? b : cap);
-        void* args[] = {(void*)&r, (void*)&o, (void*)&dgp, (void*)&b, (void*)&prm, (void*)&counter, (void*)&ws};
+        uint32_t* wm = warm ? warm + c0 * 8 : nullptr;
+        void* args[] = {(void*)&r, (void*)&o, (void*)&dgp, (void*)&b, (void*)&prm, (void*)&counter, (void*)&ws, (void*)&wm};
         CU(h, cudaLaunchKernel(h->kernel, dim3(grid), dim3(h->team), args, (size_t)h->shape->slab_bytes, st));
         h->launches += 1;
     }
+    return QPPVM_OK;
+}
+
+// Device-pointer entry points.  The caller's-stream slot (work counter, prepare workspace) is reused from call to
+// call: every call leaves an event behind on the stream it used, and a call on a different stream waits for that event
+// first -- the previous stream's handle itself is never touched again (the caller may have destroyed it).
+int solve_on_caller_stream(qppvm_handle* h, const double* rec, void* out, double* diag, uint32_t* warm, bool want_warm,
+                           int64_t batch, cudaStream_t st)
+{
+    if (!h) return QPPVM_ERR_ARG;
+    if (batch < 0 || (batch > 0 && (!rec || !out || (want_warm && !warm)))) return fail(h, QPPVM_ERR_ARG, "bad batch arguments");
+    if (((uintptr_t)rec & 15) || ((uintptr_t)out & 7) || ((uintptr_t)diag & 7) || ((uintptr_t)warm & 3))
+        return fail(h, QPPVM_ERR_ARG, "records must be 16-byte aligned (TMA bulk copy), outputs 8-byte, warm-start words 4-byte aligned");
+    ENTER(h);
+    if (h->dev_used && st != h->dev_stream) CU(h, cudaStreamWaitEvent(st, h->ev_dev, 0));
+    h->dev_stream = st; h->dev_used = true;
+    const int rc = launch(h, rec, out, diag, batch, st, HOST_STREAMS, true, warm);
+    if (rc) return rc;
+    CU(h, cudaEventRecord(h->ev_dev, st));
     return QPPVM_OK;
 }
 
@@ -219,7 +245,7 @@ int qppvm_get_layout(const qppvm_desc* d, qppvm_layout* L)
 
 int qppvm_supported_shapes(int32_t* t, int cap)
 {
-    for (int i = 0; i < N_SHAPES && i < cap; ++i) {
+    for (int i = 0; t && i < N_SHAPES && i < cap; ++i) {
         t[4 * i] = g_shapes[i].kind; t[4 * i + 1] = g_shapes[i].n_a; t[4 * i + 2] = g_shapes[i].n_c; t[4 * i + 3] = g_shapes[i].flags;
     }
     return N_SHAPES;
@@ -246,16 +272,18 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
     if (!h) return fail(nullptr, QPPVM_ERR_ARG, "out of memory");
     memset(h, 0, sizeof(*h));
     h->desc = *d; h->L = L; h->shape = sh;
+    // every failure below releases what has been created so far through qppvm_destroy (all members start out null)
 #define CUC(call)                                                                                 \
     do {                                                                                          \
         cudaError_t e_ = (call);                                                                  \
         if (e_ != cudaSuccess) {                                                                  \
             fail(nullptr, QPPVM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));        \
-            delete h;                                                                             \
+            qppvm_destroy(h);                                                                     \
             return QPPVM_ERR_CUDA;                                                                \
         }                                                                                         \
     } while (0)
-    CUC(cudaSetDevice(d->device));
+    DeviceGuard guard_(d->device);
+    if (!guard_.ok) { fail(nullptr, QPPVM_ERR_CUDA, "cudaSetDevice(%d) failed", d->device); delete h; return QPPVM_ERR_CUDA; }
     cudaDeviceProp prop;
     CUC(cudaGetDeviceProperties(&prop, d->device));
     h->sm_count = prop.multiProcessorCount;
@@ -267,7 +295,7 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
     CUC(cudaFuncSetAttribute(h->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int occ = 0;
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->kernel, h->team, (size_t)sh->slab_bytes));
-    if (occ < 1) { fail(nullptr, QPPVM_ERR_CUDA, "kernel does not fit on an SM (%d B smem)", sh->slab_bytes); delete h; return QPPVM_ERR_CUDA; }
+    if (occ < 1) { fail(nullptr, QPPVM_ERR_CUDA, "kernel does not fit on an SM (%d B smem)", sh->slab_bytes); qppvm_destroy(h); return QPPVM_ERR_CUDA; }
     h->ctas_per_sm = occ;
     if (const char* e = getenv("QPPVM_CTAS_PER_SM")) { const int c = atoi(e); if (c >= 1 && c < occ) h->ctas_per_sm = c; }   // profiling aid
     if (sh->factor_kernel) {
@@ -292,6 +320,19 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
     CUC(cudaMalloc(&h->d_one_out, L.out_bytes));
     CUC(cudaMallocHost(&h->h_one_rec, sizeof(double) * L.rec_doubles));
     CUC(cudaMallocHost(&h->h_one_out, L.out_bytes));
+    CUC(cudaEventCreateWithFlags(&h->ev_dev, cudaEventDisableTiming));
+    if (sh->factor_kernel) {
+        // Prepare workspaces, one per launch slot, sized for the largest pass that slot ever runs (nothing is allocated
+        // on the solve path): the host-path chunks, WS_CHUNK problems for the caller's stream, one problem for the
+        // latency slot.  The bulk copies of the solve kernel also move the unused Q1 / RN entries: defined contents.
+        for (int i = 0; i < N_SLOTS; ++i) {
+            const int64_t capn = i < HOST_STREAMS ? h->chunk_states : (i == HOST_STREAMS ? WS_CHUNK : 8);
+            const size_t bytes = sizeof(double) * (size_t)sh->ws_doubles * capn;
+            CUC(cudaMalloc(&h->ws[i], bytes));
+            CUC(cudaMemset(h->ws[i], 0, bytes));
+            h->ws_cap[i] = capn;
+        }
+    }
 #undef CUC
     *out = h;
     return QPPVM_OK;
@@ -300,7 +341,7 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
 int qppvm_destroy(qppvm_handle* h)
 {
     if (!h) return QPPVM_ERR_ARG;
-    cudaSetDevice(h->desc.device);
+    DeviceGuard guard_(h->desc.device);
     for (int i = 0; i < HOST_STREAMS; ++i) {
         if (h->streams[i]) { cudaStreamSynchronize(h->streams[i]); cudaStreamDestroy(h->streams[i]); }
         cudaFree(h->d_rec[i]); cudaFree(h->d_out[i]);
@@ -322,26 +363,17 @@ const char* qppvm_last_error(const qppvm_handle* h) { return h ? h->err : g_crea
 
 int qppvm_solve_batch_diag(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t batch, void* stream)
 {
-    if (!h) return QPPVM_ERR_ARG;
-    if (batch < 0 || (batch > 0 && (!rec || !out))) return fail(h, QPPVM_ERR_ARG, "bad batch arguments");
-    if (((uintptr_t)rec & 15) || ((uintptr_t)out & 7) || ((uintptr_t)diag & 7))
-        return fail(h, QPPVM_ERR_ARG, "records must be 16-byte aligned (TMA bulk copy), outputs 8-byte aligned");
-    CU(h, cudaSetDevice(h->desc.device));
-    // The caller's-stream slot (work counter, prepare workspace) is reused from call to call: when the caller moves
-    // to another stream, order the new stream after the work still queued on the previous one.
-    cudaStream_t st = (cudaStream_t)stream;
-    if (h->dev_used && st != h->dev_stream) {
-        if (!h->ev_dev) CU(h, cudaEventCreateWithFlags(&h->ev_dev, cudaEventDisableTiming));
-        if (cudaEventRecord(h->ev_dev, h->dev_stream) == cudaSuccess) CU(h, cudaStreamWaitEvent(st, h->ev_dev, 0));
-        else { cudaGetLastError(); CU(h, cudaDeviceSynchronize()); }      // the previous stream is gone
-    }
-    h->dev_stream = st; h->dev_used = true;
-    return launch(h, rec, out, diag, batch, st, HOST_STREAMS);
+    return solve_on_caller_stream(h, rec, out, diag, nullptr, false, batch, (cudaStream_t)stream);
 }
 
 int qppvm_solve_batch(qppvm_handle* h, const double* rec, void* out, int64_t batch, void* stream)
 {
-    return qppvm_solve_batch_diag(h, rec, out, nullptr, batch, stream);
+    return solve_on_caller_stream(h, rec, out, nullptr, nullptr, false, batch, (cudaStream_t)stream);
+}
+
+int qppvm_solve_batch_warm(qppvm_handle* h, const double* rec, void* out, uint32_t* warm, int64_t batch, void* stream)
+{
+    return solve_on_caller_stream(h, rec, out, nullptr, warm, true, batch, (cudaStream_t)stream);
 }
 
 int qppvm_solve_batch_host(qppvm_handle* h, const double* rec, void* out, int64_t batch)
@@ -353,7 +385,7 @@ int qppvm_solve_batch_host(qppvm_handle* h, const double* rec, void* out, int64_
 int qppvm_host_sync(qppvm_handle* h)
 {
     if (!h) return QPPVM_ERR_ARG;
-    CU(h, cudaSetDevice(h->desc.device));
+    ENTER(h);
     for (int i = 0; i < HOST_STREAMS; ++i) CU(h, cudaStreamSynchronize(h->streams[i]));
     return QPPVM_OK;
 }
@@ -362,7 +394,7 @@ int qppvm_solve_batch_host_async(qppvm_handle* h, const double* rec, void* out, 
 {
     if (!h) return QPPVM_ERR_ARG;
     if (batch < 0 || (batch > 0 && (!rec || !out))) return fail(h, QPPVM_ERR_ARG, "bad batch arguments");
-    CU(h, cudaSetDevice(h->desc.device));
+    ENTER(h);
     const size_t rb = sizeof(double) * h->L.rec_doubles, ob = (size_t)h->L.out_bytes;
     int s = 0;
     for (int64_t c0 = 0; c0 < batch; c0 += h->chunk, s = (s + 1) % HOST_STREAMS) {
@@ -379,7 +411,7 @@ int qppvm_solve_batch_host_async(qppvm_handle* h, const double* rec, void* out, 
 int qppvm_solve_one(qppvm_handle* h, const double* rec, void* out)
 {
     if (!h || !rec || !out) return h ? fail(h, QPPVM_ERR_ARG, "null argument") : QPPVM_ERR_ARG;
-    CU(h, cudaSetDevice(h->desc.device));
+    ENTER(h);
     const size_t rb = sizeof(double) * h->L.rec_doubles, ob = (size_t)h->L.out_bytes;
     // Latency mode: one launch, nothing else on the stream.  The record sits in pinned host memory that the GPU
     // addresses directly (UVA): the kernel's TMA bulk copy pulls it across PCIe and the outputs are stored straight
@@ -443,7 +475,7 @@ int qppvm_set_robot(qppvm_handle* h, const qppvm_robot* r)
     int* hi = reinterpret_cast<int*>(host.data() + nd * 8 + (size_t)nb * 8);
     memcpy(hi, r->parent, nb * 4); memcpy(hi + nb, depth.data(), nb * 4);
     for (int i = 0; i < 4; ++i) hi[2 * nb + i] = i < nc ? r->contact_body[i] : 0;
-    CU(h, cudaSetDevice(h->desc.device));
+    ENTER(h);
     if (h->rob_blob) { cudaFree(h->rob_blob); h->rob_blob = nullptr; }
     CU(h, cudaMalloc(&h->rob_blob, bytes));
     CU(h, cudaMemcpy(h->rob_blob, host.data(), bytes, cudaMemcpyHostToDevice));
@@ -475,7 +507,7 @@ int qppvm_records_from_states(qppvm_handle* h, const double* states, double* rec
     if (!h) return QPPVM_ERR_ARG;
     if (!h->has_robot) return fail(h, QPPVM_ERR_ARG, "qppvm_set_robot has not been called");
     if (batch < 0 || (batch > 0 && (!states || !recs))) return fail(h, QPPVM_ERR_ARG, "bad batch arguments");
-    CU(h, cudaSetDevice(h->desc.device));
+    ENTER(h);
     return launch_rbd(h, states, recs, batch, (cudaStream_t)stream);
 }
 
@@ -495,7 +527,7 @@ int qppvm_integrate_states(qppvm_handle* h, double* states, const void* out, dou
     if (!h) return QPPVM_ERR_ARG;
     if (!h->has_robot) return fail(h, QPPVM_ERR_ARG, "qppvm_set_robot has not been called");
     if (batch < 0 || (batch > 0 && (!states || !out)) || !(dt > 0.0)) return fail(h, QPPVM_ERR_ARG, "bad arguments");
-    CU(h, cudaSetDevice(h->desc.device));
+    ENTER(h);
     return launch_integrate(h, states, out, dt, batch, (cudaStream_t)stream);
 }
 
@@ -505,7 +537,7 @@ int qppvm_rollout_states(qppvm_handle* h, double* states, void* out, int ticks, 
     if (!h->has_robot) return fail(h, QPPVM_ERR_ARG, "qppvm_set_robot has not been called");
     if (batch < 0 || ticks < 0 || (batch > 0 && (!states || !out)) || !(dt > 0.0)) return fail(h, QPPVM_ERR_ARG, "bad arguments");
     if (batch == 0 || ticks == 0) return QPPVM_OK;
-    CU(h, cudaSetDevice(h->desc.device));
+    ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
     // States are independent, so the batch is cut into lanes that run all their ticks back to back on the handle's
     // worker streams: the tail of one lane's solve overlaps the front end / solve of the others (a single stream
@@ -560,7 +592,7 @@ int qppvm_solve_states_host_async(qppvm_handle* h, const double* states, void* o
     if (!h) return QPPVM_ERR_ARG;
     if (!h->has_robot) return fail(h, QPPVM_ERR_ARG, "qppvm_set_robot has not been called");
     if (batch < 0 || (batch > 0 && (!states || !out))) return fail(h, QPPVM_ERR_ARG, "bad batch arguments");
-    CU(h, cudaSetDevice(h->desc.device));
+    ENTER(h);
     const size_t sb = sizeof(double) * h->rsh.state_doubles, ob = (size_t)h->L.out_bytes;
     int s = 0;
     // chunk: a quarter of the batch (so that the four streams overlap copy / front end / solve), between the record
@@ -586,7 +618,7 @@ int64_t qppvm_kernel_launches(const qppvm_handle* h) { return h ? h->launches : 
 int qppvm_fp64_peak(qppvm_handle* h, double* tflops)
 {
     if (!h || !tflops) return QPPVM_ERR_ARG;
-    CU(h, cudaSetDevice(h->desc.device));
+    ENTER(h);
     const int blocks = h->sm_count * 8, threads = 256, iters = 1 << 16;
     double* buf = nullptr;
     CU(h, cudaMalloc(&buf, sizeof(double) * blocks * threads));
