@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="override records per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--fast", action="store_true", help="kernel experiments: device-resident value only, no e2e / roofline legs")
     return ap.parse_args()
 
 
@@ -281,6 +282,14 @@ def main():
         dist.all_reduce(frac, op=dist.ReduceOp.MIN)
     t_s = ms.item() * 1e-3
     value = world * args.steps * batch * frac.item() / t_s
+
+    if args.fast:
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": t_s / args.steps * 1e3, "converged_frac": frac.item(),
+                              "kkt_max": kkt_max, "n_gpus": world, "config": cfg_name, "fast": True}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the reference-facing C-ABI call with HOST buffers ("e2e") ----------------
     e2e_steps = max(3, min(args.steps, 200))

@@ -14,7 +14,8 @@ import numpy as np
 from .layout import Desc, Layout, layout
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqppvm_b200.so")
+# QPPVM_B200_LIB: another build of the same library (kernel experiments: tools/build_variant.sh)
+LIB_PATH = os.environ.get("QPPVM_B200_LIB") or os.path.join(_HERE, "libqppvm_b200.so")
 
 
 class CDesc(C.Structure):

@@ -23,6 +23,7 @@ struct ShapeEntry {
     const void* factor_kernel;   // qp_factor_kernel<P> for shapes that factor in a separate launch, else null
     int ws_doubles;              // factor workspace per problem (doubles)
     int factor_threads, factor_pairs, factor_bytes;   // CTA size, (problem, level) pairs per CTA, dynamic smem
+    const void* certify_kernel;  // qp_certify_kernel<P> (KKT certificate of the shapes above), else null
 };
 
 // Instantiated problem shapes (BASELINE.json configs).
@@ -33,12 +34,18 @@ constexpr const void* factor_entry()
     else return nullptr;
 }
 template <class P>
+constexpr const void* certify_entry()
+{
+    if constexpr (P::SPLIT_FACTOR) return (const void*)&qp_certify_kernel<P>;
+    else return nullptr;
+}
+template <class P>
 constexpr ShapeEntry entry()
 {
     return ShapeEntry{P::KIND, P::NA, P::NC, P::FLAGS,
                       (const void*)&qp_solve_kernel<P, 64>, Slab<P>::BYTES,
                       factor_entry<P>(), Slab<P>::WS,
-                      FactorShape<P>::THREADS, FactorShape<P>::FPC, FactorShape<P>::BYTES};
+                      FactorShape<P>::THREADS, FactorShape<P>::FPC, FactorShape<P>::BYTES, certify_entry<P>()};
 }
 constexpr int F_ALL = QPPVM_FLAG_FRICTION_CONES | QPPVM_FLAG_TORQUE_LIMITS;
 const ShapeEntry g_shapes[] = {
@@ -71,7 +78,7 @@ struct qppvm_handle {
     int sm_count, ctas_per_sm;
     unsigned long long* counters;          // N_SLOTS device counters
     double* ws[N_SLOTS]; int64_t ws_cap[N_SLOTS];   // factor workspaces, one per launch slot, allocated on first use
-    int factor_ctas_per_sm;
+    int factor_ctas_per_sm, certify_ctas_per_sm;
     int rowwise;                           // QPPVM_ROWWISE_EQUALITIES=1 at create (tests): see Params::rowwise
     cudaStream_t dev_stream; bool dev_used; cudaEvent_t ev_dev;   // last stream the caller's-stream slot ran on
     cudaStream_t streams[HOST_STREAMS];
@@ -153,6 +160,15 @@ int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t 
         void* args[] = {(void*)&r, (void*)&o, (void*)&dgp, (void*)&b, (void*)&prm, (void*)&counter, (void*)&ws, (void*)&wm};
         CU(h, cudaLaunchKernel(h->kernel, dim3(grid), dim3(h->team), args, (size_t)h->shape->slab_bytes, st));
         h->launches += 1;
+        if (split) {                                           // KKT certificate of the pass (reads the blocks the solve exported)
+            const long long ccap = (long long)h->sm_count * h->certify_ctas_per_sm;
+            const int cgrid = (int)(b < ccap ? b : ccap);
+            const double* cws = ws;
+            void* cargs[] = {(void*)&r, (void*)&o, (void*)&cws, (void*)&b, (void*)&prm};
+            CU(h, cudaLaunchKernel(h->shape->certify_kernel, dim3(cgrid), dim3(CERT_THREADS), cargs,
+                                   sizeof(double) * (size_t)h->L.rec_doubles, st));
+            h->launches += 1;
+        }
     }
     return QPPVM_OK;
 }
@@ -303,6 +319,10 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
         CUC(cudaFuncSetAttribute(sh->factor_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh->factor_kernel, sh->factor_threads, (size_t)sh->factor_bytes));
         h->factor_ctas_per_sm = occ < 1 ? 1 : occ;
+        const size_t cbytes = sizeof(double) * (size_t)L.rec_doubles;
+        CUC(cudaFuncSetAttribute(sh->certify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cbytes));
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh->certify_kernel, CERT_THREADS, cbytes));
+        h->certify_ctas_per_sm = occ < 1 ? 1 : occ;
     }
     CUC(cudaMalloc(&h->counters, sizeof(unsigned long long) * N_SLOTS));
     // host path: records per pipelined chunk (H2D of chunk i+1 overlaps the solve of chunk i); QPPVM_CHUNK overrides
