@@ -800,7 +800,8 @@ struct Slab {
     static constexpr int WSZ_Q = N * LDQ + ((N * LDQ) & 1), WS_RN = WS_Q + WSZ_Q;
     static constexpr int WSZ_RN = NEQ_MAX * (NEQ_MAX + 1) / 2 + ((NEQ_MAX * (NEQ_MAX + 1) / 2) & 1), WS_RDI = WS_RN + WSZ_RN;
     static constexpr int WSZ_RDI = NEQ_MAX + 2, WS_FLAG = WS_RDI + NEQ_MAX, WS_U = WS_RDI + WSZ_RDI;
-    static constexpr int WS_LEVEL = WS_U + VEC;
+    static constexpr int WS_RI = WS_U + VEC;          // inverse of the equality block of RN, packed like RN
+    static constexpr int WS_LEVEL = WS_RI + WSZ_RN;
     static_assert((SZ_J % 2 == 0) && (VEC % 2 == 0) && (WSZ_RDI % 2 == 0) && (KP >= WSZ_RDI), "bulk-copy alignment");
     static constexpr int WS = 2 * WS_LEVEL;
     // Certificate block: what qp_certify_kernel needs from the solve kernel, written over the (consumed) head of the
@@ -849,8 +850,8 @@ __device__ __forceinline__ double warp_sum_transposed(double (&p)[NV], int l)
 // strided loops, a group that has nothing to do passes j = -1.
 // ------------------------------------------------------------------------------------------
 template <int MD, int N, int NB, int GS>
-__device__ __noinline__ void factor_core(int j, double* Jm, const double* Ad, const double* dg, const double* db,
-                                            double* u0, double* jd, double* bc, double eps)
+__device__ __noinline__ void factor_qr(int j, double* Jm, const double* Ad, const double* dg, const double* db,
+                                          double* u0, double* jd, double* bc, double eps)
 {
     constexpr int LDA = NB + 1;
     constexpr int BC = MD + 4;
@@ -908,8 +909,15 @@ __device__ __noinline__ void factor_core(int j, double* Jm, const double* Ad, co
         }
     }
     __syncthreads();
-    // back substitution, lane j holds column j of J: J(i,j) = (d_ij - sum_{l>i} R(i,l) J(l,j)) / R(i,i).
-    // Uniform over lanes: Jc[l] stays 0 for l > j.  Row i of R is a broadcast read.
+}
+// Second half (independent of the number of dense task rows: one copy of the unrolled code serves both levels):
+// back substitution, lane j holds column j of J: J(i,j) = (d_ij - sum_{l>i} R(i,l) J(l,j)) / R(i,i).
+// Uniform over lanes: Jc[l] stays 0 for l > j.  Row i of R is a broadcast read.
+template <int NB>
+__device__ __noinline__ void factor_backsub(int j, double* Jm, const double* jd)
+{
+    const bool live = j >= 0;
+    const double* const rinv = jd;
     double Jc[NB];
 #pragma unroll
     for (int i = 0; i < NB; ++i) Jc[i] = 0.0;
@@ -931,6 +939,13 @@ __device__ __noinline__ void factor_core(int j, double* Jm, const double* Ad, co
         for (int i = 0; i < NB; ++i) if (i <= j) Jm[j * (j + 1) / 2 + i] = Jc[i];
     }
     __syncthreads();
+}
+template <int MD, int N, int NB, int GS>
+__device__ __forceinline__ void factor_core(int j, double* Jm, const double* Ad, const double* dg, const double* db,
+                                            double* u0, double* jd, double* bc, double eps)
+{
+    factor_qr<MD, N, NB, GS>(j, Jm, Ad, dg, db, u0, jd, bc, eps);
+    factor_backsub<NB>(j, Jm, jd);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1412,17 +1427,6 @@ struct Solver {
             lam[tid] = 0.0; act_row[tid] = row; act_sgn[tid] = 2; cstate[row] = 1;
         }
         if (tid == 0) { st[0] = neq; st[1] = 0; st[2] += neq; }
-        if (tid < neq) {
-            // column c of RI = RN^-1 e_c by back substitution; every thread stays inside its own column
-            const int c = tid;
-            RI[tri(c) + c] = rdi[c];
-#pragma unroll 1
-            for (int r = c - 1; r >= 0; --r) {
-                double sacc = 0.0;
-                for (int j = r + 1; j <= c; ++j) sacc = fma(RN[tri(j) + r], RI[tri(c) + j], sacc);
-                RI[tri(c) + r] = -sacc * rdi[r];
-            }
-        }
         tm::sync();
         if (neq > 6) {
             if (tid < neq) {
@@ -1493,7 +1497,7 @@ struct Solver {
             if (tid == 0) {
                 const double* wsl = ws_() + level * S::WS_LEVEL;
                 constexpr uint32_t B_J = S::SZ_J * 8, B_V = S::VEC * 8, B_Q = S::WSZ_Q * 8, B_RN = S::WSZ_RN * 8, B_RDI = S::WSZ_RDI * 8;
-                bulk_expect(mbar_ws_(), B_J + 3 * B_V + B_Q + B_RN + B_RDI);
+                bulk_expect(mbar_ws_(), B_J + 3 * B_V + B_Q + 2 * B_RN + B_RDI);
                 bulk_copy(Jm, wsl, B_J, mbar_ws_());
                 bulk_copy(u0, wsl + S::WS_U0, B_V, mbar_ws_());
                 bulk_copy(jd, wsl + S::WS_JD, B_V, mbar_ws_());
@@ -1501,6 +1505,7 @@ struct Solver {
                 bulk_copy(RN, wsl + S::WS_RN, B_RN, mbar_ws_());
                 bulk_copy(rdi, wsl + S::WS_RDI, B_RDI, mbar_ws_());
                 bulk_copy(u, wsl + S::WS_U, B_V, mbar_ws_());
+                bulk_copy(RI, wsl + S::WS_RI, B_RN, mbar_ws_());
             }
             init_cstate(level, wmask);
             mbar_wait(mbar_ws_(), (uint32_t)st[3]);
@@ -1967,7 +1972,12 @@ qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long 
         }
         __syncthreads();
         const double eps = P::regularised(level) ? prm.eps_reg : 0.0;
-        factor_core<F::MD, N, P::NB, F::GS>(live ? lane : -1, Jm, Ad, dg, db, u0, jd, bc, eps);
+        // Householder QR with as many dense rows as the pass needs: a pass whose pairs are all level 0 (pairs are
+        // level-major) runs the 6-row version instead of the padded one (the stride of Ad stays LDA either way)
+        const bool all_l0 = base + F::FPC <= batch;            // CTA-uniform
+        if (P::MD0 < F::MD && all_l0) factor_qr<P::MD0, N, P::NB, F::GS>(live ? lane : -1, Jm, Ad, dg, db, u0, jd, bc, eps);
+        else factor_qr<F::MD, N, P::NB, F::GS>(live ? lane : -1, Jm, Ad, dg, db, u0, jd, bc, eps);
+        factor_backsub<P::NB>(live ? lane : -1, Jm, jd);
         double* const wsl = ws + idx * (size_t)S::WS + level * S::WS_LEVEL;
         double* const Aeq = blk + F::O_AD; double* const lo_eq = bc;
         double* const WQ = blk + F::O_WQ; double* const RNb = blk + F::O_RN; double* const rdib = blk + F::O_RDI;
@@ -2082,6 +2092,24 @@ qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long 
                     if (r <= c) wso[S::WS_RN + c * (c + 1) / 2 + r] = Rq[t2];
                 }
                 if (l < wneq) wso[S::WS_RDI + l] = rdq[l];
+                {   // inverse of the equality block of RN (lane c: column c by back substitution), for the solve kernel's
+                    // thread-parallel "solves with RN"
+                    __syncwarp();
+                    double xr[F::NEQ];
+#pragma unroll
+                    for (int r = 0; r < F::NEQ; ++r) xr[r] = 0.0;
+                    const int c = l < wneq ? l : 0;
+#pragma unroll
+                    for (int r = F::NEQ - 1; r >= 0; --r) {
+                        double sacc = r == c ? -1.0 : 0.0;
+#pragma unroll
+                        for (int jj = r + 1; jj < F::NEQ; ++jj) if (jj <= c) sacc = fma(Rq[jj * F::NEQ + r], xr[jj], sacc);   // (columns > c: stale data)
+                        xr[r] = r <= c ? -sacc * rdq[r < wneq ? r : 0] : 0.0;
+                    }
+                    if (l < wneq)
+#pragma unroll
+                        for (int r = 0; r < F::NEQ; ++r) if (r <= l) wso[S::WS_RI + l * (l + 1) / 2 + r] = xr[r];
+                }
                 wso[S::WS_U + i0] = ua;
                 if (has1) wso[S::WS_U + i1] = ub;
                 if (l == 0) wso[S::WS_FLAG] = flag;
