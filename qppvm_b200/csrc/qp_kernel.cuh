@@ -39,6 +39,9 @@
 #ifndef QPPVM_STAGE_BIG
 #define QPPVM_STAGE_BIG 0        // 1: the 51-variable shapes also keep the record tail in shared memory (5 instead of 7 CTAs per SM)
 #endif
+#ifndef QPPVM_J_GLOBAL
+#define QPPVM_J_GLOBAL 1
+#endif
 #ifndef QPPVM_SELECTIVE_GS
 #define QPPVM_SELECTIVE_GS 1     // second Gram-Schmidt pass only when the first one cancelled more than half of the norm
 #endif
@@ -256,6 +259,10 @@ struct ForceAcc {
     // contact-Jacobian rows in shared memory; the task Jacobians (read once per level) stay in global memory.
     // Policy functions get `rec` = staged tail (or the global record when nothing is staged) and `g` = global record.
     static constexpr bool STAGE_RECORD = TLIM && QPPVM_STAGE_BIG >= (NA_ + 6 + 3 * NC_ > 48);
+    // J = R^-1 is only needed by the triangular products (full x for the dense slots / the end of a level, whitening
+    // of a dense row): a few times per level since the force-only rows bypass them.  The 51-variable shape reads it
+    // from the prepare workspace in global memory (L2) and spends the 6 KB on two more resident CTAs per SM.
+    static constexpr bool J_GLOBAL = QPPVM_SPLIT && TLIM && !STAGE_RECORD && QPPVM_J_GLOBAL;
     static constexpr bool EXT_IS_GLOBAL = true;                // the `ext` argument carries the global record pointer
     static constexpr int STAGE_FROM = OFF_M_();                // first staged record offset (even => 16-byte aligned)
     static constexpr int SB = STAGE_RECORD ? STAGE_FROM : 0;   // staged offset = record offset - SB
@@ -609,6 +616,7 @@ struct Torque {
     static constexpr int O_A0 = NA * LDM, O_T = O_A0 + 6 * NA;
     static constexpr int EXTRA = O_T + NA * LDM + ((O_T + NA * LDM) & 1);
     static constexpr bool SPLIT_FACTOR = false;
+    static constexpr bool J_GLOBAL = false;
     static constexpr bool HAS_EQ_COEF = false;
 
     __device__ static __forceinline__ int n_eq(int level) { return level == 0 ? 0 : 6; }
@@ -769,12 +777,12 @@ struct Slab {
     // per shape (profiles/README.md): shapes whose inequality scan re-reads M every iteration (torque-limit rows)
     // want it staged; for the others the 11-18 KB are worth more as 4 extra resident CTAs per SM.
     static constexpr bool STAGE = P::STAGE_RECORD;
-    static constexpr int O_J = O_REC + (STAGE ? P::STAGED : 0) + 2;   // staged part | global record pointer slot
+    static constexpr int O_J = O_REC + (STAGE ? P::STAGED : 0) + 4;   // staged part | pointer slots: J (global), record, workspace
     // J (and R before it) packed upper-triangular: NB (NB + 1) / 2 doubles.  R is row-major packed
     // (R(i,l) at i NB - i (i - 1) / 2 + (l - i)), J column-major packed (J(i,j) at j (j + 1) / 2 + i): triangular
     // numbers are a permutation mod 16, so a half-warp walking 16 consecutive columns is bank-conflict free.
     static constexpr int SZ_J = NB * (NB + 1) / 2 + ((NB * (NB + 1) / 2) & 1);
-    static constexpr int O_Q = O_J + SZ_J;            // Q1, aliased by Ad during the factorisation
+    static constexpr int O_Q = O_J + (P::J_GLOBAL ? 0 : SZ_J);   // Q1, aliased by Ad during the factorisation
     static constexpr int SZ_Q_RAW = (N * LDQ > P::MD_MAX * LDA) ? N * LDQ : P::MD_MAX * LDA;
     static constexpr int SZ_Q = SZ_Q_RAW + (SZ_Q_RAW & 1);     // even: RN and the vectors stay 16-byte aligned
     // RN (triangular factor of the whitened active normals) and its inverse RI, both packed by columns:
@@ -784,7 +792,11 @@ struct Slab {
     static constexpr int O_R = O_Q + SZ_Q;
     static constexpr int O_RI = O_R + SZ_TRI;
     static constexpr int O_VEC = O_RI + SZ_TRI;       // u0 u x w w2 av dg db xp jd
-    static constexpr int O_TV = O_VEC + 10 * VEC;     // values of the dense inequality slots at the last full scan
+    // dg / db hold the diagonal task part for the in-kernel factorisation and KKT check; the shapes that do both in
+    // other kernels only keep the part of dg that the 64-double exchange buffer of gs_dots spills into
+    static constexpr int SZ_DG = P::SPLIT_FACTOR ? ((VEC < 64 ? 64 - VEC : 0) + 1) / 2 * 2 : VEC, SZ_DB = P::SPLIT_FACTOR ? 0 : VEC;
+    static constexpr int O_DG = O_VEC + 6 * VEC, O_DB = O_DG + SZ_DG, O_XP = O_DB + SZ_DB, O_JD = O_XP + VEC;
+    static constexpr int O_TV = O_JD + VEC;           // values of the dense inequality slots at the last full scan
     static constexpr int O_CT = O_TV + P::NTV;        // per force-only slot: three coefficients, lower, upper bound
     static constexpr int O_SMALL = O_CT + P::NCT;     // d1 rr lam (KP each) | eopt 8 | red 16
     static constexpr int O_MBAR = O_SMALL + 6 * KP + 8 + 16;   // d1 rr lam rdi gc gs | 2 mbarriers: record staging, workspace copies
@@ -971,10 +983,19 @@ struct Solver {
         if (S::STAGE) return reinterpret_cast<double*>(g_smem) + S::O_REC;
         return grec_();
     }
-    QP_SM(Jm, S::O_J) QP_SM(Q1, S::O_Q) QP_SM(Ad, S::O_Q) QP_SM(RN, S::O_R)
+    QP_SM(Q1, S::O_Q) QP_SM(Ad, S::O_Q) QP_SM(RN, S::O_R)
+    __device__ static __forceinline__ double*& jptr_()          // J of the current level in global memory (J_GLOBAL shapes)
+    {
+        return *reinterpret_cast<double**>(reinterpret_cast<double*>(g_smem) + S::O_J - 3);
+    }
+    __device__ static __forceinline__ double* Jm_()
+    {
+        if (P::J_GLOBAL) return jptr_();
+        return reinterpret_cast<double*>(g_smem) + S::O_J;
+    }
     QP_SM(u0, S::O_VEC) QP_SM(u, S::O_VEC + S::VEC) QP_SM(x, S::O_VEC + 2 * S::VEC) QP_SM(w, S::O_VEC + 3 * S::VEC)
-    QP_SM(w2, S::O_VEC + 4 * S::VEC) QP_SM(av, S::O_VEC + 5 * S::VEC) QP_SM(dg, S::O_VEC + 6 * S::VEC)
-    QP_SM(db, S::O_VEC + 7 * S::VEC) QP_SM(xp, S::O_VEC + 8 * S::VEC) QP_SM(jd, S::O_VEC + 9 * S::VEC)
+    QP_SM(w2, S::O_VEC + 4 * S::VEC) QP_SM(av, S::O_VEC + 5 * S::VEC) QP_SM(dg, S::O_DG)
+    QP_SM(db, S::O_DB) QP_SM(xp, S::O_XP) QP_SM(jd, S::O_JD)
     QP_SM(d1, S::O_SMALL) QP_SM(rr, S::O_SMALL + KP) QP_SM(lam, S::O_SMALL + 2 * KP) QP_SM(rdi, S::O_SMALL + 3 * KP)
     QP_SM(gc, S::O_SMALL + 4 * KP) QP_SM(gsn, S::O_SMALL + 5 * KP)
     QP_SM(eopt, S::O_SMALL + 6 * KP) QP_SM(red, S::O_SMALL + 6 * KP + 8) QP_SM(ext, S::O_EXT) QP_SM(tv, S::O_TV)
@@ -1091,7 +1112,7 @@ struct Solver {
     // (CW = 16 or 32 columns wide), each walking every SEG-th row; the partial sums meet through a shuffle inside
     // the warp and a small exchange buffer across warps (`part`: WARPS x 32 doubles over av | dg, both dead during
     // the active-set iterations: dg / db are reloaded by kkt()).
-    static_assert(2 * S::VEC >= Team<TEAM>::WARPS * 32, "the exchange buffer of gs_dots covers av | dg");
+    static_assert(S::VEC + S::SZ_DG >= Team<TEAM>::WARPS * 32, "the exchange buffer of gs_dots covers av | dg");
     __device__ static __noinline__ void gs_dots(const double* v, bool accumulate, int k)
     {
         QP_BIND
@@ -1497,8 +1518,9 @@ struct Solver {
             if (tid == 0) {
                 const double* wsl = ws_() + level * S::WS_LEVEL;
                 constexpr uint32_t B_J = S::SZ_J * 8, B_V = S::VEC * 8, B_Q = S::WSZ_Q * 8, B_RN = S::WSZ_RN * 8, B_RDI = S::WSZ_RDI * 8;
-                bulk_expect(mbar_ws_(), B_J + 3 * B_V + B_Q + 2 * B_RN + B_RDI);
-                bulk_copy(Jm, wsl, B_J, mbar_ws_());
+                bulk_expect(mbar_ws_(), (P::J_GLOBAL ? 0 : B_J) + 3 * B_V + B_Q + 2 * B_RN + B_RDI);
+                if (P::J_GLOBAL) jptr_() = const_cast<double*>(wsl);
+                else bulk_copy(Jm, wsl, B_J, mbar_ws_());
                 bulk_copy(u0, wsl + S::WS_U0, B_V, mbar_ws_());
                 bulk_copy(jd, wsl + S::WS_JD, B_V, mbar_ws_());
                 bulk_copy(Q1, wsl + S::WS_Q, B_Q, mbar_ws_());
