@@ -159,8 +159,17 @@ int qppvm_solve_batch_host(qppvm_handle* h, const double* records_host, void* ou
  * executed in order. */
 int qppvm_solve_batch_host_async(qppvm_handle* h, const double* records_host, void* out_host, int64_t batch);
 int qppvm_host_sync(qppvm_handle* h);
-/* Latency mode: one record, host in / host out, synchronous (one control tick). */
+/* Latency mode: one record, host in / host out, synchronous (one control tick: ref:src/QPPVMPlugin.cpp:308-329,
+ * ref:src/ForceAcc.cpp:167-253).  For the ForceAcc shapes no kernel is launched per tick: three resident one-CTA
+ * kernels (prepare, solve, certify) poll a mailbox in pinned host memory.  Consecutive ticks hot-start from the previous
+ * tick's working sets, as the reference's persistent QPOases_sot does (ref:include/QPPVM_RT_plugin/QPPVMPlugin.h:64);
+ * qppvm_reset_warm() makes the next tick a cold start.  Environment: QPPVM_RESIDENT=0 falls back to one launch sequence
+ * per tick, QPPVM_TICK_IDLE_US (default 20000) is how long the resident kernels wait for a tick before they leave. */
 int qppvm_solve_one(qppvm_handle* h, const double* record_host, void* out_host);
+int qppvm_reset_warm(qppvm_handle* h);
+/* Device-clock stamps (ns, %globaltimer) of the last tick through the resident chain: tick seen by the prepare server,
+ * record copied to device memory, prepare done, solve start, solve done, certify start, result published. */
+int qppvm_tick_stamps(qppvm_handle* h, uint64_t* ns7);
 
 /* ---- rigid-body front end: compact states -> records on the device ------------------
  * Replaces, for batched use, what the reference obtains on the CPU from XBot::ModelInterface after

@@ -39,7 +39,7 @@ EXPORTS = ("qppvm_get_layout", "qppvm_create", "qppvm_destroy", "qppvm_last_erro
            "qppvm_solve_batch_diag", "qppvm_solve_batch_host", "qppvm_solve_one", "qppvm_kernel_launches",
            "qppvm_fp64_peak", "qppvm_supported_shapes", "qppvm_state_doubles", "qppvm_set_robot",
            "qppvm_records_from_states", "qppvm_solve_states_host", "qppvm_solve_batch_host_async", "qppvm_host_sync",
-           "qppvm_solve_states_host_async", "qppvm_integrate_states", "qppvm_rollout_states", "qppvm_solve_batch_warm")
+           "qppvm_solve_states_host_async", "qppvm_integrate_states", "qppvm_rollout_states", "qppvm_solve_batch_warm", "qppvm_reset_warm", "qppvm_tick_stamps")
 
 _lib = None
 
@@ -63,6 +63,8 @@ def load_library():
         lib.qppvm_solve_batch_warm.argtypes = [P, P, P, P, C.c_int64, P]
         lib.qppvm_solve_batch_host.argtypes = [P, P, P, C.c_int64]
         lib.qppvm_solve_one.argtypes = [P, P, P]
+        lib.qppvm_reset_warm.argtypes = [P]
+        lib.qppvm_tick_stamps.argtypes = [P, P]
         lib.qppvm_solve_batch_host_async.argtypes = [P, P, P, C.c_int64]
         lib.qppvm_host_sync.argtypes = [P]
         lib.qppvm_solve_states_host_async.argtypes = [P, P, P, C.c_int64]
@@ -191,6 +193,16 @@ class Solver:
             out = np.empty(L.out_doubles)
         self._check(self._lib.qppvm_solve_one(self._h, record.ctypes.data, out.ctypes.data))
         return out
+
+    def tick_stamps(self) -> np.ndarray:
+        """Device-clock stamps (ns) of the last tick through the resident chain (7 stage boundaries)."""
+        a = np.zeros(7, dtype=np.uint64)
+        self._check(self._lib.qppvm_tick_stamps(self._h, a.ctypes.data))
+        return a
+
+    def reset_warm(self):
+        """Forget the working sets of the previous tick: the next solve_one is a cold start."""
+        self._check(self._lib.qppvm_reset_warm(self._h))
 
     # ---- rigid-body front end (SURVEY 8(f) row 1): compact states instead of records -------
     def set_robot(self, robot, contact_bodies):

@@ -65,6 +65,65 @@ struct Params {
                         // the row-by-row equality path of the solve kernel, the one dependent rows fall back to
 };
 
+// Latency mode (one QP per control tick, ref:src/QPPVMPlugin.cpp:308-329): the three kernels stay RESIDENT, one CTA
+// each, and hand one problem along prepare -> solve -> certify through flags instead of being launched every tick.
+// The host posts a tick by writing the record into pinned memory and bumping host[0]; the prepare server polls that
+// word over PCIe, pulls the record into device memory, and the chain ends with the output record and host[1] = tick
+// written back to pinned memory.  A null `host` means the ordinary batched launch.
+struct Tick {
+    volatile uint32_t* host;    // pinned host words: [0] tick posted, [1] tick completed, [2] quit request, [3] servers alive
+    uint32_t* dev;              // device words: [0] prepare done, [1] solve done, [2] prepare server left, [3] solve server left
+    const double* host_rec;     // the record, pinned host memory
+    double* dev_rec;            // its copy in device memory (what the kernels read)
+    double* host_out;           // the output record, pinned host memory
+    uint32_t seq0;              // last tick completed before these servers were launched
+    uint32_t idle_us;           // the prepare server leaves (and takes the chain down) after this long without a tick
+};
+__device__ __forceinline__ uint32_t ld_acquire_sys(const volatile uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(volatile uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// stage timestamps of the resident chain (device words 8 ..: seven 64-bit stamps, see qppvm_tick_stamps)
+__device__ __forceinline__ void tick_stamp(const Tick& tk, int slot)
+{
+    reinterpret_cast<unsigned long long*>(tk.dev + 8)[slot] = globaltimer_ns();
+}
+// Waits (one thread) until the device word differs from `last`; returns false when the upstream server has left.
+__device__ __forceinline__ bool tick_wait_dev(const Tick& tk, int word, int down_word, uint32_t& last)
+{
+    for (;;) {
+        const uint32_t v = ld_acquire_gpu(tk.dev + word);
+        if (v != last) { last = v; return true; }
+        if (ld_acquire_gpu(tk.dev + down_word) != 0u) {
+            const uint32_t v2 = ld_acquire_gpu(tk.dev + word);  // a tick published just before the shutdown still counts
+            if (v2 != last) { last = v2; return true; }
+            return false;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Team primitives (TEAM threads = the whole CTA)
 // ------------------------------------------------------------------------------------------
@@ -1826,7 +1885,7 @@ template <class P, int TEAM>
 __global__ void __launch_bounds__(TEAM, Slab<P>::CTAS)
 qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out, double* __restrict__ diag,
                 long long batch, Params prm, unsigned long long* __restrict__ counter, double* __restrict__ ws,
-                uint32_t* __restrict__ warm)
+                uint32_t* __restrict__ warm, Tick tk)
 {
     // warm (optional, in/out): 8 words per problem, the active rows of level 0 | level 1 at the end of the previous
     // solve of this problem (previous control tick; zeros = cold).  They are tried first (scan()), which is what
@@ -1843,11 +1902,17 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
     __syncthreads();
     uint32_t phase = 0;
     unsigned long long next_static = blockIdx.x;               // counter == nullptr: static round-robin schedule
+    uint32_t tick = tk.seq0;
 #pragma unroll 1
     for (;;) {
         if (tid == 0) {
             unsigned long long i;
-            if (counter) i = atomicAdd(counter, 1ull);
+            if (tk.host) {                                     // resident: problem 0 again once the prepare server is done
+                i = tick_wait_dev(tk, 0, 2, tick) ? 0ull : (unsigned long long)batch;
+                asm volatile("fence.proxy.async;" ::: "memory");   // its generic-proxy writes vs. the bulk copies below
+                tick_stamp(tk, 3);
+            }
+            else if (counter) i = atomicAdd(counter, 1ull);
             else { i = next_static; next_static += gridDim.x; }
             s_idx = i;
             if ((long long)i < batch) {
@@ -1919,7 +1984,12 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
             tr[6] = __float_as_uint(kkt0); tr[7] = __float_as_uint(kkt1);
         }
         __syncthreads();                                       // slab (incl. s_idx, rec) is reused by the next problem
+        if (tk.host) {
+            __threadfence();
+            if (tid == 0) { tick_stamp(tk, 4); st_release_gpu(tk.dev + 1, tick); }
+        }
     }
+    if (tk.host && tid == 0) st_release_gpu(tk.dev + 3, 1u);   // the certify server follows
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1965,7 +2035,7 @@ struct FactorShape {
 template <class P>
 __global__ void __launch_bounds__(FactorShape<P>::THREADS)
 qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long long batch, Params prm,
-                 unsigned long long* __restrict__ counter)
+                 unsigned long long* __restrict__ counter, Tick tk)
 {
     using F = FactorShape<P>;
     using S = Slab<P>;
@@ -1978,8 +2048,37 @@ qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long 
     double* const Jm = blk; double* const Ad = blk + F::O_AD; double* const dg = blk + F::O_DG;
     double* const db = blk + F::O_DB; double* const u0 = blk + F::O_U0; double* const jd = blk + F::O_JD;
     double* const bc = blk + F::O_BC;
+    __shared__ uint32_t s_cmd;
+    uint32_t tick = tk.seq0;
 #pragma unroll 1
     for (long long base = (long long)blockIdx.x * F::FPC; base < 2 * batch; base += (long long)gridDim.x * F::FPC) {
+        if (tk.host) {
+            // resident: wait for the host to post the next tick, pull the record across PCIe into device memory
+            if (t == 0) {
+                const unsigned long long t0 = globaltimer_ns();
+                uint32_t cmd;
+                for (;;) {
+                    cmd = ld_acquire_sys(tk.host);
+                    if (cmd != tick) break;
+                    if (ld_acquire_sys(tk.host + 2) != 0u || globaltimer_ns() - t0 > 1000ull * tk.idle_us) { cmd = tick; break; }
+                }
+                s_cmd = cmd;
+            }
+            __syncthreads();
+            const uint32_t cmd = s_cmd;
+            __syncthreads();
+            if (cmd == tick) {                                 // quit request or idle for too long: take the chain down
+                if (t == 0) st_release_gpu(tk.dev + 2, 1u);
+                break;
+            }
+            tick = cmd;
+            if (t == 0) tick_stamp(tk, 0);
+            for (int i = t; i < P::REC / 2; i += F::THREADS)
+                reinterpret_cast<double2*>(tk.dev_rec)[i] = __ldcv(reinterpret_cast<const double2*>(tk.host_rec) + i);
+            __syncthreads();
+            if (t == 0) tick_stamp(tk, 1);
+            base = 0;
+        }
         // pairs are ordered level-major ([0, batch): level 0, [batch, 2 batch): level 1) so that the pairs sharing a
         // CTA pass have the same number of equality rows (the orthogonalisation phase is 4x longer for level 1)
         const long long pair = base + f;
@@ -2138,6 +2237,11 @@ qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long 
             }
         }
         __syncthreads();
+        if (tk.host) {                                         // hand the tick to the solve server; wait for the next one
+            __threadfence();
+            if (t == 0) { tick_stamp(tk, 2); st_release_gpu(tk.dev + 0, tick); }
+            base = -(long long)gridDim.x * F::FPC;
+        }
     }
 }
 
@@ -2156,13 +2260,24 @@ __device__ __forceinline__ void cert_max(double* slot, double v)     // v >= 0 (
     atomicMax(reinterpret_cast<unsigned long long*>(slot), (unsigned long long)__double_as_longlong(v));
 }
 
+// Resident certify server: copy the finished output record (x, tau, trailer) to pinned host memory, then the tick.
+__device__ __forceinline__ void tick_publish(const Tick& tk, const unsigned char* out, int out_bytes, uint32_t tick)
+{
+    __threadfence();
+    __syncthreads();
+    for (int i = threadIdx.x; i < out_bytes / 8; i += blockDim.x) tk.host_out[i] = reinterpret_cast<const double*>(out)[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) { tick_stamp(tk, 6); st_release_sys(tk.host + 1, tick); }
+}
+
 // One CTA per problem: the record is staged in shared memory once (coalesced), threads 0-63 certify level 0 and threads
 // 64-127 level 1 side by side (same code, same barriers); inside a level a thread per constraint row, then a thread
 // per variable.
 template <class P>
 __global__ void __launch_bounds__(CERT_THREADS)
 qp_certify_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out, const double* __restrict__ ws,
-                  long long batch, Params prm)
+                  long long batch, Params prm, Tick tk)
 {
     using S = Slab<P>;
     constexpr int N = P::N, NROWS = P::NROWS, T = 64;
@@ -2173,10 +2288,30 @@ qp_certify_kernel(const double* __restrict__ recs, unsigned char* __restrict__ o
     __shared__ signed char sg_row[2][NROWS];
     __shared__ int act[2][S::KP + 2];
     const int level = threadIdx.x >> 6, t = threadIdx.x & 63;
+    __shared__ uint32_t s_go, s_tick;
+    uint32_t tick = tk.seq0;
 #pragma unroll 1
     for (long long idx = blockIdx.x; idx < batch; idx += gridDim.x) {
+        if (tk.host) {
+            // resident: problem 0 once the solve server is done with it; afterwards the output record and the
+            // completed tick go back to pinned host memory
+            if (threadIdx.x == 0) { uint32_t nt = tick; s_go = tick_wait_dev(tk, 1, 3, nt) ? 1u : 0u; s_tick = nt; }
+            __syncthreads();
+            const uint32_t go = s_go;
+            tick = s_tick;
+            __syncthreads();
+            if (threadIdx.x == 0 && !go) st_release_sys(tk.host + 3, 0u);                  // the chain is down
+            if (!go) break;
+            if (threadIdx.x == 0) tick_stamp(tk, 5);
+            idx = 0;
+        }
         uint32_t* tr = reinterpret_cast<uint32_t*>(out + idx * (size_t)OUT_BYTES + 8 * (N + P::NA));
-        if ((int)tr[0] != QPPVM_STATUS_OK) continue;          // failed solves keep kkt = +inf (CTA-uniform)
+        if (!tk.host && (int)tr[0] != QPPVM_STATUS_OK) continue;          // failed solves keep kkt = +inf (CTA-uniform)
+        if (tk.host && (int)tr[0] != QPPVM_STATUS_OK) {
+            tick_publish(tk, out, OUT_BYTES, tick);
+            idx = -(long long)gridDim.x;
+            continue;
+        }
         const double* gr = recs + idx * (size_t)P::REC;
         for (int i = threadIdx.x; i < P::REC / 2; i += CERT_THREADS)
             reinterpret_cast<double2*>(g)[i] = reinterpret_cast<const double2*>(gr)[i];
@@ -2255,6 +2390,10 @@ qp_certify_kernel(const double* __restrict__ recs, unsigned char* __restrict__ o
             tr[6 + level] = __float_as_uint((float)kv);
         }
         __syncthreads();
+        if (tk.host) {
+            tick_publish(tk, out, OUT_BYTES, tick);
+            idx = -(long long)gridDim.x;
+        }
     }
 }
 

@@ -93,6 +93,9 @@ struct qppvm_handle {
     double* d_one_rec; unsigned char* d_one_out;
     double* h_one_rec; unsigned char* h_one_out;   // pinned staging for latency mode
     cudaStream_t one_stream;
+    // latency mode: resident prepare / solve / certify servers (qp_kernel.cuh, struct Tick)
+    uint32_t* tick_host; uint32_t* tick_dev; uint32_t* d_one_warm; double* one_ws;
+    cudaStream_t tick_streams[3]; bool tick_running; uint32_t tick_seq; int resident; uint32_t idle_us;
     int64_t launches;
     char err[512];
 };
@@ -138,6 +141,8 @@ int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t 
     const long long cap = (long long)h->sm_count * h->ctas_per_sm;
     Params prm{h->desc.eps_regularisation * QPPVM_QPOASES_EPS_REG, h->desc.n_reg_steps, h->desc.max_iter, h->rowwise};
     const bool split = h->shape->factor_kernel != nullptr;
+    Tick no_tick;
+    memset(&no_tick, 0, sizeof(no_tick));
     const int64_t pass = split ? h->ws_cap[slot] : batch;   // problems per prepare-workspace pass (allocated at create)
     for (int64_t c0 = 0; c0 < batch; c0 += pass) {
         long long b = batch - c0 < pass ? batch - c0 : pass;
@@ -149,7 +154,7 @@ int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t 
             const long long fcap = (long long)h->sm_count * h->factor_ctas_per_sm;
             const long long fneed = (2 * b + h->shape->factor_pairs - 1) / h->shape->factor_pairs;
             const int fgrid = (int)(fneed < fcap ? fneed : fcap);
-            void* fargs[] = {(void*)&r, (void*)&ws, (void*)&b, (void*)&prm, (void*)&counter};   // also resets the counter
+            void* fargs[] = {(void*)&r, (void*)&ws, (void*)&b, (void*)&prm, (void*)&counter, (void*)&no_tick};   // also resets the counter
             CU(h, cudaLaunchKernel(h->shape->factor_kernel, dim3(fgrid), dim3(h->shape->factor_threads), fargs,
                                    (size_t)h->shape->factor_bytes, st));
             h->launches += 1;
@@ -157,14 +162,14 @@ int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t 
         if (counter && !split) CU(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
         const int grid = (int)(b < cap ? b : cap);
         uint32_t* wm = warm ? warm + c0 * 8 : nullptr;
-        void* args[] = {(void*)&r, (void*)&o, (void*)&dgp, (void*)&b, (void*)&prm, (void*)&counter, (void*)&ws, (void*)&wm};
+        void* args[] = {(void*)&r, (void*)&o, (void*)&dgp, (void*)&b, (void*)&prm, (void*)&counter, (void*)&ws, (void*)&wm, (void*)&no_tick};
         CU(h, cudaLaunchKernel(h->kernel, dim3(grid), dim3(h->team), args, (size_t)h->shape->slab_bytes, st));
         h->launches += 1;
         if (split) {                                           // KKT certificate of the pass (reads the blocks the solve exported)
             const long long ccap = (long long)h->sm_count * h->certify_ctas_per_sm;
             const int cgrid = (int)(b < ccap ? b : ccap);
             const double* cws = ws;
-            void* cargs[] = {(void*)&r, (void*)&o, (void*)&cws, (void*)&b, (void*)&prm};
+            void* cargs[] = {(void*)&r, (void*)&o, (void*)&cws, (void*)&b, (void*)&prm, (void*)&no_tick};
             CU(h, cudaLaunchKernel(h->shape->certify_kernel, dim3(cgrid), dim3(CERT_THREADS), cargs,
                                    sizeof(double) * (size_t)h->L.rec_doubles, st));
             h->launches += 1;
@@ -201,6 +206,42 @@ __global__ void fp64_peak_kernel(double* out, int iters)
         a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ---- latency mode: resident servers ------------------------------------------------------------------
+void stop_servers(qppvm_handle* h)
+{
+    if (!h->tick_running) return;
+    __atomic_store_n(&h->tick_host[2], 1u, __ATOMIC_RELEASE);              // quit request (the prepare server polls it)
+    for (int i = 0; i < 3; ++i) cudaStreamSynchronize(h->tick_streams[i]);
+    h->tick_running = false;
+}
+
+int start_servers(qppvm_handle* h)
+{
+    // previous servers (if any) have left: host[3] == 0 is the last thing the chain writes
+    for (int i = 0; i < 3; ++i) CU(h, cudaStreamSynchronize(h->tick_streams[i]));
+    const uint32_t done = h->tick_host[1];
+    const uint32_t init[4] = {done, done, 0u, 0u};
+    CU(h, cudaMemcpy(h->tick_dev, init, sizeof(init), cudaMemcpyHostToDevice));
+    h->tick_host[2] = 0u;
+    __atomic_store_n(&h->tick_host[3], 1u, __ATOMIC_RELEASE);
+    Tick tk;
+    tk.host = h->tick_host; tk.dev = h->tick_dev; tk.host_rec = h->h_one_rec; tk.dev_rec = h->d_one_rec;
+    tk.host_out = reinterpret_cast<double*>(h->h_one_out); tk.seq0 = done; tk.idle_us = h->idle_us;
+    Params prm{h->desc.eps_regularisation * QPPVM_QPOASES_EPS_REG, h->desc.n_reg_steps, h->desc.max_iter, h->rowwise};
+    const double* rec = h->d_one_rec; unsigned char* out = h->d_one_out; double* dgp = nullptr;
+    double* ws = h->ws[HOST_STREAMS + 1]; const double* cws = ws;
+    long long b = 1; unsigned long long* counter = nullptr; uint32_t* wm = h->d_one_warm;
+    void* fargs[] = {(void*)&rec, (void*)&ws, (void*)&b, (void*)&prm, (void*)&counter, (void*)&tk};
+    CU(h, cudaLaunchKernel(h->shape->factor_kernel, dim3(1), dim3(h->shape->factor_threads), fargs, (size_t)h->shape->factor_bytes, h->tick_streams[0]));
+    void* args[] = {(void*)&rec, (void*)&out, (void*)&dgp, (void*)&b, (void*)&prm, (void*)&counter, (void*)&ws, (void*)&wm, (void*)&tk};
+    CU(h, cudaLaunchKernel(h->kernel, dim3(1), dim3(h->team), args, (size_t)h->shape->slab_bytes, h->tick_streams[1]));
+    void* cargs[] = {(void*)&rec, (void*)&out, (void*)&cws, (void*)&b, (void*)&prm, (void*)&tk};
+    CU(h, cudaLaunchKernel(h->shape->certify_kernel, dim3(1), dim3(CERT_THREADS), cargs, sizeof(double) * (size_t)h->L.rec_doubles, h->tick_streams[2]));
+    h->launches += 3;
+    h->tick_running = true;
+    return QPPVM_OK;
 }
 
 }  // namespace
@@ -341,6 +382,19 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
     CUC(cudaMallocHost(&h->h_one_rec, sizeof(double) * L.rec_doubles));
     CUC(cudaMallocHost(&h->h_one_out, L.out_bytes));
     CUC(cudaEventCreateWithFlags(&h->ev_dev, cudaEventDisableTiming));
+    CUC(cudaMalloc(&h->d_one_warm, sizeof(uint32_t) * QPPVM_WARM_WORDS));
+    CUC(cudaMemset(h->d_one_warm, 0, sizeof(uint32_t) * QPPVM_WARM_WORDS));
+    h->resident = sh->factor_kernel != nullptr;                 // latency mode through resident kernels (split shapes)
+    if (const char* e = getenv("QPPVM_RESIDENT")) h->resident = h->resident && atoi(e) != 0;
+    h->idle_us = 20000;
+    if (const char* e = getenv("QPPVM_TICK_IDLE_US")) { const long v = atol(e); if (v >= 100 && v <= 10000000) h->idle_us = (uint32_t)v; }
+    if (h->resident) {
+        CUC(cudaHostAlloc(&h->tick_host, 64, cudaHostAllocPortable));
+        memset(h->tick_host, 0, 64);
+        CUC(cudaMalloc(&h->tick_dev, 128));
+        CUC(cudaMemset(h->tick_dev, 0, 128));
+        for (int i = 0; i < 3; ++i) CUC(cudaStreamCreateWithFlags(&h->tick_streams[i], cudaStreamNonBlocking));
+    }
     if (sh->factor_kernel) {
         // Prepare workspaces, one per launch slot, sized for the largest pass that slot ever runs (nothing is allocated
         // on the solve path): the host-path chunks, WS_CHUNK problems for the caller's stream, one problem for the
@@ -362,6 +416,10 @@ int qppvm_destroy(qppvm_handle* h)
 {
     if (!h) return QPPVM_ERR_ARG;
     DeviceGuard guard_(h->desc.device);
+    stop_servers(h);
+    for (int i = 0; i < 3; ++i) if (h->tick_streams[i]) cudaStreamDestroy(h->tick_streams[i]);
+    if (h->tick_host) cudaFreeHost(h->tick_host);
+    cudaFree(h->tick_dev); cudaFree(h->d_one_warm);
     for (int i = 0; i < HOST_STREAMS; ++i) {
         if (h->streams[i]) { cudaStreamSynchronize(h->streams[i]); cudaStreamDestroy(h->streams[i]); }
         cudaFree(h->d_rec[i]); cudaFree(h->d_out[i]);
@@ -433,14 +491,60 @@ int qppvm_solve_one(qppvm_handle* h, const double* rec, void* out)
     if (!h || !rec || !out) return h ? fail(h, QPPVM_ERR_ARG, "null argument") : QPPVM_ERR_ARG;
     ENTER(h);
     const size_t rb = sizeof(double) * h->L.rec_doubles, ob = (size_t)h->L.out_bytes;
-    // Latency mode: one launch, nothing else on the stream.  The record sits in pinned host memory that the GPU
-    // addresses directly (UVA): the kernel's TMA bulk copy pulls it across PCIe and the outputs are stored straight
-    // back into pinned host memory, so there is no memcpy / memset node before or after the kernel.
     memcpy(h->h_one_rec, rec, rb);
-    int rc = launch(h, h->h_one_rec, h->h_one_out, nullptr, 1, h->one_stream, HOST_STREAMS + 1, false);
+    if (h->resident) {
+        // Latency mode: nothing is launched per tick.  The record goes into pinned memory, the tick number is bumped,
+        // the resident prepare -> solve -> certify chain (struct Tick) picks it up and writes the output record and the
+        // tick number back.  The solve starts from the working sets of the previous tick (qpOASES hot start,
+        // ref:src/QPPVMPlugin.cpp:246); qppvm_reset_warm() forgets them.  The servers leave after idle_us without
+        // a tick (so that they never block a device-wide synchronisation for long) and are started again on demand.
+        if (!h->tick_running || __atomic_load_n(&h->tick_host[3], __ATOMIC_ACQUIRE) == 0u) {
+            const int rc = start_servers(h);
+            if (rc) return rc;
+        }
+        const uint32_t seq = ++h->tick_seq;
+        __atomic_store_n(&h->tick_host[0], seq, __ATOMIC_RELEASE);
+        for (unsigned long spins = 0;; ++spins) {
+            if (__atomic_load_n(&h->tick_host[1], __ATOMIC_ACQUIRE) == seq) break;
+            if ((spins & 1023) == 1023) {
+                if (__atomic_load_n(&h->tick_host[3], __ATOMIC_ACQUIRE) == 0u &&
+                    __atomic_load_n(&h->tick_host[1], __ATOMIC_ACQUIRE) != seq) {      // the chain left just before the tick
+                    const int rc = start_servers(h);
+                    if (rc) return rc;
+                }
+                if (cudaStreamQuery(h->tick_streams[1]) != cudaErrorNotReady && cudaPeekAtLastError() != cudaSuccess)
+                    return fail(h, QPPVM_ERR_CUDA, "resident solve server failed: %s", cudaGetErrorString(cudaGetLastError()));
+            }
+        }
+        memcpy(out, h->h_one_out, ob);
+        return QPPVM_OK;
+    }
+    // Shapes without the resident chain: one launch sequence per tick.  The record sits in pinned host memory that the
+    // GPU addresses directly (UVA) and the outputs are stored straight back into pinned host memory.
+    int rc = launch(h, h->h_one_rec, h->h_one_out, nullptr, 1, h->one_stream, HOST_STREAMS + 1, false, h->d_one_warm);
     if (rc) return rc;
     CU(h, cudaStreamSynchronize(h->one_stream));
     memcpy(out, h->h_one_out, ob);
+    return QPPVM_OK;
+}
+
+int qppvm_tick_stamps(qppvm_handle* h, uint64_t* ns7)
+{
+    if (!h || !ns7) return QPPVM_ERR_ARG;
+    if (!h->resident) return fail(h, QPPVM_ERR_UNSUPPORTED, "this shape has no resident latency chain");
+    ENTER(h);
+    CU(h, cudaMemcpyAsync(ns7, h->tick_dev + 8, 7 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->one_stream));
+    CU(h, cudaStreamSynchronize(h->one_stream));
+    return QPPVM_OK;
+}
+
+int qppvm_reset_warm(qppvm_handle* h)
+{
+    if (!h) return QPPVM_ERR_ARG;
+    ENTER(h);
+    // (no tick is in flight: the handle is used by one thread)  A blocking memset would wait for the resident servers.
+    CU(h, cudaMemsetAsync(h->d_one_warm, 0, sizeof(uint32_t) * QPPVM_WARM_WORDS, h->one_stream));
+    CU(h, cudaStreamSynchronize(h->one_stream));
     return QPPVM_OK;
 }
 

@@ -107,6 +107,7 @@ def test_host_and_single_tick_entry_points_match_device_path(torch_mod):
     host = s.solve_batch_host(recs)
     assert np.array_equal(host, dev)                       # bitwise: problems are independent
     for i in (0, 17, 4999):
+        s.reset_warm()                                      # cold start: the same arithmetic as the batch path, bit for bit
         assert np.array_equal(s.solve_one(recs[i]), dev[i])
     # pipelined form: three overlapping calls, one sync
     pin = torch.from_numpy(recs).pin_memory()
