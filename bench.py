@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--fast", action="store_true", help="kernel experiments: device-resident value only, no e2e / roofline legs")
+    ap.add_argument("--multi", type=int, default=0,
+                    help="single-process leg: configs[3] over G GPUs through qppvm_multi_* (C++ / NCCL behind the C-ABI); prints its own line")
     return ap.parse_args()
 
 
@@ -183,8 +185,70 @@ def run_reference(args, desc, L, cfg_name, batch):
     print(json.dumps(line), flush=True)
 
 
+def run_multi(args):
+    """configs[3] (2^20 states, 33-DoF, 4 contacts, cones + tau limits) over G GPUs from ONE process through the C++ entry
+    points: records resident on the root GPU (NCCL scatter -> solve -> gather, pipelined), and host buffers (records /
+    compact states; every GPU pulls its own block over PCIe)."""
+    import torch
+    from qppvm_b200 import api, gen
+    from qppvm_b200.layout import CONFIGS, layout
+    G = args.multi
+    desc = CONFIGS[3]["desc"]
+    L = layout(desc)
+    B = args.batch or CONFIGS[3]["batch"]
+    steps = max(1, min(args.steps, 10))
+    rob = gen.robot_for(desc.n_a)
+    contacts = (rob.foot + rob.hand)[:desc.n_contacts]
+    s0 = api.Solver(desc)
+    s0.set_robot(rob, contacts)
+    st = gen.generate_states(desc, B, gen.config_seed(3))
+    recs = s0.records_from_states(torch.from_numpy(st).cuda())
+    torch.cuda.synchronize()
+    out = torch.empty((B, L.out_doubles), dtype=torch.float64, device="cuda:0")
+    res = {}
+    for g in sorted({1, G}):
+        m = api.MultiSolver(desc, list(range(g)))
+        m.set_robot(rob, contacts)
+        for _ in range(2):
+            m.solve_batch(recs, out=out)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            m.solve_batch(recs, out=out)
+        dt = (time.perf_counter() - t0) / steps
+        o = api.split_out(L, out[:65536].cpu().numpy())
+        good = float(((o["status"] == 0) & (o["kkt"].max(axis=1) <= 1e-6)).mean())
+        entry = {"root_resident_solves_per_s": B * good / dt, "ms_per_step": dt * 1e3, "nccl_calls_per_step": m.nccl_calls // (steps + 2)}
+        hst = torch.from_numpy(st).pin_memory()
+        hout = torch.empty((B, L.out_doubles), dtype=torch.float64).pin_memory()
+        m.solve_states_host_ptr(hst.data_ptr(), hout.data_ptr(), B)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            m.solve_states_host_ptr(hst.data_ptr(), hout.data_ptr(), B)
+        entry["host_states_solves_per_s"] = B / ((time.perf_counter() - t0) / steps)
+        if g == G:
+            hrec = recs.cpu().pin_memory()
+            m.solve_batch_host_ptr(hrec.data_ptr(), hout.data_ptr(), B)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                m.solve_batch_host_ptr(hrec.data_ptr(), hout.data_ptr(), B)
+            entry["host_records_solves_per_s"] = B / ((time.perf_counter() - t0) / steps)
+            del hrec
+        res["gpus_%d" % g] = entry
+        m.close()
+    line = {"leg": "multi_gpu_single_process", "api": "qppvm_multi_solve_batch / _solve_states_host / _solve_batch_host",
+            "workload": "configs[3]: %d states, 33-DoF, 4 contacts, cones + tau limits" % B, "gpus": G, "steps": steps,
+            "results": res}
+    if G > 1:
+        a, b = res["gpus_1"], res["gpus_%d" % G]
+        line["scatter_gather_efficiency_vs_1gpu"] = b["root_resident_solves_per_s"] / (G * a["root_resident_solves_per_s"])
+        line["host_states_efficiency_vs_1gpu"] = b["host_states_solves_per_s"] / (G * a["host_states_solves_per_s"])
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
+    if args.multi:
+        return run_multi(args)
     from qppvm_b200.layout import CONFIGS, layout
     if args.config < 0:
         args.config = 3 if max(args.gpus, int(os.environ.get("WORLD_SIZE", "1"))) > 1 else 2

@@ -208,6 +208,26 @@ int qppvm_solve_states_host_async(qppvm_handle* h, const double* states_host, vo
 int qppvm_integrate_states(qppvm_handle* h, double* states_dev, const void* out_dev, double dt, int64_t batch, void* stream);
 int qppvm_rollout_states(qppvm_handle* h, double* states_dev, void* out_dev, int ticks, double dt, int64_t batch, void* stream);
 
+/* ---- the batch sharded over the GPUs of one box, single process ---------------------------------------
+ * The path shards with no data-path collective (every state's cascade is independent: ref:src/QPPVMPlugin.cpp:246,
+ * ref:src/ForceAcc.cpp:189): GPU r of G solves the contiguous block [r B / G, (r + 1) B / G).  `devices` = CUDA ordinals
+ * (NULL: 0 .. n - 1), devices[0] is the root.  qppvm_multi_solve_batch: records and outputs on the ROOT GPU; the other
+ * GPUs' blocks travel by grouped ncclSend / ncclRecv (ncclCommInitAll, NVLink / NVSwitch), in chunks, so that the scatter of
+ * chunk i + 1 and the gather of chunk i - 1 overlap the solve of chunk i; outputs land directly in their place in
+ * `out_root_dev`.  Synchronous.  The *_host forms take host (pinned) buffers: every GPU moves its own block over its own
+ * PCIe link, no GPU-to-GPU traffic.  Results are bitwise those of one GPU. */
+typedef struct qppvm_multi qppvm_multi;
+int qppvm_multi_create(const qppvm_desc* desc, const int32_t* devices, int n_devices, qppvm_multi** out);
+int qppvm_multi_destroy(qppvm_multi* m);
+const char* qppvm_multi_last_error(const qppvm_multi* m);
+int qppvm_multi_devices(const qppvm_multi* m);
+int qppvm_multi_set_robot(qppvm_multi* m, const qppvm_robot* robot);
+int qppvm_multi_solve_batch(qppvm_multi* m, const double* records_root_dev, void* out_root_dev, int64_t batch);
+int qppvm_multi_solve_batch_host(qppvm_multi* m, const double* records_host, void* out_host, int64_t batch);
+int qppvm_multi_solve_states_host(qppvm_multi* m, const double* states_host, void* out_host, int64_t batch);
+int64_t qppvm_multi_kernel_launches(const qppvm_multi* m);
+int64_t qppvm_multi_nccl_calls(const qppvm_multi* m);
+
 /* Number of kernel launches issued through this handle so far. */
 int64_t qppvm_kernel_launches(const qppvm_handle* h);
 /* Measures the FP64 FMA peak of the device (TFLOP/s) with a register-resident DFMA

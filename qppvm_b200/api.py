@@ -39,7 +39,10 @@ EXPORTS = ("qppvm_get_layout", "qppvm_create", "qppvm_destroy", "qppvm_last_erro
            "qppvm_solve_batch_diag", "qppvm_solve_batch_host", "qppvm_solve_one", "qppvm_kernel_launches",
            "qppvm_fp64_peak", "qppvm_supported_shapes", "qppvm_state_doubles", "qppvm_set_robot",
            "qppvm_records_from_states", "qppvm_solve_states_host", "qppvm_solve_batch_host_async", "qppvm_host_sync",
-           "qppvm_solve_states_host_async", "qppvm_integrate_states", "qppvm_rollout_states", "qppvm_solve_batch_warm", "qppvm_reset_warm", "qppvm_tick_stamps")
+           "qppvm_solve_states_host_async", "qppvm_integrate_states", "qppvm_rollout_states", "qppvm_solve_batch_warm", "qppvm_reset_warm", "qppvm_tick_stamps",
+           "qppvm_multi_create", "qppvm_multi_destroy", "qppvm_multi_last_error", "qppvm_multi_devices",
+           "qppvm_multi_set_robot", "qppvm_multi_solve_batch", "qppvm_multi_solve_batch_host",
+           "qppvm_multi_solve_states_host", "qppvm_multi_kernel_launches", "qppvm_multi_nccl_calls")
 
 _lib = None
 
@@ -64,6 +67,19 @@ def load_library():
         lib.qppvm_solve_batch_host.argtypes = [P, P, P, C.c_int64]
         lib.qppvm_solve_one.argtypes = [P, P, P]
         lib.qppvm_reset_warm.argtypes = [P]
+        lib.qppvm_multi_create.argtypes = [C.POINTER(CDesc), C.POINTER(C.c_int32), C.c_int, C.POINTER(P)]
+        lib.qppvm_multi_destroy.argtypes = [P]
+        lib.qppvm_multi_last_error.argtypes = [P]
+        lib.qppvm_multi_last_error.restype = C.c_char_p
+        lib.qppvm_multi_devices.argtypes = [P]
+        lib.qppvm_multi_set_robot.argtypes = [P, C.POINTER(CRobot)]
+        lib.qppvm_multi_solve_batch.argtypes = [P, P, P, C.c_int64]
+        lib.qppvm_multi_solve_batch_host.argtypes = [P, P, P, C.c_int64]
+        lib.qppvm_multi_solve_states_host.argtypes = [P, P, P, C.c_int64]
+        lib.qppvm_multi_kernel_launches.argtypes = [P]
+        lib.qppvm_multi_kernel_launches.restype = C.c_int64
+        lib.qppvm_multi_nccl_calls.argtypes = [P]
+        lib.qppvm_multi_nccl_calls.restype = C.c_int64
         lib.qppvm_tick_stamps.argtypes = [P, P]
         lib.qppvm_solve_batch_host_async.argtypes = [P, P, P, C.c_int64]
         lib.qppvm_host_sync.argtypes = [P]
@@ -275,6 +291,81 @@ class Solver:
         v = C.c_double(0)
         self._check(self._lib.qppvm_fp64_peak(self._h, C.byref(v)))
         return v.value
+
+
+def _crobot(robot, contact_bodies):
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    keep = dict(parent=i32(robot.parent), axis=f64(robot.axis), offset=f64(robot.offset), mass=f64(robot.mass),
+                com=f64(robot.com), inertia=f64(robot.inertia), q_home=f64(robot.q_home), tau_max=f64(robot.tau_max),
+                contact=i32(contact_bodies))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    r = CRobot(robot.n_a, ip(keep["parent"]), dp(keep["axis"]), dp(keep["offset"]), dp(keep["mass"]), dp(keep["com"]),
+               dp(keep["inertia"]), dp(keep["q_home"]), dp(keep["tau_max"]), ip(keep["contact"]))
+    return r, keep
+
+
+class MultiSolver:
+    """One ``qppvm_multi``: the batch sharded over several GPUs of this box from ONE process (block split, NCCL
+    scatter / gather pipelined against the solves; see include/qppvm_b200.h)."""
+
+    def __init__(self, desc: Desc, devices=None):
+        import torch
+        self.desc, self.layout, self._lib = desc, layout(desc), load_library()
+        if devices is None:
+            devices = list(range(torch.cuda.device_count()))
+        self.devices = list(devices)
+        arr = (C.c_int32 * len(self.devices))(*self.devices)
+        self._m = C.c_void_p()
+        rc = self._lib.qppvm_multi_create(C.byref(cdesc(desc)), arr, len(self.devices), C.byref(self._m))
+        if rc:
+            raise QPError("qppvm_multi_create failed (%d): %s" % (rc, self._lib.qppvm_multi_last_error(None).decode()))
+
+    def close(self):
+        m, self._m = getattr(self, "_m", None), None
+        if m:
+            self._lib.qppvm_multi_destroy(m)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise QPError("qppvm_multi call failed (%d): %s" % (rc, self._lib.qppvm_multi_last_error(self._m).decode()))
+
+    def set_robot(self, robot, contact_bodies):
+        r, _keep = _crobot(robot, contact_bodies)
+        self._check(self._lib.qppvm_multi_set_robot(self._m, C.byref(r)))
+
+    def solve_batch(self, records, out=None):
+        """records: float64 CUDA tensor on the ROOT device (devices[0]); synchronous."""
+        import torch
+        L = self.layout
+        assert records.is_cuda and records.device.index == self.devices[0] and records.dtype == torch.float64
+        assert records.is_contiguous() and records.shape[1] == L.rec_doubles
+        if out is None:
+            out = torch.empty((records.shape[0], L.out_doubles), dtype=torch.float64, device=records.device)
+        torch.cuda.current_stream(records.device).synchronize()
+        self._check(self._lib.qppvm_multi_solve_batch(self._m, records.data_ptr(), out.data_ptr(), records.shape[0]))
+        return out
+
+    def solve_batch_host_ptr(self, rec_ptr: int, out_ptr: int, batch: int):
+        self._check(self._lib.qppvm_multi_solve_batch_host(self._m, rec_ptr, out_ptr, batch))
+
+    def solve_states_host_ptr(self, st_ptr: int, out_ptr: int, batch: int):
+        self._check(self._lib.qppvm_multi_solve_states_host(self._m, st_ptr, out_ptr, batch))
+
+    @property
+    def kernel_launches(self) -> int:
+        return self._lib.qppvm_multi_kernel_launches(self._m)
+
+    @property
+    def nccl_calls(self) -> int:
+        return self._lib.qppvm_multi_nccl_calls(self._m)
 
 
 def split_out(L: Layout, out: np.ndarray) -> dict:

@@ -6,7 +6,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libqppvm_b200.so")
-SOURCES = [os.path.join(HERE, "csrc", "qppvm_capi.cu")]
+SOURCES = [os.path.join(HERE, "csrc", "qppvm_capi.cu"), os.path.join(HERE, "csrc", "qppvm_multi.cu")]
 DEPS = SOURCES + [os.path.join(HERE, "csrc", "qp_kernel.cuh"), os.path.join(HERE, "csrc", "rbd_kernel.cuh"),
                   os.path.join(HERE, "..", "include", "qppvm_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -23,7 +23,7 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if force or stale():
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + ["-ldl"]
         subprocess.check_call(cmd)
     return LIB
 
