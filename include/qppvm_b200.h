@@ -228,6 +228,9 @@ int qppvm_multi_solve_states_host(qppvm_multi* m, const double* states_host, voi
 int64_t qppvm_multi_kernel_launches(const qppvm_multi* m);
 int64_t qppvm_multi_nccl_calls(const qppvm_multi* m);
 
+/* The persistent grids of this handle leave `n_sms` SMs free (default 0): room for kernels that must run concurrently
+ * with a long solve, e.g. NCCL's copy kernels on the root GPU of qppvm_multi_solve_batch. */
+int qppvm_reserve_sms(qppvm_handle* h, int n_sms);
 /* Number of kernel launches issued through this handle so far. */
 int64_t qppvm_kernel_launches(const qppvm_handle* h);
 /* Measures the FP64 FMA peak of the device (TFLOP/s) with a register-resident DFMA

@@ -40,7 +40,7 @@ EXPORTS = ("qppvm_get_layout", "qppvm_create", "qppvm_destroy", "qppvm_last_erro
            "qppvm_fp64_peak", "qppvm_supported_shapes", "qppvm_state_doubles", "qppvm_set_robot",
            "qppvm_records_from_states", "qppvm_solve_states_host", "qppvm_solve_batch_host_async", "qppvm_host_sync",
            "qppvm_solve_states_host_async", "qppvm_integrate_states", "qppvm_rollout_states", "qppvm_solve_batch_warm", "qppvm_reset_warm", "qppvm_tick_stamps",
-           "qppvm_multi_create", "qppvm_multi_destroy", "qppvm_multi_last_error", "qppvm_multi_devices",
+           "qppvm_reserve_sms", "qppvm_multi_create", "qppvm_multi_destroy", "qppvm_multi_last_error", "qppvm_multi_devices",
            "qppvm_multi_set_robot", "qppvm_multi_solve_batch", "qppvm_multi_solve_batch_host",
            "qppvm_multi_solve_states_host", "qppvm_multi_kernel_launches", "qppvm_multi_nccl_calls")
 
@@ -67,6 +67,7 @@ def load_library():
         lib.qppvm_solve_batch_host.argtypes = [P, P, P, C.c_int64]
         lib.qppvm_solve_one.argtypes = [P, P, P]
         lib.qppvm_reset_warm.argtypes = [P]
+        lib.qppvm_reserve_sms.argtypes = [P, C.c_int]
         lib.qppvm_multi_create.argtypes = [C.POINTER(CDesc), C.POINTER(C.c_int32), C.c_int, C.POINTER(P)]
         lib.qppvm_multi_destroy.argtypes = [P]
         lib.qppvm_multi_last_error.argtypes = [P]

@@ -76,6 +76,7 @@ struct qppvm_handle {
     const void* kernel;
     int team;                              // threads per problem (= CTA size)
     int sm_count, ctas_per_sm;
+    int reserve_sms;                       // SMs left free by the grids (root of a multi-GPU run: room for NCCL's copy kernels)
     unsigned long long* counters;          // N_SLOTS device counters
     double* ws[N_SLOTS]; int64_t ws_cap[N_SLOTS];   // factor workspaces, one per launch slot, allocated on first use
     int factor_ctas_per_sm, certify_ctas_per_sm;
@@ -138,7 +139,8 @@ int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t 
 {
     if (batch <= 0) return QPPVM_OK;
     unsigned long long* counter = dynamic ? h->counters + slot : nullptr;   // null: static round-robin schedule
-    const long long cap = (long long)h->sm_count * h->ctas_per_sm;
+    const int sms = h->sm_count - h->reserve_sms;
+    const long long cap = (long long)sms * h->ctas_per_sm;
     Params prm{h->desc.eps_regularisation * QPPVM_QPOASES_EPS_REG, h->desc.n_reg_steps, h->desc.max_iter, h->rowwise};
     const bool split = h->shape->factor_kernel != nullptr;
     Tick no_tick;
@@ -151,7 +153,7 @@ int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t 
         double* dgp = diag ? diag + c0 * (size_t)h->L.diag_doubles : nullptr;
         double* ws = split ? h->ws[slot] : nullptr;
         if (split) {
-            const long long fcap = (long long)h->sm_count * h->factor_ctas_per_sm;
+            const long long fcap = (long long)sms * h->factor_ctas_per_sm;
             const long long fneed = (2 * b + h->shape->factor_pairs - 1) / h->shape->factor_pairs;
             const int fgrid = (int)(fneed < fcap ? fneed : fcap);
             void* fargs[] = {(void*)&r, (void*)&ws, (void*)&b, (void*)&prm, (void*)&counter, (void*)&no_tick};   // also resets the counter
@@ -166,7 +168,7 @@ int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t 
         CU(h, cudaLaunchKernel(h->kernel, dim3(grid), dim3(h->team), args, (size_t)h->shape->slab_bytes, st));
         h->launches += 1;
         if (split) {                                           // KKT certificate of the pass (reads the blocks the solve exported)
-            const long long ccap = (long long)h->sm_count * h->certify_ctas_per_sm;
+            const long long ccap = (long long)sms * h->certify_ctas_per_sm;
             const int cgrid = (int)(b < ccap ? b : ccap);
             const double* cws = ws;
             void* cargs[] = {(void*)&r, (void*)&o, (void*)&cws, (void*)&b, (void*)&prm, (void*)&no_tick};
@@ -738,6 +740,14 @@ int qppvm_solve_states_host_async(qppvm_handle* h, const double* states, void* o
 }
 
 int64_t qppvm_kernel_launches(const qppvm_handle* h) { return h ? h->launches : 0; }
+
+int qppvm_reserve_sms(qppvm_handle* h, int n_sms)
+{
+    if (!h) return QPPVM_ERR_ARG;
+    if (n_sms < 0 || n_sms >= h->sm_count) return fail(h, QPPVM_ERR_ARG, "cannot reserve %d of %d SMs", n_sms, h->sm_count);
+    h->reserve_sms = n_sms;
+    return QPPVM_OK;
+}
 
 int qppvm_fp64_peak(qppvm_handle* h, double* tflops)
 {

@@ -5,8 +5,8 @@
 // contiguous block [r B / G, (r + 1) B / G).  NCCL only moves data to and from a root GPU -- grouped ncclSend / ncclRecv
 // over NVLink / NVSwitch -- and that movement is pipelined against the solves: the block of every non-root GPU is cut
 // into chunks, and while chunk i is being solved chunk i + 1 is being scattered and chunk i - 1 gathered (separate
-// communicators and streams for the two directions, double-buffered staging, events for the hand-offs).  The root
-// solves its own block in place, concurrently with its sends.  With host buffers no GPU-to-GPU traffic is needed at all:
+// communicators and streams for the two directions, triple-buffered staging, events for the hand-offs).  The root
+// solves its own block in place, chunk by chunk, and keeps a few SMs free for NCCL's copy kernels.  With host buffers no GPU-to-GPU traffic is needed at all:
 // every GPU pulls its own block over its own PCIe link.
 //
 // NCCL is loaded with dlopen at qppvm_multi_create (no link-time dependency: the single-GPU library loads without it,
@@ -24,6 +24,7 @@
 namespace {
 
 constexpr int MAX_DEV = 16;
+constexpr int NBUF = 3;      // staging depth: the scatter runs up to two chunks ahead of the solve
 
 struct NcclApi {
     void* lib;
@@ -49,9 +50,9 @@ struct qppvm_multi {
     ncclComm_t scatter[MAX_DEV], gather[MAX_DEV];   // two communicators: the two directions run concurrently
     bool have_comms;
     cudaStream_t s_scatter[MAX_DEV], s_solve[MAX_DEV], s_gather[MAX_DEV];
-    double* rec[MAX_DEV][2];                        // staging on the non-root GPUs, double-buffered
-    unsigned char* out[MAX_DEV][2];
-    cudaEvent_t ev_recv[MAX_DEV][2], ev_solved[MAX_DEV][2], ev_sent[MAX_DEV][2], ev_root;
+    double* rec[MAX_DEV][NBUF];                     // staging on the non-root GPUs, NBUF chunks deep
+    unsigned char* out[MAX_DEV][NBUF];
+    cudaEvent_t ev_recv[MAX_DEV][NBUF], ev_solved[MAX_DEV][NBUF], ev_sent[MAX_DEV][NBUF], ev_root;
     int64_t chunk;                                  // records per pipeline chunk and GPU
     int64_t nccl_calls;
     char err[512];
@@ -125,7 +126,7 @@ int qppvm_multi_destroy(qppvm_multi* m)
         cudaSetDevice(m->dev[r]);
         if (m->s_scatter[r]) { cudaStreamSynchronize(m->s_scatter[r]); cudaStreamSynchronize(m->s_solve[r]); cudaStreamSynchronize(m->s_gather[r]); }
         if (m->have_comms) { m->nccl.CommDestroy(m->scatter[r]); m->nccl.CommDestroy(m->gather[r]); }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NBUF; ++b) {
             cudaFree(m->rec[r][b]); cudaFree(m->out[r][b]);
             if (m->ev_recv[r][b]) cudaEventDestroy(m->ev_recv[r][b]);
             if (m->ev_solved[r][b]) cudaEventDestroy(m->ev_solved[r][b]);
@@ -157,7 +158,7 @@ int qppvm_multi_create(const qppvm_desc* desc, const int32_t* devices, int n_dev
             if (m->dev[q] == m->dev[r]) { mfail(nullptr, QPPVM_ERR_ARG, "device %d listed twice", m->dev[r]); qppvm_multi_destroy(m); return QPPVM_ERR_ARG; }
     }
     if (qppvm_get_layout(desc, &m->L)) { mfail(nullptr, QPPVM_ERR_ARG, "invalid problem description"); qppvm_multi_destroy(m); return QPPVM_ERR_ARG; }
-    m->chunk = 16384;
+    m->chunk = 32768;                               // = one prepare-workspace pass of the per-GPU handles
     if (const char* e = getenv("QPPVM_MULTI_CHUNK")) { const long c = atol(e); if (c >= 256 && c <= (1 << 20)) m->chunk = c; }
 #define MCC(call)                                                                                       \
     do {                                                                                                \
@@ -180,7 +181,7 @@ int qppvm_multi_create(const qppvm_desc* desc, const int32_t* devices, int n_dev
         MCC(cudaStreamCreateWithPriority(&m->s_scatter[r], cudaStreamNonBlocking, prio_hi));
         MCC(cudaStreamCreateWithPriority(&m->s_solve[r], cudaStreamNonBlocking, prio_lo));
         MCC(cudaStreamCreateWithPriority(&m->s_gather[r], cudaStreamNonBlocking, prio_hi));
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NBUF; ++b) {
             MCC(cudaEventCreateWithFlags(&m->ev_recv[r][b], cudaEventDisableTiming));
             MCC(cudaEventCreateWithFlags(&m->ev_solved[r][b], cudaEventDisableTiming));
             MCC(cudaEventCreateWithFlags(&m->ev_sent[r][b], cudaEventDisableTiming));
@@ -204,6 +205,11 @@ int qppvm_multi_create(const qppvm_desc* desc, const int32_t* devices, int n_dev
             return QPPVM_ERR_CUDA;
         }
         m->have_comms = true;
+        // Optionally keep SMs of the root free for NCCL's copy kernels (measured on 2 GPUs: not needed once both ends of
+        // every transfer are gated on the same readiness event, 0.93 vs 0.92 of two independent GPUs)
+        int rs = 0;
+        if (const char* e = getenv("QPPVM_MULTI_RESERVE_SMS")) rs = atoi(e);
+        if (rs > 0) qppvm_reserve_sms(m->h[0], rs);
     }
     *out = m;
     return QPPVM_OK;
@@ -255,7 +261,7 @@ int qppvm_multi_solve_batch(qppvm_multi* m, const double* rec_root, void* out_ro
         // software pipeline over chunk index c: scatter(c), solve(c), gather(c) are enqueued in that order, each on its own
         // stream per GPU; the hardware overlaps scatter(c + 1) and gather(c - 1) with solve(c)
         for (int64_t c = 0; c < nchunks; ++c) {
-            const int b = (int)(c & 1);
+            const int b = (int)(c % NBUF);
             // ---- scatter chunk c: root -> every other GPU (one group)
             MNC(m, m->nccl.GroupStart());
             for (int r = 1; r < n; ++r) {
@@ -265,7 +271,14 @@ int qppvm_multi_solve_batch(qppvm_multi* m, const double* rec_root, void* out_ro
                 if (c0 >= hi) continue;
                 const int64_t cn = hi - c0 < m->chunk ? hi - c0 : m->chunk;
                 MCU(m, cudaSetDevice(m->dev[r]));
-                if (c >= 2) MCU(m, cudaStreamWaitEvent(m->s_scatter[r], m->ev_solved[r][b], 0));   // staging buffer b is free again
+                if (c >= NBUF) {
+                    // staging buffer b is free again.  BOTH ends wait for it: a send kernel launched early would spin on the
+                    // root's SMs until the matching receive is posted.
+                    MCU(m, cudaStreamWaitEvent(m->s_scatter[r], m->ev_solved[r][b], 0));
+                    MCU(m, cudaSetDevice(m->dev[0]));
+                    MCU(m, cudaStreamWaitEvent(m->s_scatter[0], m->ev_solved[r][b], 0));
+                    MCU(m, cudaSetDevice(m->dev[r]));
+                }
                 MNC(m, m->nccl.Recv(m->rec[r][b], (size_t)cn * rd, ncclDouble, 0, m->scatter[r], m->s_scatter[r]));
                 MCU(m, cudaSetDevice(m->dev[0]));
                 MNC(m, m->nccl.Send(rec_root + c0 * rd, (size_t)cn * rd, ncclDouble, r, m->scatter[0], m->s_scatter[0]));
@@ -291,11 +304,14 @@ int qppvm_multi_solve_batch(qppvm_multi* m, const double* rec_root, void* out_ro
                 MCU(m, cudaSetDevice(m->dev[r]));
                 MCU(m, cudaEventRecord(m->ev_recv[r][b], m->s_scatter[r]));
                 MCU(m, cudaStreamWaitEvent(m->s_solve[r], m->ev_recv[r][b], 0));
-                if (c >= 2) MCU(m, cudaStreamWaitEvent(m->s_solve[r], m->ev_sent[r][b], 0));       // output buffer b has been gathered
+                if (c >= NBUF) MCU(m, cudaStreamWaitEvent(m->s_solve[r], m->ev_sent[r][b], 0));       // output buffer b has been gathered
                 const int rc = qppvm_solve_batch(m->h[r], m->rec[r][b], m->out[r][b], cn, m->s_solve[r]);
                 if (rc) return mfail(m, rc, "device %d: %s", m->dev[r], qppvm_last_error(m->h[r]));
                 MCU(m, cudaEventRecord(m->ev_solved[r][b], m->s_solve[r]));
                 MCU(m, cudaStreamWaitEvent(m->s_gather[r], m->ev_solved[r][b], 0));
+                // (the root's receive kernel must not be resident, spinning, while this GPU is still solving)
+                MCU(m, cudaSetDevice(m->dev[0]));
+                MCU(m, cudaStreamWaitEvent(m->s_gather[0], m->ev_solved[r][b], 0));
             }
             // ---- gather chunk c: outputs straight into their place in the root's output block (one group)
             MNC(m, m->nccl.GroupStart());
