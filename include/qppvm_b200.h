@@ -43,6 +43,8 @@ extern "C" {
 /* ---- optional constraint families (north_star; OpenSoT definitions) ------- */
 #define QPPVM_FLAG_FRICTION_CONES  1  /* 5-row linearised pyramid per contact    */
 #define QPPVM_FLAG_TORQUE_LIMITS   2  /* tau_min <= M_a qdd + h_a - J^T f <= max  */
+#define QPPVM_FLAG_FULL_WRENCH     4  /* 6 variables per contact (force + torque): "put 6 for full wrench",
+                                         ref:src/ForceAcc.cpp:67; the wrench bounds are then six real rows per contact */
 
 /* ---- per-problem solver status (reference: bool from solve()) ------------- */
 #define QPPVM_STATUS_OK          0
@@ -78,7 +80,7 @@ typedef struct qppvm_desc {
  * Record layout (one problem), all FP64, offsets in doubles, problem-major
  * contiguous; record stride is padded to an even number of doubles (16 B).
  *
- * FORCEACC  (n_v = n_a + 6, n_x = n_v + 3c):
+ * FORCEACC  (n_v = n_a + 6, n_x = n_v + w c with w = 3 force components per contact, 6 with QPPVM_FLAG_FULL_WRENCH):
  *   J_waist  6 x n_v row-major          level-0 Cartesian task Jacobian   (ForceAcc.cpp:118-122)
  *   J_c      c x 6 x n_v                contact-link Jacobians            (ForceAcc.cpp:83-89, 208)
  *   M        packed lower, row-major    n_v(n_v+1)/2                      (DynamicFeasibility, ID)
@@ -87,7 +89,7 @@ typedef struct qppvm_desc {
  *   rhs      6(1+c) + n_v               a_ref + l2*edot + l*e per Cartesian task, then postural
  *   tau_min, tau_max   2 n_a            only with QPPVM_FLAG_TORQUE_LIMITS
  *   cone     c x (R 3x3 row-major, mu)  only with QPPVM_FLAG_FRICTION_CONES
- *   f_lb,f_ub  c x (lb3, ub3)           force box                          (ForceAcc.cpp:74-76)
+ *   f_lb,f_ub  c x (lb w, ub w)         force / wrench box                 (ForceAcc.cpp:74-76)
  *
  * TORQUE  (n_v = n_x = n_a):
  *   J_ee     2 x 6 x n  (right hand first: stack order ee_right + ee_left, QPPVMPlugin.cpp:177)

@@ -56,7 +56,8 @@ int oracle_layout(const qppvm_desc* d, qppvm_layout* L)
         if (c < 1 || c > 4) return 1;
         int cones = (d->flags & QPPVM_FLAG_FRICTION_CONES) != 0;
         int tl = (d->flags & QPPVM_FLAG_TORQUE_LIMITS) != 0;
-        L->n_a = d->n_a; L->n_v = d->n_a + 6; L->n_c = c; L->n_x = L->n_v + 3 * c;
+        int wd = (d->flags & QPPVM_FLAG_FULL_WRENCH) ? 6 : 3;   /* variables per contact (ref:src/ForceAcc.cpp:67) */
+        L->n_a = d->n_a; L->n_v = d->n_a + 6; L->n_c = c; L->n_x = L->n_v + wd * c;
         if (L->n_x > 64) return 1;
         int nv = L->n_v;
         L->row_dyn = row; row += 6;
@@ -72,7 +73,7 @@ int oracle_layout(const qppvm_desc* d, qppvm_layout* L)
         L->off_rhs = off; off += 6 * (1 + c) + nv;
         L->off_taulim = tl ? off : -1; off += tl ? 2 * d->n_a : 0;
         L->off_cone = cones ? off : -1; off += cones ? 10 * c : 0;
-        L->off_fbox = off; off += 6 * c;
+        L->off_fbox = off; off += 2 * wd * c;
         L->off_fee = L->off_tauj = -1;
     } else if (d->kind == QPPVM_KIND_TORQUE) {
         if (d->n_contacts != 2 || d->flags != 0) return 1;
@@ -116,6 +117,7 @@ static void assemble_forceacc(const qppvm_desc* d, const qppvm_layout* L, const 
                               int level, const double* x0, level_qp* q)
 {
     const int n = L->n_x, nv = L->n_v, c = L->n_c, na = L->n_a;
+    const int wd = (d->flags & QPPVM_FLAG_FULL_WRENCH) ? 6 : 3;   /* wrench variables per contact */
     q->n = n;
     q->eps = d->eps_regularisation * QPPVM_QPOASES_EPS_REG;
     const double* Jw = rec + L->off_jwaist;
@@ -150,17 +152,16 @@ static void assemble_forceacc(const qppvm_desc* d, const qppvm_layout* L, const 
         double* Cr = q->C + (L->row_dyn + r) * n;
         for (int j = 0; j < nv; ++j) Cr[j] = mget(Mp, r, j);
         for (int ci = 0; ci < c; ++ci)
-            for (int k = 0; k < 3; ++k)                     /* wrench = [f;0]: linear rows only */
-                Cr[nv + 3 * ci + k] = -rec[L->off_jc + (ci * 6 + k) * nv + r];
+            for (int k = 0; k < wd; ++k)                    /* wrench = [f;0]: linear rows only (all six with full wrenches) */
+                Cr[nv + wd * ci + k] = -rec[L->off_jc + (ci * 6 + k) * nv + r];
         q->lA[L->row_dyn + r] = q->uA[L->row_dyn + r] = -h[r];
     }
     for (int ci = 0; ci < c; ++ci) {                        /* wrench bounds (GenericConstraint) */
-        const double* fb = rec + L->off_fbox + 6 * ci;
-        for (int k = 0; k < 3; ++k) {
+        const double* fb = rec + L->off_fbox + 2 * wd * ci;
+        for (int k = 0; k < 6; ++k) {
             int row = L->row_box + 6 * ci + k;
-            q->C[row * n + nv + 3 * ci + k] = 1.0;
-            q->lA[row] = fb[k]; q->uA[row] = fb[3 + k];
-            q->lA[row + 3] = -1.0; q->uA[row + 3] = 1.0;    /* zero rows: torque part of the wrench */
+            if (k < wd) { q->C[row * n + nv + wd * ci + k] = 1.0; q->lA[row] = fb[k]; q->uA[row] = fb[wd + k]; }
+            else { q->lA[row] = -1.0; q->uA[row] = 1.0; }   /* zero rows: torque part of the wrench = force / Zero(3) */
         }
     }
     if (L->row_cone >= 0)
@@ -173,7 +174,7 @@ static void assemble_forceacc(const qppvm_desc* d, const qppvm_layout* L, const 
                 for (int k = 0; k < 3; ++k) {
                     double s = 0;
                     for (int m = 0; m < 3; ++m) s += Ci[j][m] * R[k * 3 + m];
-                    q->C[row * n + nv + 3 * ci + k] = s;
+                    q->C[row * n + nv + wd * ci + k] = s;
                 }
                 q->lA[row] = -QPPVM_INFTY; q->uA[row] = 0.0;
             }
@@ -184,8 +185,8 @@ static void assemble_forceacc(const qppvm_desc* d, const qppvm_layout* L, const 
             double* Cr = q->C + row * n;
             for (int j = 0; j < nv; ++j) Cr[j] = mget(Mp, 6 + a, j);
             for (int ci = 0; ci < c; ++ci)
-                for (int k = 0; k < 3; ++k)
-                    Cr[nv + 3 * ci + k] = -rec[L->off_jc + (ci * 6 + k) * nv + 6 + a];
+                for (int k = 0; k < wd; ++k)
+                    Cr[nv + wd * ci + k] = -rec[L->off_jc + (ci * 6 + k) * nv + 6 + a];
             q->lA[row] = rec[L->off_taulim + a] - h[6 + a];
             q->uA[row] = rec[L->off_taulim + na + a] - h[6 + a];
         }
@@ -674,8 +675,9 @@ int oracle_solve_record(const qppvm_desc* d, const double* rec, void* out, doubl
         for (int a = 0; a < na; ++a) {                   /* tau = (M qdd + h - sum J_c^T [f;0])_actuated */
             double v = h[6 + a];
             for (int j = 0; j < nv; ++j) v += mget(rec + L.off_M, 6 + a, j) * x1[j];
+            const int wd = (d->flags & QPPVM_FLAG_FULL_WRENCH) ? 6 : 3;
             for (int ci = 0; ci < L.n_c; ++ci)
-                for (int k = 0; k < 3; ++k) v -= rec[L.off_jc + (ci * 6 + k) * nv + 6 + a] * x1[nv + 3 * ci + k];
+                for (int k = 0; k < wd; ++k) v -= rec[L.off_jc + (ci * 6 + k) * nv + 6 + a] * x1[nv + wd * ci + k];
             tau[a] = v;
         }
     }

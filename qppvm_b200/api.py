@@ -112,9 +112,11 @@ def c_layout(desc: Desc) -> dict:
 
 
 def supported_shapes():
-    buf = (C.c_int32 * 64)()
-    n = load_library().qppvm_supported_shapes(buf, 16)
-    return [tuple(buf[4 * i:4 * i + 4]) for i in range(min(n, 16))]
+    lib = load_library()
+    n = lib.qppvm_supported_shapes(None, 0)
+    buf = (C.c_int32 * (4 * n))()
+    lib.qppvm_supported_shapes(buf, n)
+    return [tuple(buf[4 * i:4 * i + 4]) for i in range(n)]
 
 
 class QPError(RuntimeError):

@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libqppvm_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "qppvm_capi.cu"), os.path.join(HERE, "csrc", "qppvm_multi.cu")]
-DEPS = SOURCES + [os.path.join(HERE, "csrc", "qp_kernel.cuh"), os.path.join(HERE, "csrc", "rbd_kernel.cuh"),
+DEPS = SOURCES + [os.path.join(HERE, "csrc", "shapes.def"), os.path.join(HERE, "csrc", "qp_kernel.cuh"), os.path.join(HERE, "csrc", "rbd_kernel.cuh"),
                   os.path.join(HERE, "..", "include", "qppvm_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]

@@ -266,7 +266,9 @@ struct ForceAcc {
     static constexpr int NA = NA_, NC = NC_, FLAGS = FLAGS_;
     static constexpr bool CONES = (FLAGS & QPPVM_FLAG_FRICTION_CONES) != 0;
     static constexpr bool TLIM = (FLAGS & QPPVM_FLAG_TORQUE_LIMITS) != 0;
-    static constexpr int NV = NA + 6, N = NV + 3 * NC;
+    // variables per contact: 3 force components, or the full wrench ("put 6 for full wrench", ref:src/ForceAcc.cpp:67)
+    static constexpr int WD = (FLAGS & QPPVM_FLAG_FULL_WRENCH) ? 6 : 3;
+    static constexpr int NV = NA + 6, N = NV + WD * NC;
     static constexpr int NB = NV;                            // columns with dense task entries (both levels)
     static constexpr int MD_MAX = 6 * NC > 6 ? 6 * NC : 6;   // dense task rows per level
     // reference row ids
@@ -275,7 +277,7 @@ struct ForceAcc {
     static constexpr int ROW_OPT = ROW_TAU + (TLIM ? NA : 0);
     static constexpr int NROWS = ROW_OPT + QPPVM_M0;
     // inequality slots scanned each iteration
-    static constexpr int NI_BOX = 3 * NC, NI_CONE = CONES ? 5 * NC : 0, NI_TAU = TLIM ? NA : 0;
+    static constexpr int NI_BOX = WD * NC, NI_CONE = CONES ? 5 * NC : 0, NI_TAU = TLIM ? NA : 0;
     static constexpr int NI = NI_BOX + NI_CONE + NI_TAU;
     // Slots [0, NI_CHEAP) are rows over the force variables of ONE contact (box, friction pyramid).  The force columns
     // carry no task entries, so they stay diagonal in the whitening (x_f = jd u_f): such a row is evaluated from u
@@ -291,7 +293,7 @@ struct ForceAcc {
     {
         const int nv = NA_ + 6;
         const int u = OFF_M_() + nv * (nv + 1) / 2 + nv + 6 * (1 + NC_) + 6 * (1 + NC_) + nv
-                      + ((FLAGS_ & QPPVM_FLAG_TORQUE_LIMITS) ? 2 * NA_ : 0) + ((FLAGS_ & QPPVM_FLAG_FRICTION_CONES) ? 10 * NC_ : 0) + 6 * NC_;
+                      + ((FLAGS_ & QPPVM_FLAG_TORQUE_LIMITS) ? 2 * NA_ : 0) + ((FLAGS_ & QPPVM_FLAG_FRICTION_CONES) ? 10 * NC_ : 0) + 2 * ((FLAGS_ & QPPVM_FLAG_FULL_WRENCH) ? 6 : 3) * NC_;
         return u + (u & 1);
     }
     static constexpr int OFF_JW = 0, OFF_JC = OFF_JW + 6 * NV, OFF_M = OFF_JC + NC * 6 * NV;
@@ -299,7 +301,7 @@ struct ForceAcc {
     static constexpr int OFF_RHS = OFF_JDQD + 6 * (1 + NC), OFF_TAULIM = OFF_RHS + 6 * (1 + NC) + NV;
     static constexpr int OFF_CONE = OFF_TAULIM + (TLIM ? 2 * NA : 0);
     static constexpr int OFF_FBOX = OFF_CONE + (CONES ? 10 * NC : 0);
-    static constexpr int REC_UNPADDED = OFF_FBOX + 6 * NC;
+    static constexpr int REC_UNPADDED = OFF_FBOX + 2 * WD * NC;
     static constexpr int REC = REC_UNPADDED + (REC_UNPADDED & 1);
     static_assert(REC == REC_() && OFF_M == OFF_M_(), "layout helpers agree");
 
@@ -317,7 +319,7 @@ struct ForceAcc {
     // the TAIL of the record [M | h | Jdqd | rhs | tau limits | cones | boxes] (one TMA bulk copy) plus the linear
     // contact-Jacobian rows in shared memory; the task Jacobians (read once per level) stay in global memory.
     // Policy functions get `rec` = staged tail (or the global record when nothing is staged) and `g` = global record.
-    static constexpr bool STAGE_RECORD = TLIM && QPPVM_STAGE_BIG >= (NA_ + 6 + 3 * NC_ > 48);
+    static constexpr bool STAGE_RECORD = TLIM && QPPVM_STAGE_BIG >= (NA_ + 6 + ((FLAGS_ & QPPVM_FLAG_FULL_WRENCH) ? 6 : 3) * NC_ > 48);
     // J = R^-1 is only needed by the triangular products (full x for the dense slots / the end of a level, whitening
     // of a dense row): a few times per level since the force-only rows bypass them.  The 51-variable shape reads it
     // from the prepare workspace in global memory (L2) and spends the 6 KB on two more resident CTAs per SM.
@@ -326,12 +328,12 @@ struct ForceAcc {
     static constexpr int STAGE_FROM = OFF_M_();                // first staged record offset (even => 16-byte aligned)
     static constexpr int SB = STAGE_RECORD ? STAGE_FROM : 0;   // staged offset = record offset - SB
     static constexpr int S_JCL = REC_() - STAGE_FROM;          // linear rows of J_c: (ci * 3 + k) * NV + col
-    static constexpr int STAGED = S_JCL + 3 * NC * NV + ((S_JCL + 3 * NC * NV) & 1);
+    static constexpr int STAGED = S_JCL + WD * NC * NV + ((S_JCL + WD * NC * NV) & 1);
     __device__ static __forceinline__ double jcl(const double* rec, const double* g, int ci, int k, int col)
     {
-        return STAGE_RECORD ? rec[S_JCL + (ci * 3 + k) * NV + col] : g[OFF_JC + (ci * 6 + k) * NV + col];
+        return STAGE_RECORD ? rec[S_JCL + (ci * WD + k) * NV + col] : g[OFF_JC + (ci * 6 + k) * NV + col];
     }
-    static constexpr int KMAX_RAW = kmax_for(12, 3 * NC + (CONES ? 5 * NC : 0) + (TLIM ? NA : 0), N);
+    static constexpr int KMAX_RAW = kmax_for(12, WD * NC + (CONES ? 5 * NC : 0) + (TLIM ? NA : 0), N);
     // 31 instead of 32 rows of capacity is what lets a fifth CTA of the 51-variable shape fit on an SM
     static constexpr int KMAX = (KMAX_RAW == 32 && N > 48) ? 31 : KMAX_RAW;
     template <int TEAM> __device__ static __forceinline__ bool prepare(const double*, double*, int) { return true; }
@@ -344,7 +346,7 @@ struct ForceAcc {
     {
         if (e < 6) {
             if (jc < NV) { sg = 1.0; return OFF_M + (e >= jc ? e * (e + 1) / 2 + jc : jc * (jc + 1) / 2 + e); }
-            const int ci = (jc - NV) / 3, k = (jc - NV) % 3;
+            const int ci = (jc - NV) / WD, k = (jc - NV) % WD;
             sg = -1.0;
             return OFF_JC + (ci * 6 + k) * NV + e;
         }
@@ -393,14 +395,14 @@ struct ForceAcc {
             for (int j = tid; j < N; j += TEAM) {
                 double v;
                 if (j < NV) v = M(rec, r, j);
-                else { const int ci = (j - NV) / 3, k = (j - NV) % 3; v = -jcl(rec, g, ci, k, r); }
+                else { const int ci = (j - NV) / WD, k = (j - NV) % WD; v = -jcl(rec, g, ci, k, r); }
                 av[j] = v;
             }
             lo = hi = -rec[OFF_H - SB + r];
         } else if (row < ROW_CONE) {                           // wrench box (GenericConstraint)
             const int ci = (row - ROW_BOX) / 6, k = (row - ROW_BOX) % 6;
-            for (int j = tid; j < N; j += TEAM) av[j] = (k < 3 && j == NV + 3 * ci + k) ? 1.0 : 0.0;
-            if (k < 3) { lo = rec[OFF_FBOX - SB + 6 * ci + k]; hi = rec[OFF_FBOX - SB + 6 * ci + 3 + k]; }
+            for (int j = tid; j < N; j += TEAM) av[j] = (k < WD && j == NV + WD * ci + k) ? 1.0 : 0.0;
+            if (k < WD) { lo = rec[OFF_FBOX - SB + 2 * WD * ci + k]; hi = rec[OFF_FBOX - SB + 2 * WD * ci + WD + k]; }
             else { lo = -1.0; hi = 1.0; }
         } else if (CONES && row < ROW_TAU) {                   // friction pyramid on R^T f
             const int ci = (row - ROW_CONE) / 5, jr = (row - ROW_CONE) % 5;
@@ -411,7 +413,7 @@ struct ForceAcc {
             const double c2 = jr == 4 ? -1.0 : -mu;
             for (int j = tid; j < N; j += TEAM) {
                 double v = 0.0;
-                const int k = j - (NV + 3 * ci);
+                const int k = j - (NV + WD * ci);
                 if (k >= 0 && k < 3) v = c0 * R[3 * k] + c1 * R[3 * k + 1] + c2 * R[3 * k + 2];
                 av[j] = v;
             }
@@ -421,7 +423,7 @@ struct ForceAcc {
             for (int j = tid; j < N; j += TEAM) {
                 double v;
                 if (j < NV) v = M(rec, 6 + a, j);
-                else { const int ci = (j - NV) / 3, k = (j - NV) % 3; v = -jcl(rec, g, ci, k, 6 + a); }
+                else { const int ci = (j - NV) / WD, k = (j - NV) % WD; v = -jcl(rec, g, ci, k, 6 + a); }
                 av[j] = v;
             }
             const double ha = rec[OFF_H - SB + 6 + a];
@@ -437,17 +439,18 @@ struct ForceAcc {
     // variables of its contact and the two bounds.
     static constexpr int CT = 5;
     static constexpr int NCT = NI_CHEAP * CT + ((NI_CHEAP * CT) & 1);
-    __device__ static __forceinline__ int slot_row(int q) { return q < NI_BOX ? ROW_BOX + 6 * (q / 3) + q % 3 : ROW_CONE + (q - NI_BOX); }
-    __device__ static __forceinline__ int slot_col(int q) { return NV + 3 * (q < NI_BOX ? q / 3 : (q - NI_BOX) / 5); }
+    __device__ static __forceinline__ int slot_row(int q) { return q < NI_BOX ? ROW_BOX + 6 * (q / WD) + q % WD : ROW_CONE + (q - NI_BOX); }
+    // first of the three consecutive variables the slot's coefficients refer to (force or torque part of a wrench)
+    __device__ static __forceinline__ int slot_col(int q) { return q < NI_BOX ? NV + WD * (q / WD) + 3 * ((q % WD) / 3) : NV + WD * ((q - NI_BOX) / 5); }
     template <int TEAM>
     __device__ static __forceinline__ void fill_slot_table(const double* rec, double* ct, int tid)
     {
         for (int q = tid; q < NI_CHEAP; q += TEAM) {
             double a0, a1, a2, lo, hi;
             if (q < NI_BOX) {                                  // wrench box (GenericConstraint), force rows
-                const int ci = q / 3, k = q % 3;
-                a0 = k == 0 ? 1.0 : 0.0; a1 = k == 1 ? 1.0 : 0.0; a2 = k == 2 ? 1.0 : 0.0;
-                lo = rec[OFF_FBOX - SB + 6 * ci + k]; hi = rec[OFF_FBOX - SB + 6 * ci + 3 + k];
+                const int ci = q / WD, k = q % WD;
+                a0 = k % 3 == 0 ? 1.0 : 0.0; a1 = k % 3 == 1 ? 1.0 : 0.0; a2 = k % 3 == 2 ? 1.0 : 0.0;
+                lo = rec[OFF_FBOX - SB + 2 * WD * ci + k]; hi = rec[OFF_FBOX - SB + 2 * WD * ci + WD + k];
             } else {                                           // friction pyramid on R^T f
                 const int qq = q - NI_BOX, ci = qq / 5, jr = qq % 5;
                 const double* R = rec + OFF_CONE - SB + 10 * ci;
@@ -468,7 +471,7 @@ struct ForceAcc {
     __device__ static __forceinline__ bool sparse_row(const double* ct, int row, int& j0, double& a0, double& a1, double& a2)
     {
         if (row < ROW_BOX || row >= ROW_TAU) return false;     // (without cones ROW_TAU == ROW_CONE)
-        const int q = row < ROW_CONE ? 3 * ((row - ROW_BOX) / 6) + (row - ROW_BOX) % 6 : NI_BOX + (row - ROW_CONE);
+        const int q = row < ROW_CONE ? WD * ((row - ROW_BOX) / 6) + (row - ROW_BOX) % 6 : NI_BOX + (row - ROW_CONE);
         j0 = slot_col(q);
         a0 = ct[q * CT]; a1 = ct[q * CT + 1]; a2 = ct[q * CT + 2];
         return true;
@@ -508,7 +511,7 @@ struct ForceAcc {
 #pragma unroll 1
             for (int ci = 0; ci < NC; ++ci)
 #pragma unroll
-                for (int k = 0; k < 3; ++k) v2 = fma(-jcl(rec, g, ci, k, i), x[NV + 3 * ci + k], v2);
+                for (int k = 0; k < WD; ++k) v2 = fma(-jcl(rec, g, ci, k, i), x[NV + WD * ci + k], v2);
             const double ha = rec[OFF_H - SB + i];
             val = (v0 + v1) + (v2 + v3); lo = rec[OFF_TAULIM - SB + a] - ha; hi = rec[OFF_TAULIM - SB + NA + a] - ha;
         }
@@ -529,7 +532,7 @@ struct ForceAcc {
 #pragma unroll 1
             for (int j = i + 1; j < NV; ++j) v1 = fma(g[OFF_M + j * (j + 1) / 2 + i], x[j], v1);
 #pragma unroll 1
-            for (int f = 0; f < 3 * NC; ++f) v0 = fma(-g[OFF_JC + ((f / 3) * 6 + f % 3) * NV + i], x[NV + f], v0);
+            for (int f = 0; f < WD * NC; ++f) v0 = fma(-g[OFF_JC + ((f / WD) * 6 + f % WD) * NV + i], x[NV + f], v0);
             val = v0 + v1;
             const double hv = g[OFF_H + i];
             if (row < ROW_BOX) lo = hi = -hv;
@@ -538,14 +541,14 @@ struct ForceAcc {
         }
         if (row < ROW_CONE) {
             const int ci = (row - ROW_BOX) / 6, k = (row - ROW_BOX) % 6;
-            if (k >= 3) return false;
-            val = x[NV + 3 * ci + k]; lo = g[OFF_FBOX + 6 * ci + k]; hi = g[OFF_FBOX + 6 * ci + 3 + k];
+            if (k >= WD) return false;
+            val = x[NV + WD * ci + k]; lo = g[OFF_FBOX + 2 * WD * ci + k]; hi = g[OFF_FBOX + 2 * WD * ci + WD + k];
             return true;
         }
         if (CONES && row < ROW_TAU) {
             double v = 0.0;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) v = fma(row_coef(g, row, NV + 3 * ((row - ROW_CONE) / 5) + k), x[NV + 3 * ((row - ROW_CONE) / 5) + k], v);
+            for (int k = 0; k < 3; ++k) v = fma(row_coef(g, row, NV + WD * ((row - ROW_CONE) / 5) + k), x[NV + WD * ((row - ROW_CONE) / 5) + k], v);
             val = v; lo = -QPPVM_INFTY; hi = 0.0;
             return true;
         }
@@ -564,15 +567,15 @@ struct ForceAcc {
             const int i = row < ROW_BOX ? row : 6 + (row - ROW_TAU);
             if (j < NV) return i >= j ? g[OFF_M + i * (i + 1) / 2 + j] : g[OFF_M + j * (j + 1) / 2 + i];
             const int f = j - NV;
-            return -g[OFF_JC + ((f / 3) * 6 + f % 3) * NV + i];
+            return -g[OFF_JC + ((f / WD) * 6 + f % WD) * NV + i];
         }
         if (row < ROW_CONE) {
             const int ci = (row - ROW_BOX) / 6, k = (row - ROW_BOX) % 6;
-            return (k < 3 && j == NV + 3 * ci + k) ? 1.0 : 0.0;
+            return (k < WD && j == NV + WD * ci + k) ? 1.0 : 0.0;
         }
         if (CONES && row < ROW_TAU) {
             const int ci = (row - ROW_CONE) / 5, jr = (row - ROW_CONE) % 5;
-            const int k = j - (NV + 3 * ci);
+            const int k = j - (NV + WD * ci);
             if (k < 0 || k >= 3) return 0.0;
             const double* R = g + OFF_CONE + 10 * ci;
             const double mu = R[9] * 0.70710678118654752440;
@@ -635,7 +638,7 @@ struct ForceAcc {
                 const int i = 6 + a;
                 v = rec[OFF_H - SB + i];
                 for (int j = 0; j < NV; ++j) v = fma(M(rec, i, j), x[j], v);
-                for (int j = 0; j < 3 * NC; ++j) v = fma(-jcl(rec, g, j / 3, j % 3, i), x[NV + j], v);
+                for (int j = 0; j < WD * NC; ++j) v = fma(-jcl(rec, g, j / WD, j % WD, i), x[NV + j], v);
             }
             tau_out[a] = v;     // failure: nothing is commanded (ForceAcc.cpp:189-193) -> zeros
         }
@@ -657,6 +660,7 @@ struct Torque {
     static constexpr int NV = NA, N = NA, NB = NA;
     static constexpr int MD0 = 6, MD1 = NA, MD_MAX = NA;
     static constexpr int ROW_BOX = 0, ROW_OPT = NA, NROWS = NA + QPPVM_M0;
+    static constexpr int WD = 3;
     static constexpr int NI = NA, NI_CHEAP = 0;              // every bound row is a (dense) row of J in whitened coordinates
     static constexpr bool TAUVAL = false;
     static constexpr int NTV = 0, NCT = 0;
@@ -1102,7 +1106,8 @@ struct Solver {
     // Triangular mat-vecs with J.  A warp executes as many iterations as its longest lane, and with one column
     // (row) per thread the long ones sit next to idle lanes: the part of a column beyond HALF entries goes to a
     // helper thread (tid >= NB), whose partial sum travels through d1 (scratch of gs_pass, free here).
-    static constexpr int HALF = (NB - 1) / 2;                  // main lanes: entries [0, HALF] of their column
+    // (at most TEAM - NB helper lanes exist: wide shapes leave more of each column to the main lane)
+    static constexpr int HALF = (NB - 1) / 2 > 2 * NB - 1 - TEAM ? (NB - 1) / 2 : 2 * NB - 1 - TEAM;   // main lanes: entries [0, HALF] of their column
     static constexpr int NHELP = NB - 1 - HALF;                // columns HALF + 1 .. NB - 1 have a helper
     static_assert(NB + NHELP <= TEAM && NHELP <= KP, "helper lanes and their exchange slots");
 
@@ -1940,9 +1945,9 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
         if (Slab<P>::STAGE) {
             // linear contact-Jacobian rows next to the staged tail (plain coalesced loads, overlapping the TMA copy)
             const double* gr = recs + idx * (size_t)P::REC;
-            for (int t = tid; t < 3 * P::NC * P::NV; t += TEAM) {
+            for (int t = tid; t < P::WD * P::NC * P::NV; t += TEAM) {
                 const int rowl = t / P::NV, col = t - rowl * P::NV;
-                SV::rec_()[P::S_JCL + t] = gr[P::NV * 6 + ((rowl / 3) * 6 + (rowl % 3)) * P::NV + col];
+                SV::rec_()[P::S_JCL + t] = gr[P::NV * 6 + ((rowl / P::WD) * 6 + (rowl % P::WD)) * P::NV + col];
             }
             mbar_wait(SV::mbar_(), phase); phase ^= 1;
             __syncthreads();
@@ -2023,7 +2028,9 @@ struct FactorShape {
     // per-pair block (doubles): J | Ad | dg | db | u0 | jd | broadcast | normals -> Q | RN | 1/diag.
     // After the factorisation Ad|dg|db hold the equality rows [e][i] and the broadcast slots their right-hand sides.
     static constexpr int NEQ = Slab<P>::NEQ_MAX;
-    static constexpr int O_AD = SZ_J, O_DG = O_AD + MD * LDA + ((MD * LDA) & 1), O_DB = O_DG + VEC, O_U0 = O_DB + VEC;
+    // (Ad | dg | db are reused for the NEQ x N equality rows: wide shapes with few task rows pad Ad)
+    static constexpr int SZ_AD_RAW = MD * LDA > NEQ * N - 2 * VEC ? MD * LDA : NEQ * N - 2 * VEC;
+    static constexpr int O_AD = SZ_J, O_DG = O_AD + SZ_AD_RAW + (SZ_AD_RAW & 1), O_DB = O_DG + VEC, O_U0 = O_DB + VEC;
     static constexpr int O_JD = O_U0 + VEC, O_BC = O_JD + VEC, O_WQ = O_BC + 2 * (MD + 4);
     static constexpr int O_RN = O_WQ + NEQ * N + ((NEQ * N) & 1), O_RDI = O_RN + NEQ * NEQ, BLOCK = O_RDI + NEQ;
     static_assert(O_U0 - O_AD >= NEQ * N, "equality rows fit over Ad | dg | db");

@@ -47,14 +47,13 @@ constexpr ShapeEntry entry()
                       factor_entry<P>(), Slab<P>::WS,
                       FactorShape<P>::THREADS, FactorShape<P>::FPC, FactorShape<P>::BYTES, certify_entry<P>()};
 }
-constexpr int F_ALL = QPPVM_FLAG_FRICTION_CONES | QPPVM_FLAG_TORQUE_LIMITS;
+// The instantiation list is generated from the build-time table shapes.def (one line per robot / constraint set).
 const ShapeEntry g_shapes[] = {
-    entry<ForceAcc<29, 2, 0>>(),       // config [1]: literal ForceAcc structure, COMAN-like, 2 contacts
-    entry<ForceAcc<29, 2, F_ALL>>(),   // configs [0], [4]: + cones + torque limits
-    entry<ForceAcc<33, 4, F_ALL>>(),   // configs [2], [3]: WALK-MAN-like, 4 contacts
-    entry<ForceAcc<33, 4, 0>>(),
-    entry<Torque<29>>(),               // literal QPPVMPlugin stack (fixed base), 29 and 39 joints
-    entry<Torque<39>>(),
+#define QPPVM_SHAPE_FORCEACC(NA, NC, FLAGS) entry<ForceAcc<NA, NC, (FLAGS)>>(),
+#define QPPVM_SHAPE_TORQUE(NA) entry<Torque<NA>>(),
+#include "shapes.def"
+#undef QPPVM_SHAPE_FORCEACC
+#undef QPPVM_SHAPE_TORQUE
 };
 constexpr int N_SHAPES = sizeof(g_shapes) / sizeof(g_shapes[0]);
 
@@ -261,7 +260,8 @@ int qppvm_get_layout(const qppvm_desc* d, qppvm_layout* L)
         if (c < 1 || c > 4) return QPPVM_ERR_ARG;
         const bool cones = d->flags & QPPVM_FLAG_FRICTION_CONES, tl = d->flags & QPPVM_FLAG_TORQUE_LIMITS;
         const int nv = d->n_a + 6;
-        L->n_a = d->n_a; L->n_v = nv; L->n_c = c; L->n_x = nv + 3 * c;
+        const int wd = (d->flags & QPPVM_FLAG_FULL_WRENCH) ? 6 : 3;
+        L->n_a = d->n_a; L->n_v = nv; L->n_c = c; L->n_x = nv + wd * c;
         if (L->n_x > 64) return QPPVM_ERR_ARG;
         L->row_dyn = row; row += 6;
         L->row_box = row; row += 6 * c;
@@ -276,7 +276,7 @@ int qppvm_get_layout(const qppvm_desc* d, qppvm_layout* L)
         L->off_rhs = off; off += 6 * (1 + c) + nv;
         L->off_taulim = tl ? off : -1; if (tl) off += 2 * d->n_a;
         L->off_cone = cones ? off : -1; if (cones) off += 10 * c;
-        L->off_fbox = off; off += 6 * c;
+        L->off_fbox = off; off += 2 * wd * c;
         L->off_fee = L->off_tauj = -1;
     } else if (d->kind == QPPVM_KIND_TORQUE) {
         if (d->n_contacts != 2 || d->flags != 0) return QPPVM_ERR_ARG;
@@ -553,7 +553,7 @@ int qppvm_reset_warm(qppvm_handle* h)
 static int state_layout(const qppvm_desc* d, RbdShape* sh)
 {
     qppvm_layout L;
-    if (!d || d->kind != QPPVM_KIND_FORCEACC || qppvm_get_layout(d, &L)) return -1;
+    if (!d || d->kind != QPPVM_KIND_FORCEACC || (d->flags & QPPVM_FLAG_FULL_WRENCH) || qppvm_get_layout(d, &L)) return -1;
     const int na = L.n_a, c = L.n_c;
     int o = 0;
     RbdShape s;

@@ -15,7 +15,7 @@ from __future__ import annotations
 import numpy as np
 from scipy.special import ndtri
 
-from .layout import (Desc, Layout, layout, KIND_FORCEACC, KIND_TORQUE, FLAG_FRICTION_CONES,
+from .layout import (Desc, Layout, layout, KIND_FORCEACC, KIND_TORQUE, FLAG_FRICTION_CONES, FLAG_FULL_WRENCH,
                      FLAG_TORQUE_LIMITS)
 
 DRAWS = 256            # uniforms reserved per problem (multiple of 4: Philox yields 4 per step)
@@ -321,8 +321,12 @@ def records_from_states(desc: Desc, states: np.ndarray) -> np.ndarray:
                 o = L.off_cone + 10 * ci
                 rec[:, o:o + 9] = dyn["links"][b]["R"].reshape(n, 9)
                 rec[:, o + 9] = mu[:, ci]
-            o = L.off_fbox + 6 * ci
-            rec[:, o:o + 6] = np.array([-1000.0, -1000.0, 10.0, 1000.0, 1000.0, 1000.0])  # ForceAcc.cpp:75-76
+            if desc.flags & FLAG_FULL_WRENCH:                    # "put 6 for full wrench" (ForceAcc.cpp:67): lb / ub of :75-76 in full
+                o = L.off_fbox + 12 * ci
+                rec[:, o:o + 12] = np.array([-1000.0, -1000.0, 10.0, -1.0, -1.0, -1.0, 1000.0, 1000.0, 1000.0, 1.0, 1.0, 1.0])
+            else:
+                o = L.off_fbox + 6 * ci
+                rec[:, o:o + 6] = np.array([-1000.0, -1000.0, 10.0, 1000.0, 1000.0, 1000.0])  # ForceAcc.cpp:75-76
         # postural: qddot = l2 (0 - qdot) + l (q_home - q); base rows carry the damping term only
         e_p = np.concatenate([np.zeros((n, 6)), rob.q_home[None] - q], axis=1)
         o = L.off_rhs + 6 * (1 + c)

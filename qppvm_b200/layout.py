@@ -16,6 +16,7 @@ KIND_TORQUE = 0
 KIND_FORCEACC = 1
 FLAG_FRICTION_CONES = 1
 FLAG_TORQUE_LIMITS = 2
+FLAG_FULL_WRENCH = 4      # 6 variables per contact ("put 6 for full wrench", ref:src/ForceAcc.cpp:67)
 STATUS_OK, STATUS_MAX_ITER, STATUS_INFEASIBLE, STATUS_NUMERIC = 0, 1, 2, 3
 QPOASES_EPS = 2.221e-16
 QPOASES_EPS_REG = 1.0e3 * QPOASES_EPS
@@ -94,7 +95,8 @@ def layout(desc: Desc) -> Layout:
         if c < 1 or c > 4:
             raise ValueError("n_contacts out of range")
         n_a, n_v = desc.n_a, desc.n_a + 6
-        n_x = n_v + 3 * c
+        wd = 6 if desc.flags & FLAG_FULL_WRENCH else 3
+        n_x = n_v + wd * c
         if n_x > 64:
             raise ValueError("n_x > 64 unsupported")
         cones = bool(desc.flags & FLAG_FRICTION_CONES)
@@ -114,7 +116,7 @@ def layout(desc: Desc) -> Layout:
         off_rhs = off; off += 6 * (1 + c) + n_v
         off_taulim = off if tl else -1; off += 2 * n_a if tl else 0
         off_cone = off if cones else -1; off += 10 * c if cones else 0
-        off_fbox = off; off += 6 * c
+        off_fbox = off; off += 2 * wd * c
         off_fee = off_tauj = -1
     elif desc.kind == KIND_TORQUE:
         if desc.n_contacts != 2 or desc.flags != 0:

@@ -20,33 +20,34 @@ def level_matrices(desc: Desc, rec: np.ndarray, level: int, x0=None):
         jdqd = rec[L.off_jdqd:L.off_jdqd + 6 * (1 + c)]
         rhs = rec[L.off_rhs:L.off_rhs + 6 * (1 + c) + nv]
         Z = np.zeros
+        wd = (n - nv) // c                       # 3 force components per contact, 6 with full wrenches (ForceAcc.cpp:67)
         if level == 0:   # _waist_task (ForceAcc.cpp:118-122)
-            A = np.hstack([Jw, Z((6, 3 * c))]); b = rhs[:6] - jdqd[:6]
+            A = np.hstack([Jw, Z((6, wd * c))]); b = rhs[:6] - jdqd[:6]
         else:            # _postural_task + feet_cart_aggr (ForceAcc.cpp:131)
-            A = np.vstack([np.hstack([np.eye(nv), Z((nv, 3 * c))])] +
-                          [np.hstack([Jc[i], Z((6, 3 * c))]) for i in range(c)])
+            A = np.vstack([np.hstack([np.eye(nv), Z((nv, wd * c))])] +
+                          [np.hstack([Jc[i], Z((6, wd * c))]) for i in range(c)])
             b = np.concatenate([rhs[6 * (1 + c):]] + [rhs[6 * (1 + i):6 * (2 + i)] - jdqd[6 * (1 + i):6 * (2 + i)] for i in range(c)])
         rows, lo, hi = [], [], []
         # DynamicFeasibility: (M qdd + h - sum J_i^T [f_i; 0])[0:6] = 0
-        D = np.hstack([M[:6]] + [-Jc[i][:3, :6].T for i in range(c)])
+        D = np.hstack([M[:6]] + [-Jc[i][:wd, :6].T for i in range(c)])
         rows.append(D); lo.append(-h[:6]); hi.append(-h[:6])
         for i in range(c):   # wrench_i = force_i / Zero(3)  in [lb, ub]  (ForceAcc.cpp:74-76, 81, 91-95)
-            W = Z((6, n)); W[:3, nv + 3 * i:nv + 3 * i + 3] = np.eye(3)
-            fb = rec[L.off_fbox + 6 * i:L.off_fbox + 6 * i + 6]
-            rows.append(W); lo.append(np.concatenate([fb[:3], -np.ones(3)])); hi.append(np.concatenate([fb[3:], np.ones(3)]))
+            W = Z((6, n)); W[:wd, nv + wd * i:nv + wd * i + wd] = np.eye(wd)
+            fb = rec[L.off_fbox + 2 * wd * i:L.off_fbox + 2 * wd * i + 2 * wd]
+            rows.append(W); lo.append(np.concatenate([fb[:wd], -np.ones(6 - wd)])); hi.append(np.concatenate([fb[wd:], np.ones(6 - wd)]))
         if L.row_cone >= 0:
             for i in range(c):
                 blk = rec[L.off_cone + 10 * i:L.off_cone + 10 * i + 10]
                 R, mu = blk[:9].reshape(3, 3), blk[9] / np.sqrt(2.0)
                 Ci = np.array([[1, 0, -mu], [-1, 0, -mu], [0, 1, -mu], [0, -1, -mu], [0, 0, -1.0]])
-                F = Z((5, n)); F[:, nv + 3 * i:nv + 3 * i + 3] = Ci @ R.T
+                F = Z((5, n)); F[:, nv + wd * i:nv + wd * i + 3] = Ci @ R.T
                 rows.append(F); lo.append(np.full(5, -INFTY)); hi.append(np.zeros(5))
         if L.row_tau >= 0:
-            T = np.hstack([M[6:]] + [-Jc[i][:3, 6:].T for i in range(c)])
+            T = np.hstack([M[6:]] + [-Jc[i][:wd, 6:].T for i in range(c)])
             tl = rec[L.off_taulim:L.off_taulim + 2 * na]
             rows.append(T); lo.append(tl[:na] - h[6:]); hi.append(tl[na:] - h[6:])
         if level == 1:
-            A0 = np.hstack([Jw, Z((6, 3 * c))])
+            A0 = np.hstack([Jw, Z((6, wd * c))])
             rows.append(A0); lo.append(A0 @ x0); hi.append(A0 @ x0)
         eps = desc.eps_regularisation * QPOASES_EPS_REG
     else:

@@ -49,6 +49,55 @@ def test_parity_vs_oracle(torch_mod, oracle_mod, ci, batch):
     assert rel_inf(gdg["x0"], odg["x0"]).max() <= 1e-4      # level-0 point: eps-defined directions
 
 
+def test_parity_literal_forceacc_shape(torch_mod, oracle_mod):
+    """The reference's own ForceAcc stack: four foot contacts, n_v = 45, no cones / torque limits
+    (ref:src/ForceAcc.cpp:58-137); one line in csrc/shapes.def."""
+    from qppvm_b200 import api
+    desc = Desc(n_a=39, n_contacts=4, flags=0)
+    L = layout(desc)
+    assert (1, 39, 4, 0) in api.supported_shapes()
+    recs = gen.generate(desc, 512, 3939)
+    oo, od = oracle_mod.solve_batch(desc, recs, diag=True)
+    o, odg = oracle_mod.split_out(desc, oo), api.split_diag(L, od)
+    g, gdg = _solve_gpu(torch_mod, desc, recs)
+    r = compare(L, g, o, gdg, odg)
+    assert r["status_equal"] and r["both_ok"] == 512
+    assert r["primal"] <= PRIMAL_TOL and r["tau"] <= PRIMAL_TOL and r["kkt_gpu"] <= KKT_TOL
+    assert r["mask_equal"] == 1.0 and r["strong_active_equal"] == 1.0 and r["strong_sign_equal"] == 1.0
+
+
+@pytest.mark.parametrize("n_a,c,flags", [(29, 2, 4), (29, 2, 7)])
+def test_parity_full_wrench_variables(torch_mod, oracle_mod, n_a, c, flags):
+    """Six variables per contact ("put 6 for full wrench", ref:src/ForceAcc.cpp:67) with the reference's literal wrench
+    bounds lb = (-1000, -1000, 10, -1, -1, -1), ub = (1000, 1000, 1000, 1, 1, 1) (ref:src/ForceAcc.cpp:75-76): all six
+    rows of every GenericConstraint are real rows, the contact torques enter the dynamics and the torque recovery."""
+    from qppvm_b200 import api
+    desc = Desc(n_a=n_a, n_contacts=c, flags=flags)
+    L = layout(desc)
+    assert L.n_x == n_a + 6 + 6 * c
+    recs = gen.generate(desc, 384, 6006)
+    oo, od = oracle_mod.solve_batch(desc, recs, diag=True)
+    o, odg = oracle_mod.split_out(desc, oo), api.split_diag(L, od)
+    g, gdg = _solve_gpu(torch_mod, desc, recs)
+    r = compare(L, g, o, gdg, odg)
+    assert r["status_equal"] and r["both_ok"] == 384
+    assert r["kkt_gpu"] <= KKT_TOL and r["kkt_oracle"] <= KKT_TOL and r["eopt"] <= PRIMAL_TOL
+    # Accelerations and contact forces to north_star's 1e-6.  The contact TORQUES carry no task cost: where the
+    # dynamics only see a combination of them, the split between contacts is defined by the 2.2e-9 regularisation
+    # alone, i.e. to (KKT residual ~1e-12) / 2.2e-9 -- two KKT-exact solutions (same objective to 12 digits, same active
+    # set) differ by ~5e-4 there.  Those variables, and the joint torques they feed, are compared to 1e-4.
+    sel = np.ones(L.n_x, dtype=bool)
+    sel[L.n_v:] = np.tile(np.array([1, 1, 1, 0, 0, 0], dtype=bool), c)
+    assert rel_inf(g["x"][:, sel], o["x"][:, sel]).max() <= PRIMAL_TOL
+    assert r["primal"] <= 1e-4 and r["tau"] <= 1e-4
+    ndiff, tight = mask_differences_are_degenerate(desc, L, recs, g["x"], gdg["x0"], g["active"], o["active"])
+    assert tight and ndiff <= 0.02 * 384
+    assert r["strong_active_equal"] >= 0.98
+    # the contact torques are variables now and sit inside (mostly on) their +-1 bounds
+    tq = g["x"][:, L.n_v:].reshape(384, c, 6)[:, :, 3:]
+    assert np.abs(tq).max() <= 1.0 + 1e-9 and (np.abs(tq) > 1e-3).any()
+
+
 @pytest.mark.parametrize("n_a", (29, 39))
 def test_parity_torque_kind(torch_mod, oracle_mod, n_a):
     """The literal QPPVMPlugin stack (x = tau, fixed base): ref:src/QPPVMPlugin.cpp:112-188, 201-259."""

@@ -85,10 +85,11 @@ def _run(built, lib, factory, states, out, T, nv, floating, links):
 
 
 @pytest.mark.gpu
-def test_forceacc_plugin_boundary(built, oracle_mod, tmp_path):
-    rob = gen.robot_for(33)
-    nv, T = 39, 10
-    desc = Desc(n_a=33, n_contacts=4, flags=0)
+@pytest.mark.parametrize("n_a", (33, 39))                  # 39: the reference's literal shape, n_v = 45 (ref:src/ForceAcc.cpp:58-70)
+def test_forceacc_plugin_boundary(built, oracle_mod, tmp_path, n_a):
+    rob = gen.robot_for(n_a)
+    nv, T = n_a + 6, 10
+    desc = Desc(n_a=n_a, n_contacts=4, flags=0)
     L = layout(desc)
     links = ["pelvis", "foot_fl", "foot_fr", "foot_hr", "foot_hl"]
     bodies = [0] + rob.foot + rob.hand
