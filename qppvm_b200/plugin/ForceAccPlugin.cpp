@@ -166,6 +166,23 @@ void XBotPlugin::ForceAccExample::control_loop(double time, double period)
         _logger->add(_contact_links[i] + "_wrench", _wrench_value[i]);
     }
 
+    /* Dynamic-feasibility residual, what _dyn_feas->checkConstraint(_x) reports at :203: the base rows of
+     * M qdd + h - sum J_i^T w_i, from the same record the solver saw.  Traced next to the solver diagnostics. */
+    {
+        Eigen::VectorXd res(6), diag(4);
+        const double* M = _record.data() + _L.off_M;
+        for (int r = 0; r < 6; ++r) {
+            double v = _record[_L.off_h + r];
+            for (int j = 0; j < nv; ++j) v += (r >= j ? M[r * (r + 1) / 2 + j] : M[j * (j + 1) / 2 + r]) * _x[j];
+            for (size_t i = 0; i < _contact_links.size(); ++i)
+                for (int k = 0; k < 3; ++k) v -= _record[_L.off_jc + (i * 6 + k) * nv + r] * _x[nv + 3 * i + k];
+            res[r] = v;
+        }
+        _logger->add("dyn_feas_residual", res);
+        diag[0] = tr.status; diag[1] = tr.iters & 0xffff; diag[2] = tr.iters >> 16; diag[3] = tr.kkt[0] > tr.kkt[1] ? tr.kkt[0] : tr.kkt[1];
+        _logger->add("qp_status_iters_kkt", diag);
+    }
+
     /* Torques due to contacts (:206-210) and inverse dynamics (:213-219): tau = M qdd + h - sum J^T w.
      * The kernel returns the actuated rows; the 6 base rows are the dyn-feas residual (zero). */
     _model->setJointAcceleration(_qddot_value);

@@ -4,7 +4,9 @@
 // MatLogger / Handle as the reference calls them (file:line next to each).
 #pragma once
 #include <Eigen/Dense>
+#include "../../MatTrace.h"
 #include <map>
+#include <cstdlib>
 #include <memory>
 #include <string>
 #include <vector>
@@ -17,11 +19,30 @@ typedef std::map<int, double> JointIdMap;
 class MatLogger {
 public:
     typedef std::shared_ptr<MatLogger> Ptr;
-    static Ptr getLogger(const std::string&) { return std::make_shared<MatLogger>(); }      // ForceAcc.cpp:34
-    void add(const std::string& name, const Eigen::VectorXd& v) { last_[name] = v; }         // ForceAcc.cpp:200,233-236
-    void add(const std::string&, double) {}
-    void flush() { ++flushes; }                                                              // ForceAcc.h:43
+    static Ptr getLogger(const std::string& path)                                            // ForceAcc.cpp:34
+    {
+        auto p = std::make_shared<MatLogger>();
+        p->path_ = path;
+        return p;
+    }
+    void add(const std::string& name, const Eigen::VectorXd& v)                              // ForceAcc.cpp:200,233-236
+    {
+        last_[name] = v;
+        trace_.add(name, v.data(), (int)v.size());
+    }
+    void add(const std::string& name, double v) { trace_.add(name, v); }                     // QPPVMPlugin.cpp:322
+    // the real MatLogger writes <path>.mat on flush; here the file lands next to the test outputs (QPPVM_TRACE_DIR)
+    void flush()                                                                             // ForceAcc.h:43
+    {
+        ++flushes;
+        const char* dir = getenv("QPPVM_TRACE_DIR");
+        if (!dir) return;
+        std::string base = path_.substr(path_.find_last_of('/') == std::string::npos ? 0 : path_.find_last_of('/') + 1);
+        trace_.flush(std::string(dir) + "/" + base + ".mat");
+    }
     std::map<std::string, Eigen::VectorXd> last_;
+    qppvm::MatTrace trace_;
+    std::string path_;
     int flushes = 0;
 };
 

@@ -106,6 +106,7 @@ def test_forceacc_plugin_boundary(built, oracle_mod, tmp_path, n_a):
             lk = dyn["links"][b]
             yield from (lk["J"][t], lk["Jdqd"][t], lk["R"][t], lk["p"][t], lk["J"][t] @ vfull[t])
     _write_states(tmp_path / "s.bin", T, nv, tick)
+    os.environ["QPPVM_TRACE_DIR"] = str(tmp_path)
     stdout, stderr = _run(built, "libForceAccPlugin.so", "create_instance", str(tmp_path / "s.bin"), str(tmp_path / "o.bin"), T, nv, True, links)
     per = 3 + nv + L.rec_doubles + L.out_doubles
     o = np.fromfile(tmp_path / "o.bin").reshape(T, per)
@@ -143,6 +144,16 @@ def test_forceacc_plugin_boundary(built, oracle_mod, tmp_path, n_a):
     assert (oo["status"] == 0).all()
     assert rel_inf(out[:-1, :L.n_x], oo["x"]).max() <= PRIMAL_TOL
     assert rel_inf(eff[:-1, 6:], oo["tau"]).max() <= PRIMAL_TOL and np.abs(eff[:-1, :6]).max() == 0.0
+    # ---- MatLogger-compatible trace (ref:src/ForceAcc.cpp:200,233-236, flushed in close(): ForceAcc.h:43): one column per
+    # commanded tick under the reference's variable names, readable as a MAT-file
+    import scipy.io
+    tr = scipy.io.loadmat(str(tmp_path / "opensot_force_acc_example.mat"))
+    assert tr["x"].shape == (L.n_x, T - 1) and tr["tau"].shape == (nv, T - 1) and tr["foot_fl_wrench"].shape == (6, T - 1)
+    np.testing.assert_array_equal(tr["x"].T, out[:-1, :L.n_x])
+    np.testing.assert_array_equal(tr["tau"].T[:, 6:], out[:-1, L.n_x:L.n_x + L.n_a])
+    np.testing.assert_array_equal(tr["qddot_value"].T, out[:-1, :nv])
+    assert np.abs(tr["dyn_feas_residual"]).max() <= 1e-8          # what checkConstraint(_x) reports at ForceAcc.cpp:203
+    assert (tr["qp_status_iters_kkt"][0] == 0).all() and tr["qp_status_iters_kkt"][3].max() <= 1e-6
 
 
 @pytest.mark.gpu
