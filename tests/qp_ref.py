@@ -97,3 +97,86 @@ def brute_force_qp(H, g, C, lA, uA, tol=1e-9):
         if best is None or f < best[2] - 1e-12:
             best = (x, y, f)
     return best
+
+
+def primal_active_set(A, b, C, lA, uA, eps, xp=None, maxit=4000):
+    """min 1/2 ||A x - b||^2 + eps/2 ||x - xp||^2  s.t. lA <= C x <= uA  by a PRIMAL active-set method (the family qpOASES
+    belongs to; the oracle and the CUDA kernels are DUAL methods, Goldfarb-Idnani): start from a feasible vertex found
+    by HiGHS' LP phase 1, keep every iterate feasible, solve the equality-constrained problem on the working set, step
+    until a constraint blocks (it joins the working set) or the step is complete (then the most wrong-signed multiplier
+    leaves).  Whitened coordinates u = R x with R from a QR of [A; sqrt(eps) I] so that H is never formed; the working
+    set is re-factorised from scratch every iteration (numpy QR): nothing incremental, nothing shared with oracle/.
+    Returns (x, y, iterations); y > 0: active at lA, y < 0: active at uA (qpOASES sign convention)."""
+    from scipy.linalg import solve_triangular
+    from scipy.optimize import linprog
+    m, n = C.shape
+    Rq = np.linalg.qr(np.vstack([A, np.sqrt(eps) * np.eye(n)]), mode="r")
+    u0 = solve_triangular(Rq.T, A.T @ b + (eps * xp if xp is not None else 0.0), lower=True)
+    Wm = solve_triangular(Rq.T, C.T, lower=True)               # whitened normals, one column per row of C
+    wnorm = np.linalg.norm(Wm, axis=0)
+    eq = lA == uA
+    lo_f, hi_f = (lA > -0.5 * INF) & ~eq, (uA < 0.5 * INF) & ~eq
+    lp = linprog(np.zeros(n), A_ub=np.vstack([C[hi_f], -C[lo_f]]), b_ub=np.concatenate([uA[hi_f], -lA[lo_f]]),
+                 A_eq=C[eq] if eq.any() else None, b_eq=lA[eq] if eq.any() else None, bounds=(None, None), method="highs")
+    if lp.status != 0:
+        raise RuntimeError("phase 1: " + lp.message)
+    u = Rq @ lp.x
+    work = [(int(i), 0) for i in np.nonzero(eq)[0]]
+    for it in range(maxit):
+        idx = [i for i, _ in work]
+        if idx:
+            Wk = Wm[:, idx]
+            bk = np.array([uA[i] if s < 0 else lA[i] for i, s in work])
+            Q, R1 = np.linalg.qr(Wk)
+            ustar = u0 + Q @ solve_triangular(R1.T, bk - Wk.T @ u0, lower=True)
+        else:
+            ustar = u0
+        p = ustar - u
+        if len(idx) >= n or np.linalg.norm(p) <= 1e-11 * max(1.0, np.linalg.norm(u)):   # (n independent rows: a vertex)
+            u = ustar
+            y = solve_triangular(R1, Q.T @ (ustar - u0)) if idx else np.zeros(0)
+            sc = max(1.0, np.abs(y).max()) if idx else 1.0
+            worst, wj = 0.0, -1
+            for j, (i, s) in enumerate(work):
+                if s != 0 and y[j] * s < -1e-11 * sc and y[j] * s < worst:
+                    worst, wj = y[j] * s, j
+            if wj < 0:
+                yy = np.zeros(m)
+                yy[idx] = y
+                return solve_triangular(Rq, ustar), yy, it
+            del work[wj]
+            continue
+        cu, cp = Wm.T @ u, Wm.T @ p
+        inw = np.zeros(m, dtype=bool)
+        inw[idx] = True
+        alpha, blk = 1.0, None
+        thr = 1e-13 * np.linalg.norm(p) * wnorm                # a row only blocks if the step really moves along it
+        for i in np.nonzero(~inw & ~eq)[0]:
+            if lo_f[i] and cp[i] < -thr[i]:
+                a = max((lA[i] - cu[i]) / cp[i], 0.0)
+                if a < alpha:
+                    alpha, blk = a, (int(i), 1)
+            if hi_f[i] and cp[i] > thr[i]:
+                a = max((uA[i] - cu[i]) / cp[i], 0.0)
+                if a < alpha:
+                    alpha, blk = a, (int(i), -1)
+        u = u + alpha * p
+        if blk is not None:
+            work.append(blk)
+    raise RuntimeError("primal active set: iteration limit")
+
+
+def cascade_primal(desc, rec, level_matrices):
+    """The two-level cascade of one record with primal_active_set, including qpOASES' regularisation semantics
+    (solve with H + eps I, then numRegularisationSteps proximal re-solves g <- g - eps x_prev).
+    Returns (x0, x1, y1)."""
+    xs = []
+    x0 = None
+    for level in (0, 1):
+        A, b, C, lA, uA, eps = level_matrices(desc, rec, level, x0)
+        x, y, _ = primal_active_set(A, b, C, lA, uA, eps)
+        for _ in range(desc.n_reg_steps if eps > 0.0 else 0):
+            x, y, _ = primal_active_set(A, b, C, lA, uA, eps, xp=x)
+        xs.append(x)
+        x0 = x
+    return xs[0], xs[1], y
