@@ -73,7 +73,12 @@ typedef struct qppvm_desc {
     int32_t n_reg_steps;        /* qpOASES numRegularisationSteps (MPC option set: 1)    */
     int32_t max_iter;           /* working-set changes allowed per level (nWSR): 132     */
     int32_t device;             /* CUDA ordinal                                          */
-    int32_t reserved;
+    int32_t postural_actuated_only; /* FORCEACC: 1 = the Postural task has no rows for the 6 floating-base velocities
+                                   (later OpenSoT versions); 0 = A = [I 0] on all n_v rows    */
+    /* Upstream semantics that varied across OpenSoT versions ("make it a parameter").  FORCEACC kind.
+     * 0.0 means "not set" and is read as 1.0, so a zero-initialised tail reproduces the consistent reading. */
+    double  lambda_solver;      /* QPOases_sot: g = -lambda A^T W b (A.2): multiplies every task right-hand side */
+    double  task_weight[3];     /* W = w I per task: waist (level 0), postural, contact-link Cartesian (level 1) */
 } qppvm_desc;
 
 /*

@@ -21,7 +21,8 @@ FACTOR_QR = 1         # Householder QR of [A; sqrt(eps) I]
 class CDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_a", C.c_int32), ("n_contacts", C.c_int32), ("flags", C.c_int32),
                 ("eps_regularisation", C.c_double), ("n_reg_steps", C.c_int32), ("max_iter", C.c_int32),
-                ("device", C.c_int32), ("reserved", C.c_int32)]
+                ("device", C.c_int32), ("postural_actuated_only", C.c_int32), ("lambda_solver", C.c_double),
+                ("task_weight", C.c_double * 3)]
 
 
 LAYOUT_FIELDS = ("n_a", "n_v", "n_c", "n_x", "n_rows", "row_dyn", "row_box", "row_cone", "row_tau",
@@ -64,7 +65,8 @@ def lib():
 
 def cdesc(desc) -> CDesc:
     return CDesc(desc.kind, desc.n_a, desc.n_contacts, desc.flags, desc.eps_regularisation,
-                 desc.n_reg_steps, desc.max_iter, desc.device, 0)
+                 desc.n_reg_steps, desc.max_iter, desc.device, desc.postural_actuated_only, desc.lambda_solver,
+                 (C.c_double * 3)(*desc.task_weight))
 
 
 def c_layout(desc) -> dict:

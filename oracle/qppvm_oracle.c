@@ -120,27 +120,34 @@ static void assemble_forceacc(const qppvm_desc* d, const qppvm_layout* L, const 
     const int wd = (d->flags & QPPVM_FLAG_FULL_WRENCH) ? 6 : 3;   /* wrench variables per contact */
     q->n = n;
     q->eps = d->eps_regularisation * QPPVM_QPOASES_EPS_REG;
+    /* H = A^T W A, g = -lambda A^T W b, W = w I per task: rows scaled by sqrt(w), rhs by lambda sqrt(w).
+     * 0.0 = not set = 1.0 (qppvm_desc).  Postural: A = [I 0] on all n_v rows, or without the six base rows (A.6). */
+    const double lam = d->lambda_solver != 0.0 ? d->lambda_solver : 1.0;
+    const double sw0 = sqrt(d->task_weight[0] != 0.0 ? d->task_weight[0] : 1.0);
+    const double sw1 = sqrt(d->task_weight[1] != 0.0 ? d->task_weight[1] : 1.0);
+    const double sw2 = sqrt(d->task_weight[2] != 0.0 ? d->task_weight[2] : 1.0);
     const double* Jw = rec + L->off_jwaist;
     if (level == 0) {
         q->m = 6;
         memset(q->A, 0, sizeof(double) * q->m * n);
         for (int r = 0; r < 6; ++r) {
-            for (int j = 0; j < nv; ++j) q->A[r * n + j] = Jw[r * nv + j];
-            q->b[r] = rec[L->off_rhs + r] - rec[L->off_jdqd + r];
+            for (int j = 0; j < nv; ++j) q->A[r * n + j] = sw0 * Jw[r * nv + j];
+            q->b[r] = sw0 * lam * (rec[L->off_rhs + r] - rec[L->off_jdqd + r]);
         }
     } else {
         q->m = nv + 6 * c;
         memset(q->A, 0, sizeof(double) * q->m * n);
         for (int i = 0; i < nv; ++i) {                      /* Postural: A = [I 0] */
-            q->A[i * n + i] = 1.0;
-            q->b[i] = rec[L->off_rhs + 6 * (1 + c) + i];
+            const double s = (d->postural_actuated_only && i < 6) ? 0.0 : sw1;
+            q->A[i * n + i] = s;
+            q->b[i] = s * lam * rec[L->off_rhs + 6 * (1 + c) + i];
         }
         for (int ci = 0; ci < c; ++ci)                      /* contact-link Cartesian tasks */
             for (int r = 0; r < 6; ++r) {
                 int row = nv + 6 * ci + r;
                 const double* J = rec + L->off_jc + (ci * 6 + r) * nv;
-                for (int j = 0; j < nv; ++j) q->A[row * n + j] = J[j];
-                q->b[row] = rec[L->off_rhs + 6 * (1 + ci) + r] - rec[L->off_jdqd + 6 * (1 + ci) + r];
+                for (int j = 0; j < nv; ++j) q->A[row * n + j] = sw2 * J[j];
+                q->b[row] = sw2 * lam * (rec[L->off_rhs + 6 * (1 + ci) + r] - rec[L->off_jdqd + 6 * (1 + ci) + r]);
             }
     }
     /* global constraints, in stack order */

@@ -21,7 +21,8 @@ LIB_PATH = os.environ.get("QPPVM_B200_LIB") or os.path.join(_HERE, "libqppvm_b20
 class CDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_a", C.c_int32), ("n_contacts", C.c_int32), ("flags", C.c_int32),
                 ("eps_regularisation", C.c_double), ("n_reg_steps", C.c_int32), ("max_iter", C.c_int32),
-                ("device", C.c_int32), ("reserved", C.c_int32)]
+                ("device", C.c_int32), ("postural_actuated_only", C.c_int32), ("lambda_solver", C.c_double),
+                ("task_weight", C.c_double * 3)]
 
 
 class CLayout(C.Structure):
@@ -101,7 +102,8 @@ def load_library():
 
 def cdesc(desc: Desc) -> CDesc:
     return CDesc(desc.kind, desc.n_a, desc.n_contacts, desc.flags, desc.eps_regularisation,
-                 desc.n_reg_steps, desc.max_iter, desc.device, 0)
+                 desc.n_reg_steps, desc.max_iter, desc.device, desc.postural_actuated_only, desc.lambda_solver,
+                 (C.c_double * 3)(*desc.task_weight))
 
 
 def c_layout(desc: Desc) -> dict:

@@ -63,6 +63,10 @@ struct Params {
     int max_iter;
     int rowwise;        // test switch (QPPVM_ROWWISE_EQUALITIES=1 at create): the prepare kernel flags every problem for
                         // the row-by-row equality path of the solve kernel, the one dependent rows fall back to
+    // upstream-uncertain semantics made explicit (qppvm_desc), ForceAcc kind:
+    double lam;         // lambda_solver: g = -lambda A^T W b
+    double sw[3];       // square roots of the task weights: waist, postural, contact Cartesian (W = w I per task)
+    int post_act_only;  // Postural without the six floating-base rows
 };
 
 // Latency mode (one QP per control tick, ref:src/QPPVMPlugin.cpp:308-329): the three kernels stay RESIDENT, one CTA
@@ -365,21 +369,25 @@ struct ForceAcc {
     // Dense task rows of a level into Ad (row-major, ld = NB+1, last column = b); diagonal task
     // weights / targets into dg, db (postural rows are unit rows -> kept as a diagonal).
     // Level 0: waist Cartesian (ForceAcc.cpp:118-122).  Level 1: postural + contact Cartesian (:131).
+    // The cost of a level is sum_k w_k/2 ||A_k x - lambda b_k||^2 (H = A^T W A, g = -lambda A^T W b: SURVEY App. A.2):
+    // rows are stored scaled by sqrt(w_k), right-hand sides by lambda sqrt(w_k).
     template <int TEAM>
-    __device__ static int load_tasks(const double* rec, const double* g, int level, double* Ad, double* dg, double* db, int tid)
+    __device__ static int load_tasks(const double* rec, const double* g, int level, double* Ad, double* dg, double* db, int tid,
+                                     const Params& prm)
     {
         constexpr int LDA = NB + 1;
         const int md = level == 0 ? 6 : 6 * NC;
+        const double sw = level == 0 ? prm.sw[0] : prm.sw[2];
         const double* Jr = level == 0 ? g + OFF_JW : g + OFF_JC;
-        for (int e = tid; e < md * NV; e += TEAM) { const int r = e / NV, j = e - r * NV; Ad[r * LDA + j] = Jr[e]; }
+        for (int e = tid; e < md * NV; e += TEAM) { const int r = e / NV, j = e - r * NV; Ad[r * LDA + j] = sw * Jr[e]; }
         for (int r = tid; r < md; r += TEAM) {
             const int t = level == 0 ? r : 6 + r;            // task-row index into rhs / Jdqd
-            Ad[r * LDA + NB] = rec[OFF_RHS - SB + t] - rec[OFF_JDQD - SB + t];
+            Ad[r * LDA + NB] = sw * prm.lam * (rec[OFF_RHS - SB + t] - rec[OFF_JDQD - SB + t]);
         }
         for (int j = tid; j < N; j += TEAM) {
-            const bool post = level == 1 && j < NV;
-            dg[j] = post ? 1.0 : 0.0;
-            db[j] = post ? rec[OFF_RHS - SB + 6 * (1 + NC) + j] : 0.0;
+            const bool post = level == 1 && j < NV && !(prm.post_act_only && j < 6);
+            dg[j] = post ? prm.sw[1] * prm.sw[1] : 0.0;
+            db[j] = post ? prm.lam * rec[OFF_RHS - SB + 6 * (1 + NC) + j] : 0.0;
         }
         return md;
     }
@@ -588,19 +596,19 @@ struct ForceAcc {
     }
     // dense task rows of a level (coefficient, right-hand side) and the diagonal (postural) part
     __device__ static __forceinline__ int task_rows(int level) { return level == 0 ? MD0 : MD1; }
-    __device__ static __forceinline__ double task_coef(const double* g, int level, int r, int j)
+    __device__ static __forceinline__ double task_coef(const double* g, int level, int r, int j, const Params& prm)
     {
-        return j < NV ? g[(level == 0 ? OFF_JW : OFF_JC) + r * NV + j] : 0.0;
+        return j < NV ? (level == 0 ? prm.sw[0] : prm.sw[2]) * g[(level == 0 ? OFF_JW : OFF_JC) + r * NV + j] : 0.0;
     }
-    __device__ static __forceinline__ double task_rhs(const double* g, int level, int r)
+    __device__ static __forceinline__ double task_rhs(const double* g, int level, int r, const Params& prm)
     {
         const int t = level == 0 ? r : 6 + r;
-        return g[OFF_RHS + t] - g[OFF_JDQD + t];
+        return (level == 0 ? prm.sw[0] : prm.sw[2]) * prm.lam * (g[OFF_RHS + t] - g[OFF_JDQD + t]);
     }
-    __device__ static __forceinline__ void task_diag(const double* g, int level, int j, double& dgv, double& dbv)
+    __device__ static __forceinline__ void task_diag(const double* g, int level, int j, double& dgv, double& dbv, const Params& prm)
     {
-        const bool post = level == 1 && j < NV;
-        dgv = post ? 1.0 : 0.0; dbv = post ? g[OFF_RHS + 6 * (1 + NC) + j] : 0.0;
+        const bool post = level == 1 && j < NV && !(prm.post_act_only && j < 6);
+        dgv = post ? prm.sw[1] * prm.sw[1] : 0.0; dbv = post ? prm.lam * g[OFF_RHS + 6 * (1 + NC) + j] : 0.0;
     }
 
     // row id and bounds of a dense slot (q >= NI_CHEAP)
@@ -750,7 +758,8 @@ struct Torque {
     }
 
     template <int TEAM>
-    __device__ static int load_tasks(const double* rec, const double* ext, int level, double* Ad, double* dg, double* db, int tid)
+    __device__ static int load_tasks(const double* rec, const double* ext, int level, double* Ad, double* dg, double* db, int tid,
+                                     const Params&)
     {
         constexpr int LDA = NB + 1;
         const double* Minv = ext;
@@ -863,7 +872,8 @@ struct Slab {
     static constexpr int O_CT = O_TV + P::NTV;        // per force-only slot: three coefficients, lower, upper bound
     static constexpr int O_SMALL = O_CT + P::NCT;     // d1 rr lam (KP each) | eopt 8 | red 16
     static constexpr int O_MBAR = O_SMALL + 6 * KP + 8 + 16;   // d1 rr lam rdi gc gs | 2 mbarriers: record staging, workspace copies
-    static constexpr int O_STATE = O_MBAR + 2;        // ints: k, n_act_ineq, iters, ws phase | act_row[KP] | act_sgn[KP]
+    static constexpr int O_PRM = O_MBAR + 2;          // the kernel's Params (for the policy functions called inside the solver)
+    static constexpr int O_STATE = O_PRM + (sizeof(Params) + 7) / 8;   // ints: k, n_act_ineq, iters, ws phase | act_row[KP] | act_sgn[KP]
     static constexpr int O_CSTATE = O_STATE + 2 + KP;     // bytes
     static constexpr int O_EXT = O_CSTATE + ((P::NROWS + 15) & ~15) / 8;   // policy scratch
     static constexpr int DOUBLES = O_EXT + P::EXTRA;
@@ -1065,6 +1075,7 @@ struct Solver {
     QP_SM(RI, S::O_RI) QP_SM(ct, S::O_CT)
     __device__ static __forceinline__ constexpr int tri(int c) { return c * (c + 1) / 2; }   // start of packed column c
 #undef QP_SM
+    __device__ static __forceinline__ Params* prm_() { return reinterpret_cast<Params*>(reinterpret_cast<double*>(g_smem) + S::O_PRM); }
     __device__ static __forceinline__ uint64_t* mbar_() { return reinterpret_cast<uint64_t*>(g_smem) + S::O_MBAR; }
     __device__ static __forceinline__ uint64_t* mbar_ws_() { return reinterpret_cast<uint64_t*>(g_smem) + S::O_MBAR + 1; }
     __device__ static __forceinline__ int* state_() { return reinterpret_cast<int*>(reinterpret_cast<double*>(g_smem) + S::O_STATE); }
@@ -1548,7 +1559,7 @@ struct Solver {
     __device__ static __forceinline__ int load_and_factor(int level, double eps)
     {
         QP_BIND
-        const int md = P::template load_tasks<TEAM>(rec, ext, level, Ad, dg, db, tid);
+        const int md = P::template load_tasks<TEAM>(rec, ext, level, Ad, dg, db, tid, *prm_());
         tm::sync();
         // One instantiation serves both levels when level 1 is at most twice as tall (level 0 is padded with zero
         // rows): the kernel is instruction-fetch sensitive, a second copy of the unrolled inversion costs more
@@ -1834,7 +1845,7 @@ struct Solver {
         }
         // task part (reload the dense task rows over the dead Q1 region); (A x)_r -> w2, b_r -> av
         tm::sync();
-        P::template load_tasks<TEAM>(rec, ext, level, Ad, dg, db, tid);
+        P::template load_tasks<TEAM>(rec, ext, level, Ad, dg, db, tid, *prm_());
         tm::sync();
         for (int r = tid; r < md; r += TEAM) {
             double s0 = 0.0, s1 = 0.0;
@@ -1902,7 +1913,7 @@ qp_solve_kernel(const double* __restrict__ recs, unsigned char* __restrict__ out
     constexpr int OUT_BYTES = 8 * (N + P::NA) + 32;
     constexpr int DIAG = N + 2 * P::NROWS + QPPVM_M0;
     __shared__ unsigned long long s_idx;
-    if (tid == 0) { mbar_init(SV::mbar_(), 1); mbar_init(SV::mbar_ws_(), 1); SV::state_()[3] = 0; }   // state[3]: phase of the workspace copies
+    if (tid == 0) { mbar_init(SV::mbar_(), 1); mbar_init(SV::mbar_ws_(), 1); SV::state_()[3] = 0; *SV::prm_() = prm; }   // state[3]: phase of the workspace copies
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     uint32_t phase = 0;
@@ -2095,7 +2106,7 @@ qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long 
         if (live) {
             const double* gr = recs + idx * (size_t)P::REC;
             // (policy functions address the staged tail as rec[OFF - SB]: hand them the global record shifted by SB)
-            const int md = P::template load_tasks<F::GS>(gr + P::SB, gr, level, Ad, dg, db, lane);
+            const int md = P::template load_tasks<F::GS>(gr + P::SB, gr, level, Ad, dg, db, lane, prm);
             for (int e = md * F::LDA + lane; e < F::MD * F::LDA; e += F::GS) Ad[e] = 0.0;   // pad to the common height
         }
         __syncthreads();
@@ -2361,22 +2372,22 @@ qp_certify_kernel(const double* __restrict__ recs, unsigned char* __restrict__ o
             int j = 0;
 #pragma unroll 1
             for (; j + 1 < P::NB; j += 2) {
-                s0 = fma(P::task_coef(g, level, r, j), x[j], s0);
-                s1 = fma(P::task_coef(g, level, r, j + 1), x[j + 1], s1);
+                s0 = fma(P::task_coef(g, level, r, j, prm), x[j], s0);
+                s1 = fma(P::task_coef(g, level, r, j + 1, prm), x[j + 1], s1);
             }
-            if (j < P::NB) s0 = fma(P::task_coef(g, level, r, j), x[j], s0);
-            ax[level][r] = s0 + s1; bx[level][r] = P::task_rhs(g, level, r);
+            if (j < P::NB) s0 = fma(P::task_coef(g, level, r, j, prm), x[j], s0);
+            ax[level][r] = s0 + s1; bx[level][r] = P::task_rhs(g, level, r, prm);
         }
         __syncthreads();
         // ---- stationarity, a variable per thread: H x + g - sum_c y_c a_c
         double rs = 0.0, gmax = 0.0, hxmax = 0.0, xmax = 0.0;
         for (int j = t; j < N; j += T) {
             double dgv, dbv;
-            P::task_diag(g, level, j, dgv, dbv);
+            P::task_diag(g, level, j, dgv, dbv, prm);
             double hx = (dgv + eps) * x[j], gg = -dgv * dbv - eps * xps[level][j];
             if (j < P::NB)
 #pragma unroll 1
-                for (int r = 0; r < md; ++r) { const double a = P::task_coef(g, level, r, j); hx = fma(a, ax[level][r], hx); gg = fma(-a, bx[level][r], gg); }
+                for (int r = 0; r < md; ++r) { const double a = P::task_coef(g, level, r, j, prm); hx = fma(a, ax[level][r], hx); gg = fma(-a, bx[level][r], gg); }
             double cy = 0.0;
 #pragma unroll 1
             for (int c = 0; c < k; ++c) { const int row = act[level][c]; cy = fma(yrow[level][row], P::row_coef(g, row, j), cy); }

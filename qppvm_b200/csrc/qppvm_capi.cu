@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <new>
@@ -133,6 +134,19 @@ struct DeviceGuard {
             return fail(h, QPPVM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
+// qppvm_desc -> kernel parameters (0.0 in the upstream-semantics fields means "not set": 1.0)
+Params make_params(const qppvm_handle* h)
+{
+    Params p;
+    memset(&p, 0, sizeof(p));
+    p.eps_reg = h->desc.eps_regularisation * QPPVM_QPOASES_EPS_REG;
+    p.n_reg_steps = h->desc.n_reg_steps; p.max_iter = h->desc.max_iter; p.rowwise = h->rowwise;
+    p.lam = h->desc.lambda_solver != 0.0 ? h->desc.lambda_solver : 1.0;
+    for (int k = 0; k < 3; ++k) p.sw[k] = sqrt(h->desc.task_weight[k] != 0.0 ? h->desc.task_weight[k] : 1.0);
+    p.post_act_only = h->desc.postural_actuated_only != 0;
+    return p;
+}
+
 int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t batch,
            cudaStream_t st, int slot, bool dynamic = true, uint32_t* warm = nullptr)
 {
@@ -140,7 +154,7 @@ int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t 
     unsigned long long* counter = dynamic ? h->counters + slot : nullptr;   // null: static round-robin schedule
     const int sms = h->sm_count - h->reserve_sms;
     const long long cap = (long long)sms * h->ctas_per_sm;
-    Params prm{h->desc.eps_regularisation * QPPVM_QPOASES_EPS_REG, h->desc.n_reg_steps, h->desc.max_iter, h->rowwise};
+    const Params prm = make_params(h);
     const bool split = h->shape->factor_kernel != nullptr;
     Tick no_tick;
     memset(&no_tick, 0, sizeof(no_tick));
@@ -230,7 +244,7 @@ int start_servers(qppvm_handle* h)
     Tick tk;
     tk.host = h->tick_host; tk.dev = h->tick_dev; tk.host_rec = h->h_one_rec; tk.dev_rec = h->d_one_rec;
     tk.host_out = reinterpret_cast<double*>(h->h_one_out); tk.seq0 = done; tk.idle_us = h->idle_us;
-    Params prm{h->desc.eps_regularisation * QPPVM_QPOASES_EPS_REG, h->desc.n_reg_steps, h->desc.max_iter, h->rowwise};
+    Params prm = make_params(h);
     const double* rec = h->d_one_rec; unsigned char* out = h->d_one_out; double* dgp = nullptr;
     double* ws = h->ws[HOST_STREAMS + 1]; const double* cws = ws;
     long long b = 1; unsigned long long* counter = nullptr; uint32_t* wm = h->d_one_warm;
@@ -318,6 +332,12 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
     if (qppvm_get_layout(d, &L)) return fail(nullptr, QPPVM_ERR_ARG, "invalid problem description");
     if (d->max_iter < 1 || d->n_reg_steps < 0 || !(d->eps_regularisation >= 0.0))
         return fail(nullptr, QPPVM_ERR_ARG, "invalid solver options");
+    if (!(d->lambda_solver >= 0.0) || !(d->task_weight[0] >= 0.0) || !(d->task_weight[1] >= 0.0) || !(d->task_weight[2] >= 0.0))
+        return fail(nullptr, QPPVM_ERR_ARG, "lambda_solver and the task weights must be positive (0 = default 1.0)");
+    if (d->kind == QPPVM_KIND_TORQUE && (d->postural_actuated_only || (d->lambda_solver != 0.0 && d->lambda_solver != 1.0) ||
+                                         (d->task_weight[0] != 0.0 && d->task_weight[0] != 1.0) || (d->task_weight[1] != 0.0 && d->task_weight[1] != 1.0) ||
+                                         (d->task_weight[2] != 0.0 && d->task_weight[2] != 1.0)))
+        return fail(nullptr, QPPVM_ERR_UNSUPPORTED, "lambda_solver / task weights / postural switch apply to the ForceAcc kind");
     const ShapeEntry* sh = nullptr;
     for (int i = 0; i < N_SHAPES; ++i)
         if (g_shapes[i].kind == d->kind && g_shapes[i].n_a == d->n_a && g_shapes[i].n_c == d->n_contacts && g_shapes[i].flags == d->flags)

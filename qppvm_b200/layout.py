@@ -35,6 +35,9 @@ class Desc:
     n_reg_steps: int = 1                # qpOASES setToMPC(): numRegularisationSteps = 1
     max_iter: int = 132                 # nWSR
     device: int = 0
+    postural_actuated_only: int = 0     # later OpenSoT versions drop the 6 base rows of Postural
+    lambda_solver: float = 1.0          # g = -lambda A^T W b
+    task_weight: tuple = (1.0, 1.0, 1.0)   # W = w I per task: waist, postural, contact Cartesian
 
     @property
     def eps(self) -> float:

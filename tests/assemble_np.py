@@ -21,12 +21,19 @@ def level_matrices(desc: Desc, rec: np.ndarray, level: int, x0=None):
         rhs = rec[L.off_rhs:L.off_rhs + 6 * (1 + c) + nv]
         Z = np.zeros
         wd = (n - nv) // c                       # 3 force components per contact, 6 with full wrenches (ForceAcc.cpp:67)
+        # cost of a level: sum_k w_k/2 ||A_k x - lambda b_k||^2  (H = A^T W A, g = -lambda A^T W b: SURVEY App. A.2)
+        lam = desc.lambda_solver
+        w_waist, w_post, w_cont = (np.sqrt(w) for w in desc.task_weight)
         if level == 0:   # _waist_task (ForceAcc.cpp:118-122)
-            A = np.hstack([Jw, Z((6, wd * c))]); b = rhs[:6] - jdqd[:6]
+            A = w_waist * np.hstack([Jw, Z((6, wd * c))]); b = w_waist * lam * (rhs[:6] - jdqd[:6])
         else:            # _postural_task + feet_cart_aggr (ForceAcc.cpp:131)
-            A = np.vstack([np.hstack([np.eye(nv), Z((nv, wd * c))])] +
-                          [np.hstack([Jc[i], Z((6, wd * c))]) for i in range(c)])
-            b = np.concatenate([rhs[6 * (1 + c):]] + [rhs[6 * (1 + i):6 * (2 + i)] - jdqd[6 * (1 + i):6 * (2 + i)] for i in range(c)])
+            P = np.eye(nv) * w_post
+            if desc.postural_actuated_only:   # later OpenSoT versions: no postural rows for the floating base (A.6)
+                P[:6] = 0.0
+            A = np.vstack([np.hstack([P, Z((nv, wd * c))])] +
+                          [w_cont * np.hstack([Jc[i], Z((6, wd * c))]) for i in range(c)])
+            b = np.concatenate([P @ (lam * rhs[6 * (1 + c):])] +
+                               [w_cont * lam * (rhs[6 * (1 + i):6 * (2 + i)] - jdqd[6 * (1 + i):6 * (2 + i)]) for i in range(c)])
         rows, lo, hi = [], [], []
         # DynamicFeasibility: (M qdd + h - sum J_i^T [f_i; 0])[0:6] = 0
         D = np.hstack([M[:6]] + [-Jc[i][:wd, :6].T for i in range(c)])
@@ -46,7 +53,7 @@ def level_matrices(desc: Desc, rec: np.ndarray, level: int, x0=None):
             T = np.hstack([M[6:]] + [-Jc[i][:wd, 6:].T for i in range(c)])
             tl = rec[L.off_taulim:L.off_taulim + 2 * na]
             rows.append(T); lo.append(tl[:na] - h[6:]); hi.append(tl[na:] - h[6:])
-        if level == 1:
+        if level == 1:   # optimality rows: the level-0 task rows themselves (a task weight does not change the set they define)
             A0 = np.hstack([Jw, Z((6, wd * c))])
             rows.append(A0); lo.append(A0 @ x0); hi.append(A0 @ x0)
         eps = desc.eps_regularisation * QPOASES_EPS_REG

@@ -66,6 +66,28 @@ def test_parity_literal_forceacc_shape(torch_mod, oracle_mod):
     assert r["mask_equal"] == 1.0 and r["strong_active_equal"] == 1.0 and r["strong_sign_equal"] == 1.0
 
 
+@pytest.mark.parametrize("ci", (1, 2))
+def test_parity_with_upstream_semantics_parameters(torch_mod, oracle_mod, ci):
+    """The details that varied across OpenSoT versions are explicit parameters of qppvm_desc:
+    lambda_solver (g = -lambda A^T W b), one weight per task (W = w I), Postural with or without the six base rows."""
+    import dataclasses
+    from qppvm_b200 import api
+    base = CONFIGS[ci]["desc"]
+    desc = dataclasses.replace(base, lambda_solver=0.7, task_weight=(2.0, 0.5, 3.0), postural_actuated_only=1)
+    L = layout(desc)
+    recs = gen.generate(desc, 384, gen.config_seed(ci) + 5)
+    oo, od = oracle_mod.solve_batch(desc, recs, diag=True)
+    o, odg = oracle_mod.split_out(desc, oo), api.split_diag(L, od)
+    g, gdg = _solve_gpu(torch_mod, desc, recs)
+    r = compare(L, g, o, gdg, odg)
+    assert r["status_equal"] and r["both_ok"] == 384
+    assert r["primal"] <= PRIMAL_TOL and r["tau"] <= PRIMAL_TOL and r["kkt_gpu"] <= KKT_TOL and r["eopt"] <= PRIMAL_TOL
+    assert r["strong_active_equal"] == 1.0 and r["strong_sign_equal"] == 1.0
+    # and they do change the answer
+    gb, _ = _solve_gpu(torch_mod, base, recs, diag=False)
+    assert rel_inf(g["x"], gb["x"]).max() > 1e-3
+
+
 @pytest.mark.parametrize("n_a,c,flags", [(29, 2, 4), (29, 2, 7)])
 def test_parity_full_wrench_variables(torch_mod, oracle_mod, n_a, c, flags):
     """Six variables per contact ("put 6 for full wrench", ref:src/ForceAcc.cpp:67) with the reference's literal wrench
