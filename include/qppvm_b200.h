@@ -184,7 +184,9 @@ int qppvm_tick_stamps(qppvm_handle* h, uint64_t* ns7);
  * and the OpenSoT task right-hand sides.  ForceAcc kind only.
  * State layout (doubles): q n_a | qd n_a | R0 3x3 row-major | p0 3 | base twist (v0, w0) 6 | gains 4
  *                         (lambda, lambda2 factors: waist, postural/contacts) | waist orientation error 3 |
- *                         contact pose errors 6c | mu c | tau-limit scale n_a.                                  */
+ *                         contact pose errors 6c | mu c | tau-limit scale n_a | waist position error 3
+ *                         (errors = reference - current; the references are captured once, ref:src/ForceAcc.cpp:158-164,
+ *                         waist position reference = initial - 0.1 z, :181).                                       */
 typedef struct qppvm_robot {
     int32_t n_a;                    /* actuated joints; bodies = n_a + 1, body 0 = floating base            */
     const int32_t* parent;          /* [n_a + 1] parent body of each body, parent[0] = -1                   */
@@ -211,8 +213,14 @@ int qppvm_solve_states_host_async(qppvm_handle* h, const double* states_host, vo
  * qppvm_solve_batch wrote for the same states): q += dt*qd + dt^2/2*qdd, qd += dt*qdd, floating base likewise
  * (ref:src/ForceAcc.cpp:225-226).  A state whose solve failed is left as it is (ref:src/ForceAcc.cpp:189-193).
  * qppvm_rollout_states: `ticks` control periods of front end -> 2-level solve -> integrate, all on `stream`, nothing
- * crossing PCIe; `out` holds the last tick's solutions.  Task references stay those stored in the states. */
+ * crossing PCIe; `out` holds the last tick's solutions.  The task references are those the states were created with: the
+ * stored errors shrink as the robot moves towards them. */
 int qppvm_integrate_states(qppvm_handle* h, double* states_dev, const void* out_dev, double dt, int64_t batch, void* stream);
+/* The same plus the tick's records: the task errors stored in the states follow the motion (e <- e - dt v_link -
+ * dt^2/2 a_link per task link), which is what keeps multi-tick rollouts closed-loop in the task references;
+ * qppvm_rollout_states integrates this way. */
+int qppvm_integrate_states_tracking(qppvm_handle* h, double* states_dev, const void* out_dev, const double* records_dev,
+                                    double dt, int64_t batch, void* stream);
 int qppvm_rollout_states(qppvm_handle* h, double* states_dev, void* out_dev, int ticks, double dt, int64_t batch, void* stream);
 
 /* ---- the batch sharded over the GPUs of one box, single process ---------------------------------------

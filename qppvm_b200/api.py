@@ -41,7 +41,7 @@ EXPORTS = ("qppvm_get_layout", "qppvm_create", "qppvm_destroy", "qppvm_last_erro
            "qppvm_fp64_peak", "qppvm_supported_shapes", "qppvm_state_doubles", "qppvm_set_robot",
            "qppvm_records_from_states", "qppvm_solve_states_host", "qppvm_solve_batch_host_async", "qppvm_host_sync",
            "qppvm_solve_states_host_async", "qppvm_integrate_states", "qppvm_rollout_states", "qppvm_solve_batch_warm", "qppvm_reset_warm", "qppvm_tick_stamps",
-           "qppvm_reserve_sms", "qppvm_multi_create", "qppvm_multi_destroy", "qppvm_multi_last_error", "qppvm_multi_devices",
+           "qppvm_reserve_sms", "qppvm_integrate_states_tracking", "qppvm_multi_create", "qppvm_multi_destroy", "qppvm_multi_last_error", "qppvm_multi_devices",
            "qppvm_multi_set_robot", "qppvm_multi_solve_batch", "qppvm_multi_solve_batch_host",
            "qppvm_multi_solve_states_host", "qppvm_multi_kernel_launches", "qppvm_multi_nccl_calls")
 
@@ -87,6 +87,7 @@ def load_library():
         lib.qppvm_host_sync.argtypes = [P]
         lib.qppvm_solve_states_host_async.argtypes = [P, P, P, C.c_int64]
         lib.qppvm_integrate_states.argtypes = [P, P, P, C.c_double, C.c_int64, P]
+        lib.qppvm_integrate_states_tracking.argtypes = [P, P, P, P, C.c_double, C.c_int64, P]
         lib.qppvm_rollout_states.argtypes = [P, P, P, C.c_int, C.c_double, C.c_int64, P]
         lib.qppvm_kernel_launches.argtypes = [P]
         lib.qppvm_kernel_launches.restype = C.c_int64
@@ -254,13 +255,19 @@ class Solver:
         self._check(self._lib.qppvm_records_from_states(self._h, states.data_ptr(), records.data_ptr(), B, st.cuda_stream))
         return records
 
-    def integrate_states(self, states, out, dt: float, stream=None):
-        """In place: advance `states` (cuda float64) by dt with the accelerations in `out` (solve_batch's block)."""
+    def integrate_states(self, states, out, dt: float, stream=None, records=None):
+        """In place: advance `states` (cuda float64) by dt with the accelerations in `out` (solve_batch's block); with the
+        tick's `records` the stored task errors follow the motion (closed loop in the references)."""
         import torch
         assert states.is_cuda and states.dtype == torch.float64 and states.is_contiguous() and out.is_contiguous()
         assert states.shape[1] == self.state_doubles and out.shape == (states.shape[0], self.layout.out_doubles)
         st = torch.cuda.current_stream(states.device) if stream is None else stream
-        self._check(self._lib.qppvm_integrate_states(self._h, states.data_ptr(), out.data_ptr(), dt, states.shape[0], st.cuda_stream))
+        if records is None:
+            self._check(self._lib.qppvm_integrate_states(self._h, states.data_ptr(), out.data_ptr(), dt, states.shape[0], st.cuda_stream))
+        else:
+            assert records.is_cuda and records.is_contiguous() and records.shape == (states.shape[0], self.layout.rec_doubles)
+            self._check(self._lib.qppvm_integrate_states_tracking(self._h, states.data_ptr(), out.data_ptr(), records.data_ptr(),
+                                                                  dt, states.shape[0], st.cuda_stream))
         return states
 
     def rollout_states(self, states, ticks: int, dt: float, out=None, stream=None):

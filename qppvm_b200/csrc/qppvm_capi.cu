@@ -583,6 +583,7 @@ static int state_layout(const qppvm_desc* d, RbdShape* sh)
     s.off_rhs = L.off_rhs; s.off_taulim = L.off_taulim; s.off_cone = L.off_cone; s.off_fbox = L.off_fbox; s.rec_doubles = L.rec_doubles;
     s.s_q = o; o += na; s.s_qd = o; o += na; s.s_R0 = o; o += 9; s.s_p0 = o; o += 3; s.s_tw = o; o += 6; s.s_gains = o; o += 4;
     s.s_ori = o; o += 3; s.s_foot = o; o += 6 * c; s.s_mu = o; o += c; s.s_tscale = o; o += na;
+    s.s_wpos = o; o += 3;
     s.state_doubles = o;
     if (sh) *sh = s;
     return o;
@@ -657,24 +658,30 @@ int qppvm_records_from_states(qppvm_handle* h, const double* states, double* rec
     return launch_rbd(h, states, recs, batch, (cudaStream_t)stream);
 }
 
-static int launch_integrate(qppvm_handle* h, double* states, const void* out, double dt, int64_t batch, cudaStream_t st)
+static int launch_integrate(qppvm_handle* h, double* states, const void* out, const double* recs, double dt, int64_t batch, cudaStream_t st)
 {
     if (batch <= 0) return QPPVM_OK;
     const int threads = 128, grid = (int)((batch + threads - 1) / threads);
-    integrate_states_kernel<<<grid, threads, 0, st>>>(h->rsh, states, (const double*)out, h->L.out_bytes / 8,
+    integrate_states_kernel<<<grid, threads, 0, st>>>(h->rsh, states, (const double*)out, recs, h->L.out_bytes / 8,
                                                       h->L.n_x + h->L.n_a, dt, (long long)batch);
     CU(h, cudaGetLastError());
     h->launches += 1;
     return QPPVM_OK;
 }
 
-int qppvm_integrate_states(qppvm_handle* h, double* states, const void* out, double dt, int64_t batch, void* stream)
+int qppvm_integrate_states_tracking(qppvm_handle* h, double* states, const void* out, const double* recs, double dt,
+                                    int64_t batch, void* stream)
 {
     if (!h) return QPPVM_ERR_ARG;
     if (!h->has_robot) return fail(h, QPPVM_ERR_ARG, "qppvm_set_robot has not been called");
     if (batch < 0 || (batch > 0 && (!states || !out)) || !(dt > 0.0)) return fail(h, QPPVM_ERR_ARG, "bad arguments");
     ENTER(h);
-    return launch_integrate(h, states, out, dt, batch, (cudaStream_t)stream);
+    return launch_integrate(h, states, out, recs, dt, batch, (cudaStream_t)stream);
+}
+
+int qppvm_integrate_states(qppvm_handle* h, double* states, const void* out, double dt, int64_t batch, void* stream)
+{
+    return qppvm_integrate_states_tracking(h, states, out, nullptr, dt, batch, stream);
 }
 
 int qppvm_rollout_states(qppvm_handle* h, double* states, void* out, int ticks, double dt, int64_t batch, void* stream)
@@ -716,7 +723,7 @@ int qppvm_rollout_states(qppvm_handle* h, double* states, void* out, int ticks, 
             if (rc) return rc;
             rc = launch(h, rec, o, nullptr, n, ws, w);
             if (rc) return rc;
-            rc = launch_integrate(h, s, o, dt, n, ws);
+            rc = launch_integrate(h, s, o, rec, dt, n, ws);
             if (rc) return rc;
         }
     }

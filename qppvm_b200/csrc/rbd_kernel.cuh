@@ -44,7 +44,7 @@ struct RobotTables {               // device pointers
 struct RbdShape {                  // record / state offsets (doubles), filled on the host from qppvm_layout
     int n_a, n_v, n_c, flags;
     int off_jwaist, off_jc, off_M, off_h, off_jdqd, off_rhs, off_taulim, off_cone, off_fbox, rec_doubles;
-    int s_q, s_qd, s_R0, s_p0, s_tw, s_gains, s_ori, s_foot, s_mu, s_tscale, state_doubles;
+    int s_q, s_qd, s_R0, s_p0, s_tw, s_gains, s_ori, s_foot, s_mu, s_tscale, s_wpos, state_doubles;
 };
 
 __device__ __forceinline__ void cross3(const double* a, const double* b, double* o)
@@ -258,7 +258,7 @@ rbd_records_kernel(RobotTables rob, RbdShape sh, const double* __restrict__ stat
         for (int r = 0; r < 6; ++r) {
             rec[sh.off_jdqd + 6 * t + r] = r < 3 ? ba[body][r] : bal[body][r - 3];
             double e;
-            if (t == 0) e = r < 3 ? (r == 2 ? -0.1 : 0.0) : st[sh.s_ori + r - 3];                 // ref:src/ForceAcc.cpp:181
+            if (t == 0) e = r < 3 ? st[sh.s_wpos + r] : st[sh.s_ori + r - 3];   // reference = initial - 0.1 z (ref:src/ForceAcc.cpp:181)
             else e = st[sh.s_foot + 6 * (t - 1) + r];
             rec[sh.off_rhs + 6 * t + r] = (t == 0 ? lam_w : lam_p) * e - (t == 0 ? lam2_w : lam2_p) * jvel[r];
         }
@@ -298,8 +298,8 @@ rbd_records_kernel(RobotTables rob, RbdShape sh, const double* __restrict__ stat
 // rotation vector dt*w + dt^2/2*alpha).  A state whose solve failed is left untouched (nothing is commanded,
 // ref:src/ForceAcc.cpp:189-193).  One thread per state; 2 x state bytes + n_v doubles of traffic.
 __global__ void __launch_bounds__(128)
-integrate_states_kernel(RbdShape sh, double* __restrict__ states, const double* __restrict__ out, int out_doubles,
-                        int trailer_off, double dt, long long batch)
+integrate_states_kernel(RbdShape sh, double* __restrict__ states, const double* __restrict__ out,
+                        const double* __restrict__ recs, int out_doubles, int trailer_off, double dt, long long batch)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= batch) return;
@@ -307,6 +307,28 @@ integrate_states_kernel(RbdShape sh, double* __restrict__ states, const double* 
     const double* x = out + idx * (size_t)out_doubles;
     if (reinterpret_cast<const int*>(x + trailer_off)[0] != 0) return;
     const double h2 = 0.5 * dt * dt;
+    if (recs) {
+        // The task references were captured once (ref:src/ForceAcc.cpp:158-164: resetReference at on_start, :181 waist
+        // reference = initial - 0.1 z): the errors the states carry shrink as the links move.  Link velocity from the
+        // record's right-hand side (rhs = lambda e - lambda2 J v), link acceleration J qdd + Jdot qdot.
+        const double* rec = recs + idx * (size_t)sh.rec_doubles;
+        const double* gains = st + sh.s_gains;
+        const int nv = sh.n_v;
+#pragma unroll 1
+        for (int t = 0; t <= sh.n_c; ++t) {
+            const double lam = 100.0 * gains[t == 0 ? 0 : 2], lam2 = 20.0 * gains[t == 0 ? 1 : 3];
+            const double* J = rec + (t == 0 ? sh.off_jwaist : sh.off_jc + (t - 1) * 6 * nv);
+#pragma unroll 1
+            for (int r = 0; r < 6; ++r) {
+                double* e = t == 0 ? (r < 3 ? st + sh.s_wpos + r : st + sh.s_ori + r - 3) : st + sh.s_foot + 6 * (t - 1) + r;
+                double al = rec[sh.off_jdqd + 6 * t + r];
+#pragma unroll 4
+                for (int j = 0; j < nv; ++j) al = fma(J[r * nv + j], x[j], al);
+                const double vl = (lam * *e - rec[sh.off_rhs + 6 * t + r]) / lam2;
+                *e = *e - dt * vl - h2 * al;
+            }
+        }
+    }
     double* tw = st + sh.s_tw;
     double th[3];
 #pragma unroll

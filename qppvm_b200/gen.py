@@ -222,16 +222,17 @@ def unpack_lower(Mp: np.ndarray, n: int) -> np.ndarray:
 
 def state_doubles(desc: Desc) -> int:
     """Compact synthetic state of one problem (what the rigid-body front end consumes):
-    q | qd | R0 (3x3 row-major) | p0 | base twist (v0, w0) | gains 4 | ori_err 3 | foot_err 6c | mu c | tau_scale n_a."""
+    q | qd | R0 (3x3 row-major) | p0 | base twist (v0, w0) | gains 4 | ori_err 3 | foot_err 6c | mu c | tau_scale n_a |
+    waist position error 3."""
     na, c = desc.n_a, desc.n_contacts
-    return 2 * na + 9 + 3 + 6 + 4 + 3 + 6 * c + c + na
+    return 2 * na + 9 + 3 + 6 + 4 + 3 + 6 * c + c + na + 3
 
 
 def state_offsets(desc: Desc) -> dict:
     na, c = desc.n_a, desc.n_contacts
     o, out = 0, {}
     for name, n in (("q", na), ("qd", na), ("R0", 9), ("p0", 3), ("tw", 6), ("gains", 4), ("ori_err", 3),
-                    ("foot_err", 6 * c), ("mu", c), ("tau_scale", na)):
+                    ("foot_err", 6 * c), ("mu", c), ("tau_scale", na), ("waist_pos_err", 3)):
         out[name] = (o, o + n)
         o += n
     return out
@@ -267,7 +268,11 @@ def generate_states(desc: Desc, count: int, seed: int = BASE_SEED, start: int = 
     assert k <= DRAWS
     if desc.kind == KIND_TORQUE:                              # fixed base
         R0 = np.tile(np.eye(3), (count, 1, 1)); p0 = np.zeros((count, 3)); tw = np.zeros((count, 6))
-    return np.concatenate([q, qd, R0.reshape(count, 9), p0, tw, gains, ori_err, foot_err, mu, tau_scale], axis=1)
+    # waist position error = reference - current: the reference is captured once as "initial - 0.1 z"
+    # (ref:src/ForceAcc.cpp:158-164,181), so at the first tick the error is (0, 0, -0.1); it then shrinks as the robot
+    # moves (integrate_states with the tick's records)
+    wpos = np.tile(np.array([0.0, 0.0, -0.1]), (count, 1))
+    return np.concatenate([q, qd, R0.reshape(count, 9), p0, tw, gains, ori_err, foot_err, mu, tau_scale, wpos], axis=1)
 
 
 def generate(desc: Desc, count: int, seed: int = BASE_SEED, start: int = 0,
@@ -290,8 +295,8 @@ def records_from_states(desc: Desc, states: np.ndarray) -> np.ndarray:
     n = states.shape[0]
     so = state_offsets(desc)
     g = lambda name: states[:, so[name][0]:so[name][1]]
-    q, qd, p0, tw, gains, ori_err, foot_err, mu, tau_scale = (g(k) for k in
-        ("q", "qd", "p0", "tw", "gains", "ori_err", "foot_err", "mu", "tau_scale"))
+    q, qd, p0, tw, gains, ori_err, foot_err, mu, tau_scale, wpos = (g(k) for k in
+        ("q", "qd", "p0", "tw", "gains", "ori_err", "foot_err", "mu", "tau_scale", "waist_pos_err"))
     R0 = g("R0").reshape(n, 3, 3)
 
     rec = np.zeros((n, L.rec_doubles))
@@ -307,7 +312,7 @@ def records_from_states(desc: Desc, states: np.ndarray) -> np.ndarray:
         rec[:, L.off_h:L.off_h + nv] = dyn["h"]
         rec[:, L.off_jdqd:L.off_jdqd + 6] = dyn["links"][0]["Jdqd"]
         # waist: position reference = current - 0.1 z (ref:src/ForceAcc.cpp:181), velocity ref 0
-        e_w = np.concatenate([np.tile([0.0, 0.0, -0.1], (n, 1)), ori_err], axis=1)
+        e_w = np.concatenate([wpos, ori_err], axis=1)
         rec[:, L.off_rhs:L.off_rhs + 6] = lam_w * e_w - lam2_w * np.einsum("bij,bj->bi", Jw, v)
         for ci, b in enumerate(contact_bodies):
             Jc = dyn["links"][b]["J"]
@@ -361,10 +366,13 @@ def config_seed(config_index: int) -> int:
     return BASE_SEED + 1000 * config_index
 
 
-def integrate_states(desc: Desc, states: np.ndarray, out: np.ndarray, dt: float) -> np.ndarray:
+def integrate_states(desc: Desc, states: np.ndarray, out: np.ndarray, dt: float, recs: np.ndarray | None = None) -> np.ndarray:
     """Numpy mirror of integrate_states_kernel (the integration ref:src/ForceAcc.cpp:225-226
     carries): one control period with the solved acceleration; failed solves leave their state untouched.
-    `out` is the solver's output block viewed as float64 (B, out_doubles)."""
+    `out` is the solver's output block viewed as float64 (B, out_doubles).
+    With the tick's records the stored task errors (waist position / orientation, contact poses) follow the motion:
+    the references were captured once (ref:src/ForceAcc.cpp:158-164,181), so e <- e - dt v_link - dt^2/2 a_link with
+    v_link = J v recovered from the record's right-hand side (rhs = lambda e - lambda2 J v) and a_link = J qdd + Jdot qdot."""
     from .layout import layout
     L, o = layout(desc), state_offsets(desc)
     nv, na = L.n_v, desc.n_a
@@ -394,5 +402,26 @@ def integrate_states(desc: Desc, states: np.ndarray, out: np.ndarray, dt: float)
     new[:, o["R0"][0]:o["R0"][1]] = Rn.reshape(-1, 9)
     new[:, o["q"][0]:o["q"][1]] = q + dt * qd + h2 * x[:, 6:nv]
     new[:, o["qd"][0]:o["qd"][1]] = qd + dt * x[:, 6:nv]
+    if recs is not None:
+        c = L.n_c
+        gains = states[:, o["gains"][0]:o["gains"][1]]
+        for t in range(1 + c):
+            lam = 100.0 * gains[:, 0 if t == 0 else 2][:, None]
+            lam2 = 20.0 * gains[:, 1 if t == 0 else 3][:, None]
+            if t == 0:
+                e = np.concatenate([states[:, o["waist_pos_err"][0]:o["waist_pos_err"][1]], states[:, o["ori_err"][0]:o["ori_err"][1]]], axis=1)
+                J = recs[:, L.off_jwaist:L.off_jwaist + 6 * nv].reshape(-1, 6, nv)
+            else:
+                e = states[:, o["foot_err"][0] + 6 * (t - 1):o["foot_err"][0] + 6 * t]
+                J = recs[:, L.off_jc + (t - 1) * 6 * nv:L.off_jc + t * 6 * nv].reshape(-1, 6, nv)
+            rhs = recs[:, L.off_rhs + 6 * t:L.off_rhs + 6 * t + 6]
+            vl = (lam * e - rhs) / lam2
+            al = np.einsum("bij,bj->bi", J, x) + recs[:, L.off_jdqd + 6 * t:L.off_jdqd + 6 * t + 6]
+            en = e - dt * vl - h2 * al
+            if t == 0:
+                new[:, o["waist_pos_err"][0]:o["waist_pos_err"][1]] = en[:, :3]
+                new[:, o["ori_err"][0]:o["ori_err"][1]] = en[:, 3:]
+            else:
+                new[:, o["foot_err"][0] + 6 * (t - 1):o["foot_err"][0] + 6 * t] = en
     st[ok] = new[ok]
     return st

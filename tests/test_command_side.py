@@ -66,18 +66,31 @@ def test_failed_solves_leave_their_state_untouched():
     assert (np.abs(new[~bad] - st[~bad]).max(axis=1) > 0).all()
 
 
-def test_closed_loop_with_oracle_stays_bounded(oracle_mod):
-    """Closed loop on the CPU statement over 150 periods: the ticks keep solving, the base rotation stays a
-    rotation and nothing blows up (the task references in the states are constant, so this is a smoke run of the
-    loop, not a tracking claim)."""
+def test_closed_loop_with_oracle_tracks_the_waist_reference(oracle_mod):
+    """Closed loop on the CPU statement over 150 periods.  The references are captured once (ref:src/ForceAcc.cpp:158-164,
+    waist position reference = initial - 0.1 z, :181), so the stored waist error must SHRINK as the waist moves down --
+    with a constant error the waist would be driven down at lambda e / lambda2 = 0.5 m/s for ever."""
     desc = CONFIGS[1]["desc"]
     o = gen.state_offsets(desc)
     st = gen.generate_states(desc, 24, 11)
+    st[:, o["qd"][0]:o["qd"][1]] *= 0.1                       # start near rest: the test is about the waist task
+    st[:, o["tw"][0]:o["tw"][1]] *= 0.1
+    p_start = st[:, o["p0"][0]:o["p0"][1]].copy()
+    e_start = st[:, o["waist_pos_err"][0]:o["waist_pos_err"][1]].copy()
+    assert np.array_equal(e_start, np.tile([0.0, 0.0, -0.1], (24, 1)))
     for _ in range(150):
-        out, _ = oracle_mod.solve_batch(desc, gen.records_from_states(desc, st))
+        recs = gen.records_from_states(desc, st)
+        out, _ = oracle_mod.solve_batch(desc, recs)
         g = oracle_mod.split_out(desc, out)
         assert (g["status"] == 0).mean() >= 0.9
-        st = gen.integrate_states(desc, st, out.view(np.float64).reshape(len(st), -1), DT)
+        st = gen.integrate_states(desc, st, out.view(np.float64).reshape(len(st), -1), DT, recs=recs)
+    # the stored error is reference - current: what is left of it plus the distance travelled is the initial error
+    moved = st[:, o["p0"][0]:o["p0"][1]] - p_start
+    e_now = st[:, o["waist_pos_err"][0]:o["waist_pos_err"][1]]
+    np.testing.assert_allclose(e_now + moved, e_start, rtol=0, atol=2e-3)
+    ok = oracle_mod.split_out(desc, out)["status"] == 0
+    # critically damped second-order response, omega = 10 sqrt(gain): e(0.15 s) = 0.1 (1 + 1.5) exp(-1.5) = 0.056
+    assert (np.abs(e_now[ok, 2]) < 0.07).all() and (moved[ok, 2] < -0.03).all()
     R = st[:, o["R0"][0]:o["R0"][1]].reshape(-1, 3, 3)
     np.testing.assert_allclose(R @ R.transpose(0, 2, 1), np.tile(np.eye(3), (len(st), 1, 1)), rtol=0, atol=1e-12)
     assert np.isfinite(st).all()
@@ -111,6 +124,15 @@ def test_integrate_kernel_matches_numpy(ci):
     ref = gen.integrate_states(desc, st, out, DT)
     np.testing.assert_allclose(d.cpu().numpy(), ref, rtol=0, atol=1e-14)
     np.testing.assert_array_equal(d.cpu().numpy()[::7], st[::7])
+    # with the tick's records: the stored task errors follow the motion
+    recs = gen.records_from_states(desc, st)
+    d = torch.from_numpy(st).cuda()
+    s.integrate_states(d, torch.from_numpy(out).cuda(), DT, records=torch.from_numpy(recs).cuda())
+    torch.cuda.synchronize()
+    ref = gen.integrate_states(desc, st, out, DT, recs=recs)
+    o = gen.state_offsets(desc)
+    assert np.abs(ref[:, o["waist_pos_err"][0]:o["waist_pos_err"][1]] - st[:, o["waist_pos_err"][0]:o["waist_pos_err"][1]]).max() > 0
+    np.testing.assert_allclose(d.cpu().numpy(), ref, rtol=0, atol=1e-12)
 
 
 @pytest.mark.gpu
@@ -130,7 +152,7 @@ def test_rollout_matches_cpu_closed_loop(oracle_mod):
     for _ in range(T):
         o_out, _ = oracle_mod.solve_batch(desc, gen.records_from_states(desc, st))
         o_out = o_out.view(np.float64).reshape(B, -1)
-        st_prev, st = st, gen.integrate_states(desc, st, o_out, DT)
+        st_prev, st = st, gen.integrate_states(desc, st, o_out, DT, recs=gen.records_from_states(desc, st))
     g, o = api.split_out(L, out.cpu().numpy()), oracle_mod.split_out(desc, o_out)
     assert (g["status"] == 0).all() and np.array_equal(g["status"], o["status"])
     assert rel_inf(g["x"], o["x"]).max() <= 1e-6 and np.array_equal(g["active"], o["active"])
@@ -141,8 +163,9 @@ def test_rollout_matches_cpu_closed_loop(oracle_mod):
         out2 = s.rollout_states(d2, 1, DT)
     d3 = torch.from_numpy(st0).cuda()
     for _ in range(T):
-        out3, _ = s.solve_batch(s.records_from_states(d3))
-        s.integrate_states(d3, out3, DT)
+        r3 = s.records_from_states(d3)
+        out3, _ = s.solve_batch(r3)
+        s.integrate_states(d3, out3, DT, records=r3)
     torch.cuda.synchronize()
     assert torch.equal(d2, d) and torch.equal(out2, out) and torch.equal(d3, d) and torch.equal(out3, out)
 
