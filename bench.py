@@ -127,6 +127,7 @@ def host_threads():
 def cpu_reference(desc, recs, target_s, mode):
     """Times the oracle (restated active-set path, not the qpOASES binary) on a bounded sample."""
     from oracle import oracle
+    oracle.use_native()                                    # -march=native build made on this box (falls back to the portable one)
     threads = host_threads()
     if len(recs) < 2048:                                   # tiny workloads (single-tick configs): tile to a useful sample
         recs = np.tile(recs, ((2048 + len(recs) - 1) // len(recs), 1))
@@ -157,6 +158,7 @@ def run_reference(args, desc, L, cfg_name, batch):
     from qppvm_b200 import gen
     from oracle import oracle
     recs = gen.generate(desc, min(batch, 8192), gen.config_seed(args.config))   # a step samples from these
+    native = oracle.use_native()                           # -march=native build made on this box
     threads = host_threads()
     ncal = min(256, len(recs))
     t0 = time.perf_counter(); oracle.solve_batch(desc, recs[:ncal], mode=oracle.FACTOR_CHOLESKY, threads=threads)
@@ -179,7 +181,8 @@ def run_reference(args, desc, L, cfg_name, batch):
             "config": config_dict(args, cfg_name, desc, L, batch, args.gpus),
             "cpu_baseline": {"value": val, "unit": "solves/s", "cores": threads, "kind": "port",
                              "sample": "%d records/step of the %d-record batch, restated active-set path "
-                                       "(qpOASES semantics, formed H + Cholesky), not the qpOASES binary" % (sample, batch)},
+                                       "(qpOASES semantics, formed H + Cholesky), not the qpOASES binary; %s build"
+                                       % (sample, batch, "-O3 -march=native" if native else "-O3 -march=x86-64-v3")},
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -576,22 +579,35 @@ def main():
                                            "qppvm_solve_one (host in / host out, resident kernels, hot start)"}
         if not args.no_cpu_baseline:                       # the same ticks on one host core (restated active-set path)
             from oracle import oracle
+            oracle.use_native()
             n_cpu = 2000
-            clat = np.empty(n_cpu)
+            clat, hlat = np.empty(n_cpu), np.empty(n_cpu)
             for i in range(n_cpu + 20):
                 t0 = time.perf_counter(); oracle.solve_batch(d4, r4[i:i + 1], mode=oracle.FACTOR_CHOLESKY, threads=1)
                 if i >= 20:
                     clat[i - 20] = time.perf_counter() - t0
+            wcpu = np.zeros(8, dtype=np.uint32)
+            for i in range(n_cpu + 20):                    # the same ticks, hot-started from the previous tick's working sets
+                t0 = time.perf_counter(); oracle.solve_sequence(d4, r4[i:i + 1], wcpu, mode=oracle.FACTOR_CHOLESKY)
+                if i >= 20:
+                    hlat[i - 20] = time.perf_counter() - t0
             line["single_tick"]["cpu_port_p50_us"] = float(np.percentile(clat, 50) * 1e6)
             line["single_tick"]["cpu_port_p99_us"] = float(np.percentile(clat, 99) * 1e6)
+            line["single_tick"]["cpu_port_hot_p50_us"] = float(np.percentile(hlat, 50) * 1e6)
+            line["single_tick"]["cpu_port_hot_p99_us"] = float(np.percentile(hlat, 99) * 1e6)
             line["single_tick"]["cpu_port_ticks"] = n_cpu
-            line["single_tick"]["cpu_port"] = "oracle port, cold start per tick, 1 core, called through ctypes like the GPU path"
+            line["single_tick"]["cpu_port"] = ("oracle port built -O3 -march=native on this box, 1 core, called through ctypes like the GPU "
+                                               "path: cold start per tick, and hot-started from the previous tick (oracle_solve_sequence)")
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
         v, threads, n_done, dt = cpu_reference(desc, host_recs[:65536], 12.0, oracle.FACTOR_CHOLESKY)
+        t0 = time.perf_counter(); oracle.solve_batch(desc, host_recs[:2048], mode=oracle.FACTOR_CHOLESKY, threads=1)
+        v1 = 2048 / (time.perf_counter() - t0)
         line["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": threads, "kind": "port",
+                                "single_thread_value": v1,
                                 "sample": "%d records of the same workload in %.1f s; restated active-set path "
-                                          "(qpOASES semantics), not the qpOASES binary" % (n_done, dt)}
+                                          "(qpOASES semantics), not the qpOASES binary; built -O3 -march=native on this box; "
+                                          "single_thread_value: 2048 records on one core" % (n_done, dt)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

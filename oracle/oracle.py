@@ -43,14 +43,29 @@ def build(force: bool = False) -> str:
 
 
 _lib = None
+_NATIVE_PATH = os.path.join(_HERE, "_build", "liboracle_native.so")
 
 
-def lib():
+def use_native() -> bool:
+    """Switches this process to a -march=native build made on THIS machine (bench.py's CPU legs); falls back to the
+    portable library when the compiler is missing.  Returns whether the native build is in use."""
+    global _lib
+    try:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except Exception:
+        return False
+    _lib = None
+    lib(_NATIVE_PATH)
+    return True
+
+
+def lib(path: str | None = None):
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
+        if path is None and not os.path.exists(_LIB_PATH):
             build()
-        _lib = C.CDLL(_LIB_PATH)
+        _lib = C.CDLL(path or _LIB_PATH)
+        _lib.oracle_solve_sequence.argtypes = [C.POINTER(CDesc), C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
         _lib.oracle_solve_batch.argtypes = [C.POINTER(CDesc), C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_longlong, C.c_int, C.c_int]
         _lib.oracle_layout.argtypes = [C.POINTER(CDesc), C.POINTER(CLayout)]
@@ -93,6 +108,19 @@ def solve_batch(desc, records: np.ndarray, mode: int = FACTOR_QR, threads: int =
     if rc:
         raise RuntimeError("oracle_solve_batch failed: %d" % rc)
     return out, dg
+
+
+def solve_sequence(desc, records: np.ndarray, warm: np.ndarray, mode: int = FACTOR_QR) -> np.ndarray:
+    """Consecutive ticks on one thread, hot-started: `warm` (8 x uint32, in/out) carries the working sets."""
+    L = c_layout(desc)
+    records = np.ascontiguousarray(records, dtype=np.float64).reshape(-1, L["rec_doubles"])
+    assert warm.dtype == np.uint32 and warm.size == 8 and warm.flags.c_contiguous
+    out = np.zeros((records.shape[0], L["out_bytes"] // 8))
+    rc = lib().oracle_solve_sequence(C.byref(cdesc(desc)), records.ctypes.data, out.ctypes.data, records.shape[0], mode,
+                                     warm.ctypes.data)
+    if rc:
+        raise RuntimeError("oracle_solve_sequence failed: %d" % rc)
+    return out
 
 
 def dense_qp(A, b, Cm, lA, uA, eps, n_reg_steps=0, mode=FACTOR_QR, max_iter=1000):

@@ -434,7 +434,8 @@ static void gi_drop(gi_state* g, int l)
  * minimiser x (in/out).  y[row] > 0: active at lA, < 0: active at uA.  Returns QPPVM_STATUS_*. */
 static int gi_solve(int n, const double* Jfac, double* x, int nc, const double* C,
                     const double* lA, const double* uA, int max_iter, double* y, int* iters,
-                    double* wk /* >= 2 n^2 + 4 n */, int* iwk /* >= 3 n + nc */)
+                    double* wk /* >= 2 n^2 + 4 n */, int* iwk /* >= 3 n + nc */,
+                    const unsigned char* cand /* rows to try first (hot start), or NULL */)
 {
     gi_state g;
     g.n = n; g.k = 0;
@@ -461,7 +462,7 @@ static int gi_solve(int n, const double* Jfac, double* x, int nc, const double* 
             sp = -fabs(s);
             ++next_eq;
         } else {
-            double worst = 0;
+            double worst = 0, wsl = 0;
             for (int i = 0; i < nc; ++i) {
                 /* the side opposite to an active one is still checked: an empty box (lA > uA) must surface as
                  * infeasible instead of being masked by the active side */
@@ -469,11 +470,13 @@ static int gi_solve(int n, const double* Jfac, double* x, int nc, const double* 
                 double cx = 0;
                 for (int j = 0; j < n; ++j) cx += C[i * n + j] * x[j];
                 double tol = 1e-9 * fmax(1.0, fabs(cx));
-                if (act[i] != 1 && lA[i] > -0.5 * QPPVM_INFTY && cx - lA[i] < -tol && cx - lA[i] < worst) { worst = cx - lA[i]; p = i; psgn = 1; }
-                if (act[i] != -1 && uA[i] < 0.5 * QPPVM_INFTY && uA[i] - cx < -tol && uA[i] - cx < worst) { worst = uA[i] - cx; p = i; psgn = -1; }
+                /* hot start: violated rows of the previous working set go first (any violated row is a valid pivot) */
+                const double pri = (cand && cand[i]) ? 0x1p100 : 1.0;
+                if (act[i] != 1 && lA[i] > -0.5 * QPPVM_INFTY && cx - lA[i] < -tol && (cx - lA[i]) * pri < worst) { worst = (cx - lA[i]) * pri; wsl = cx - lA[i]; p = i; psgn = 1; }
+                if (act[i] != -1 && uA[i] < 0.5 * QPPVM_INFTY && uA[i] - cx < -tol && (uA[i] - cx) * pri < worst) { worst = (uA[i] - cx) * pri; wsl = uA[i] - cx; p = i; psgn = -1; }
             }
             if (p < 0) break;              /* primal feasible: optimal */
-            sp = worst;
+            sp = wsl;
         }
         double up = 0.0;                   /* multiplier of p while it is being added */
         for (;;) {
@@ -601,7 +604,7 @@ static void scratch_free(scratch* s)
 
 /* Solves one level: x (out), y (out, nc), returns status; *kkt = certificate of the solved problem. */
 static int solve_level(const level_qp* q, int mode, int n_reg_steps, int max_iter, scratch* s,
-                       double* x, double* y, int* iters, double* kkt)
+                       double* x, double* y, int* iters, double* kkt, unsigned char* cand)
 {
     const int n = q->n, m = q->m;
     if (factor_J(q, mode, s->J, s->wk)) return QPPVM_STATUS_NUMERIC;
@@ -622,7 +625,8 @@ static int solve_level(const level_qp* q, int mode, int n_reg_steps, int max_ite
         for (int j = 0; j < n; ++j) { double v = 0; for (int i = 0; i < n; ++i) v += s->J[i * n + j] * s->g[i]; t[j] = v; }
         for (int i = 0; i < n; ++i) { double v = 0; for (int j = 0; j < n; ++j) v += s->J[i * n + j] * t[j]; s->xu[i] = -v; }
         int it = 0;
-        status = gi_solve(n, s->J, s->xu, q->nc, q->C, q->lA, q->uA, max_iter, y, &it, s->giwk, s->iwk);
+        status = gi_solve(n, s->J, s->xu, q->nc, q->C, q->lA, q->uA, max_iter, y, &it, s->giwk, s->iwk, cand);
+        if (cand) for (int i = 0; i < q->nc; ++i) cand[i] = (unsigned char)(cand[i] || y[i] != 0.0);   /* hot: the re-solve starts from this set */
         total += it;
         memcpy(x, s->xu, sizeof(double) * n);
         for (int j = 0; j < n && status == QPPVM_STATUS_OK; ++j) if (!isfinite(x[j])) status = QPPVM_STATUS_NUMERIC;
@@ -633,7 +637,14 @@ static int solve_level(const level_qp* q, int mode, int n_reg_steps, int max_ite
     return status;
 }
 
+/* warm (optional, in/out): 8 words, the active rows of level 0 | level 1 of the previous solve of this problem
+ * (what QPOases_sot carries from tick to tick: ref:include/QPPVM_RT_plugin/QPPVMPlugin.h:64) -- tried first. */
+int oracle_solve_record_warm(const qppvm_desc* d, const double* rec, void* out, double* diag, int mode, scratch* s, unsigned* warm);
 int oracle_solve_record(const qppvm_desc* d, const double* rec, void* out, double* diag, int mode, scratch* s)
+{
+    return oracle_solve_record_warm(d, rec, out, diag, mode, s, NULL);
+}
+int oracle_solve_record_warm(const qppvm_desc* d, const double* rec, void* out, double* diag, int mode, scratch* s, unsigned* warm)
 {
     qppvm_layout L;
     if (oracle_layout(d, &L)) return QPPVM_ERR_ARG;
@@ -653,8 +664,16 @@ int oracle_solve_record(const qppvm_desc* d, const double* rec, void* out, doubl
         for (int i = 0; i < q.nc; ++i) if (!(isfinite(q.lA[i]) && isfinite(q.uA[i]))) status = QPPVM_STATUS_NUMERIC;
         if (status) break;
         double* x = level ? x1 : x0;
+        unsigned char cand[128];
+        if (warm) {
+            for (int i = 0; i < q.nc; ++i) cand[i] = (unsigned char)(((warm[4 * level + (i >> 5)] >> (i & 31)) & 1u) || (level == 1 && i < L.row_opt && y[i] != 0.0));
+        }
         status = solve_level(&q, mode, d->n_reg_steps, d->max_iter, s, x, y, level ? &it1 : &it0,
-                             level ? &kkt1 : &kkt0);
+                             level ? &kkt1 : &kkt0, warm ? cand : NULL);
+        if (warm && status == QPPVM_STATUS_OK) {
+            for (int w = 0; w < 4; ++w) warm[4 * level + w] = 0u;
+            for (int i = 0; i < q.nc; ++i) if (y[i] != 0.0 || q.lA[i] == q.uA[i]) warm[4 * level + (i >> 5)] |= 1u << (i & 31);
+        }
         if (diag) {
             if (level == 0) memcpy(diag, x0, sizeof(double) * n);
             memcpy(diag + n + level * L.n_rows, y, sizeof(double) * q.nc);
@@ -715,6 +734,19 @@ int oracle_solve_batch(const qppvm_desc* d, const double* recs, void* out, doubl
     return 0;
 }
 
+/* A tick sequence on ONE thread with the hot start a persistent solver gives: `warm` (8 words, in/out) carries the
+ * working sets from record to record (zero it for a cold first tick).  The CPU side of the latency comparison. */
+int oracle_solve_sequence(const qppvm_desc* d, const double* recs, void* out, long long ticks, int mode, unsigned* warm)
+{
+    qppvm_layout L;
+    if (oracle_layout(d, &L) || !warm) return QPPVM_ERR_ARG;
+    static __thread scratch* s = NULL;
+    if (!s) s = scratch_new();
+    for (long long i = 0; i < ticks; ++i)
+        oracle_solve_record_warm(d, recs + i * (size_t)L.rec_doubles, (char*)out + i * (size_t)L.out_bytes, NULL, mode, s, warm);
+    return 0;
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP
@@ -734,7 +766,7 @@ int oracle_dense_qp(int n, int m, const double* A, const double* b, int nc, cons
     scratch* s = scratch_new();
     level_qp q; q.n = n; q.m = m; q.nc = nc; q.eps = eps;
     q.A = (double*)A; q.b = (double*)b; q.C = (double*)C; q.lA = (double*)lA; q.uA = (double*)uA;
-    int st = solve_level(&q, mode, n_reg_steps, max_iter, s, x, y, iters, kkt);
+    int st = solve_level(&q, mode, n_reg_steps, max_iter, s, x, y, iters, kkt, NULL);
     scratch_free(s);
     return st;
 }

@@ -113,3 +113,22 @@ def test_factor_modes_agree_on_forceacc(oracle_mod):
         rel = np.abs(a["x"] - b["x"]).max(axis=1) / np.maximum(1, np.abs(b["x"]).max(axis=1))
         assert rel.max() < 1e-8
         assert (a["active"] == b["active"]).all()
+
+
+def test_hot_started_sequence_matches_cold_solves(oracle_mod):
+    """oracle_solve_sequence (the CPU side of the latency comparison: one thread, working sets carried from tick to tick
+    like a persistent QPOases_sot, ref:include/QPPVM_RT_plugin/QPPVMPlugin.h:64) lands on the cold solutions."""
+    desc = CONFIGS[4]["desc"]
+    n = 120
+    st0 = gen.generate_states(desc, 1, 77)[0]
+    rng = np.random.default_rng(77)
+    st = np.repeat(st0[None], n, axis=0)
+    st[:, :desc.n_a] += np.cumsum(rng.normal(0.0, 2e-3, (n, desc.n_a)), axis=0)
+    recs = gen.records_from_states(desc, st)
+    cold = oracle_mod.split_out(desc, oracle_mod.solve_batch(desc, recs, threads=1)[0])
+    warm = np.zeros(8, dtype=np.uint32)
+    hot = oracle_mod.split_out(desc, oracle_mod.solve_sequence(desc, recs, warm))
+    assert (hot["status"] == 0).all() and warm.any()
+    rel = np.abs(hot["x"] - cold["x"]).max(axis=1) / np.maximum(1.0, np.abs(cold["x"]).max(axis=1))
+    assert rel.max() <= 1e-9 and np.array_equal(hot["active"], cold["active"])
+    assert (hot["iters0"] + hot["iters1"]).sum() < (cold["iters0"] + cold["iters1"]).sum()
