@@ -300,15 +300,19 @@ def main():
         err = np.abs(d_all[:32].cpu().numpy() - chk).max() / max(1.0, np.abs(chk).max())
         assert err < 1e-10, "device front end disagrees with the numpy dynamics: %g" % err
         d_recs = [d_all[i * batch:(i + 1) * batch] for i in range(N_BUF)]
-        n_host = min(n_in, max(batch, 16384)) if batch <= 65536 else batch
+        # records in pinned host memory for the record-path e2e legs: whole batches up to 131 072 records (2.4 GB); the
+        # 2^20-state workload runs those legs on a 131 072-record part of the shard (its headline e2e ships states)
+        hb = min(batch, 131072)
+        n_host = min(n_in, max(hb, 16384)) if batch <= 65536 else hb
         pinned = torch.empty((n_host, L.rec_doubles), dtype=torch.float64).pin_memory()
         pinned.copy_(d_all[:n_host])
         host_recs = pinned.numpy()
     else:
+        hb = batch
         host_recs = gen.generate(desc, n_in, gen.config_seed(args.config), start=rank * n_in)
         pinned = torch.from_numpy(host_recs).pin_memory()
         d_recs = [pinned[i * batch:(i + 1) * batch].to(dev, non_blocking=False).contiguous() for i in range(N_BUF)]
-    n_hbuf = max(1, pinned.shape[0] // batch)                 # host-side batches available for the e2e legs
+    n_hbuf = max(1, pinned.shape[0] // hb)                    # host-side batches available for the e2e legs
     d_out = [torch.empty((batch, L.out_doubles), dtype=torch.float64, device=dev) for _ in range(N_BUF)]
     h_out = torch.empty((batch, L.out_doubles), dtype=torch.float64).pin_memory()
     stream = torch.cuda.current_stream(dev)
@@ -350,6 +354,15 @@ def main():
     t_s = ms.item() * 1e-3
     value = world * args.steps * batch * frac.item() / t_s
 
+    # per-kernel share of a step (events around every launch; a separate short pass, not the timed region above)
+    solver.kernel_timing(True)
+    for i in range(min(3, args.steps)):
+        solver.solve_batch(d_recs[i % N_BUF], out=d_out[i % N_BUF])
+    kms, kn = solver.kernel_timing(False)
+    ksplit = {"prepare_ms_per_step": kms[0] / max(1, min(3, args.steps)), "solve_ms_per_step": kms[1] / max(1, min(3, args.steps)),
+              "certify_ms_per_step": kms[2] / max(1, min(3, args.steps)), "launches": [int(v) for v in kn],
+              "solve_share": float(kms[1] / max(1e-12, kms.sum())),
+              "what": "CUDA events on the launching stream around qp_factor_kernel / qp_solve_kernel / qp_certify_kernel"}
     if args.fast:
         if rank == 0:
             print(json.dumps({"value": value, "ms_per_step": t_s / args.steps * 1e3, "converged_frac": frac.item(),
@@ -360,39 +373,39 @@ def main():
 
     # ---- end to end through the reference-facing C-ABI call with HOST buffers ("e2e") ----------------
     e2e_steps = max(3, min(args.steps, 200))
-    rec_ptr = [pinned[i * batch:(i + 1) * batch].data_ptr() for i in range(n_hbuf)]
+    rec_ptr = [pinned[i * hb:(i + 1) * hb].data_ptr() for i in range(n_hbuf)]
     for i in range(3):
-        solver.solve_batch_host_ptr(rec_ptr[i % n_hbuf], h_out.data_ptr(), batch)
+        solver.solve_batch_host_ptr(rec_ptr[i % n_hbuf], h_out.data_ptr(), hb)
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        solver.solve_batch_host_ptr(rec_ptr[i % n_hbuf], h_out.data_ptr(), batch)   # H2D + solve + D2H, synchronous
+        solver.solve_batch_host_ptr(rec_ptr[i % n_hbuf], h_out.data_ptr(), hb)   # H2D + solve + D2H, synchronous
     torch.cuda.synchronize(dev)
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    ge = api.split_out(L, h_out.numpy())
+    ge = api.split_out(L, h_out.numpy()[:hb])
     e2e_ok = float(((ge["status"] == 0) & (ge["kkt"].max(axis=1) <= 1e-6)).mean())
-    e2e_val = world * e2e_steps * batch * e2e_ok / t_e2e.item()
+    e2e_val = world * e2e_steps * hb * e2e_ok / t_e2e.item()
 
     # pipelined variant: the async entry point, two output buffers in flight, one sync at the end; every step still
     # copies its own records in and its own results out inside the timed region.  Reported beside `e2e`, not as it.
     h_out2 = [h_out, torch.empty_like(h_out).pin_memory()]
     for i in range(3):
-        solver.solve_batch_host_async_ptr(rec_ptr[i % n_hbuf], h_out2[i % 2].data_ptr(), batch)
+        solver.solve_batch_host_async_ptr(rec_ptr[i % n_hbuf], h_out2[i % 2].data_ptr(), hb)
     solver.host_sync()
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        solver.solve_batch_host_async_ptr(rec_ptr[i % n_hbuf], h_out2[i % 2].data_ptr(), batch)
+        solver.solve_batch_host_async_ptr(rec_ptr[i % n_hbuf], h_out2[i % 2].data_ptr(), hb)
     solver.host_sync()
     t_pipe = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_pipe, op=dist.ReduceOp.MAX)
-    gp = api.split_out(L, h_out2[(e2e_steps - 1) % 2].numpy())
+    gp = api.split_out(L, h_out2[(e2e_steps - 1) % 2].numpy()[:hb])
     pipe_ok = float(((gp["status"] == 0) & (gp["kkt"].max(axis=1) <= 1e-6)).mean())
-    e2e_pipe = {"value": world * e2e_steps * batch * pipe_ok / t_pipe.item(), "unit": "solves/s",
-                "h2d_bytes_per_step": batch * L.rec_doubles * 8, "d2h_bytes_per_step": batch * L.out_bytes,
+    e2e_pipe = {"value": world * e2e_steps * hb * pipe_ok / t_pipe.item(), "unit": "solves/s",
+                "h2d_bytes_per_step": hb * L.rec_doubles * 8, "d2h_bytes_per_step": hb * L.out_bytes,
                 "steps": e2e_steps, "api": "qppvm_solve_batch_host_async + qppvm_host_sync (steps overlap)"}
 
     # ---- end to end from compact STATES: rigid-body front end + solve on the device; the host
@@ -491,7 +504,8 @@ def main():
     per_step = max(1, int(round(launches / max(1, args.steps))))
     kname = "qp_solve_kernel<ForceAcc<%d,%d,%d>>" % (desc.n_a, desc.n_contacts, desc.flags) if desc.kind == 1 else "qp_solve_kernel<Torque<%d>>" % desc.n_a
     if per_step >= 2:
-        kname = "qp_factor_kernel + " + kname + " (%d launches per step: the batch runs in workspace-sized passes of one factor + one solve launch, timed together)" % per_step
+        kname = ("qp_factor_kernel + " + kname + " + qp_certify_kernel (%d launches per step: the batch runs in workspace-sized "
+                 "passes of one prepare, one solve and one certify launch, timed together; kernel_split has the shares)" % per_step)
     alg_bytes = L.algorithmic_bytes() * batch
     fp64_peak = solver.fp64_peak_tflops()
     f_alg = F_ALG.get((desc.n_a, desc.n_contacts))
@@ -518,19 +532,28 @@ def main():
                 "flop_per_solve": f_alg, "kernel": kname, "launches_per_step": per_step,
                 "note": "FP64 CUDA-core path (tcgen05 has no FP64): `bound` names the binding roof; HBM roof in roofline_hbm"}
 
+    e2e_records = {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": hb * L.rec_doubles * 8,
+                   "d2h_bytes_per_step": hb * L.out_bytes, "steps": e2e_steps, "records_per_step_per_gpu": hb,
+                   "api": "qppvm_solve_batch_host (records in pinned host buffers in, outputs out)"}
+    # headline e2e: the sharded 2^20-state workload ships compact states (records from a single root are
+    # egress / PCIe bound); the single-GPU workload ships the records the reference's plugin hands to OpenSoT
+    if strong and e2e_states:
+        e2e_head = {k: e2e_states[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "steps", "api")}
+    else:
+        e2e_head = e2e_records
     line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_s / args.steps * 1e3, "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args, cfg_name, desc, L, batch, world),
             "clocks": sampler.result(),
-            "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": batch * L.rec_doubles * 8,
-                    "d2h_bytes_per_step": batch * L.out_bytes, "steps": e2e_steps,
-                    "api": "qppvm_solve_batch_host (pinned host buffers in/out)"},
+            "e2e": e2e_head,
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_hbm": roofline_hbm,
             "converged_frac": frac.item(), "kkt_max": kkt_max}
     if sg:
         line["scatter_gather"] = sg
+    line["e2e_records"] = e2e_records
+    line["kernel_split"] = ksplit
     line["e2e_pipelined"] = e2e_pipe
     if rollout:
         line["rollout"] = rollout

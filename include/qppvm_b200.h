@@ -243,6 +243,10 @@ int qppvm_multi_solve_states_host(qppvm_multi* m, const double* states_host, voi
 int64_t qppvm_multi_kernel_launches(const qppvm_multi* m);
 int64_t qppvm_multi_nccl_calls(const qppvm_multi* m);
 
+/* Per-kernel device time (CUDA events on the launching stream around every launch of the prepare / solve / certify
+ * kernels).  Returns in ms3 / launches3 the totals accumulated since the previous call (both may be NULL), forgets them,
+ * and switches the recording on or off.  Meant for measurements: the events serialise nothing but cost a few us each. */
+int qppvm_kernel_timing(qppvm_handle* h, int enable, double* ms3, int64_t* launches3);
 /* The persistent grids of this handle leave `n_sms` SMs free (default 0): room for kernels that must run concurrently
  * with a long solve, e.g. NCCL's copy kernels on the root GPU of qppvm_multi_solve_batch. */
 int qppvm_reserve_sms(qppvm_handle* h, int n_sms);

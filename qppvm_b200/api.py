@@ -41,7 +41,7 @@ EXPORTS = ("qppvm_get_layout", "qppvm_create", "qppvm_destroy", "qppvm_last_erro
            "qppvm_fp64_peak", "qppvm_supported_shapes", "qppvm_state_doubles", "qppvm_set_robot",
            "qppvm_records_from_states", "qppvm_solve_states_host", "qppvm_solve_batch_host_async", "qppvm_host_sync",
            "qppvm_solve_states_host_async", "qppvm_integrate_states", "qppvm_rollout_states", "qppvm_solve_batch_warm", "qppvm_reset_warm", "qppvm_tick_stamps",
-           "qppvm_reserve_sms", "qppvm_integrate_states_tracking", "qppvm_multi_create", "qppvm_multi_destroy", "qppvm_multi_last_error", "qppvm_multi_devices",
+           "qppvm_reserve_sms", "qppvm_kernel_timing", "qppvm_integrate_states_tracking", "qppvm_multi_create", "qppvm_multi_destroy", "qppvm_multi_last_error", "qppvm_multi_devices",
            "qppvm_multi_set_robot", "qppvm_multi_solve_batch", "qppvm_multi_solve_batch_host",
            "qppvm_multi_solve_states_host", "qppvm_multi_kernel_launches", "qppvm_multi_nccl_calls")
 
@@ -69,6 +69,7 @@ def load_library():
         lib.qppvm_solve_one.argtypes = [P, P, P]
         lib.qppvm_reset_warm.argtypes = [P]
         lib.qppvm_reserve_sms.argtypes = [P, C.c_int]
+        lib.qppvm_kernel_timing.argtypes = [P, C.c_int, P, P]
         lib.qppvm_multi_create.argtypes = [C.POINTER(CDesc), C.POINTER(C.c_int32), C.c_int, C.POINTER(P)]
         lib.qppvm_multi_destroy.argtypes = [P]
         lib.qppvm_multi_last_error.argtypes = [P]
@@ -215,6 +216,12 @@ class Solver:
             out = np.empty(L.out_doubles)
         self._check(self._lib.qppvm_solve_one(self._h, record.ctypes.data, out.ctypes.data))
         return out
+
+    def kernel_timing(self, enable: bool):
+        """(ms[3], launches[3]) of the prepare / solve / certify kernels since the previous call; switches recording on/off."""
+        ms = np.zeros(3); n = np.zeros(3, dtype=np.int64)
+        self._check(self._lib.qppvm_kernel_timing(self._h, int(enable), ms.ctypes.data, n.ctypes.data))
+        return ms, n
 
     def tick_stamps(self) -> np.ndarray:
         """Device-clock stamps (ns) of the last tick through the resident chain (7 stage boundaries)."""

@@ -8,8 +8,8 @@
 #include <string.h>
 #include <new>
 #include "qp_kernel.cuh"
-#include "rbd_kernel.cuh"
 #include <vector>
+#include "rbd_kernel.cuh"
 
 using namespace qppvm;
 
@@ -98,6 +98,9 @@ struct qppvm_handle {
     uint32_t* tick_host; uint32_t* tick_dev; uint32_t* d_one_warm; double* one_ws;
     cudaStream_t tick_streams[3]; bool tick_running; uint32_t tick_seq; int resident; uint32_t idle_us;
     int64_t launches;
+    // optional per-kernel timing (bench.py: share of the step per kernel): events around every launch of the three kernels
+    bool timing; std::vector<cudaEvent_t>* tev;     // (kind, start, stop) triples flattened: kind in tkind
+    std::vector<int>* tkind;
     char err[512];
 };
 
@@ -133,6 +136,13 @@ struct DeviceGuard {
         if (e_ != cudaSuccess)                                                             \
             return fail(h, QPPVM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
+
+// Records a start / stop event pair around one kernel launch when timing is on (kind: 0 prepare, 1 solve, 2 certify).
+struct LaunchTimer {
+    qppvm_handle* h; cudaStream_t st; cudaEvent_t e1 = nullptr;
+    LaunchTimer(qppvm_handle* h_, int kind, cudaStream_t st_);
+    ~LaunchTimer() { if (e1) cudaEventRecord(e1, st); }
+};
 
 // qppvm_desc -> kernel parameters (0.0 in the upstream-semantics fields means "not set": 1.0)
 Params make_params(const qppvm_handle* h)
@@ -170,21 +180,28 @@ int launch(qppvm_handle* h, const double* rec, void* out, double* diag, int64_t 
             const long long fneed = (2 * b + h->shape->factor_pairs - 1) / h->shape->factor_pairs;
             const int fgrid = (int)(fneed < fcap ? fneed : fcap);
             void* fargs[] = {(void*)&r, (void*)&ws, (void*)&b, (void*)&prm, (void*)&counter, (void*)&no_tick};   // also resets the counter
-            CU(h, cudaLaunchKernel(h->shape->factor_kernel, dim3(fgrid), dim3(h->shape->factor_threads), fargs,
-                                   (size_t)h->shape->factor_bytes, st));
+            {
+                LaunchTimer tm(h, 0, st);
+                CU(h, cudaLaunchKernel(h->shape->factor_kernel, dim3(fgrid), dim3(h->shape->factor_threads), fargs,
+                                       (size_t)h->shape->factor_bytes, st));
+            }
             h->launches += 1;
         }
         if (counter && !split) CU(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
         const int grid = (int)(b < cap ? b : cap);
         uint32_t* wm = warm ? warm + c0 * 8 : nullptr;
         void* args[] = {(void*)&r, (void*)&o, (void*)&dgp, (void*)&b, (void*)&prm, (void*)&counter, (void*)&ws, (void*)&wm, (void*)&no_tick};
-        CU(h, cudaLaunchKernel(h->kernel, dim3(grid), dim3(h->team), args, (size_t)h->shape->slab_bytes, st));
+        {
+            LaunchTimer tm(h, 1, st);
+            CU(h, cudaLaunchKernel(h->kernel, dim3(grid), dim3(h->team), args, (size_t)h->shape->slab_bytes, st));
+        }
         h->launches += 1;
         if (split) {                                           // KKT certificate of the pass (reads the blocks the solve exported)
             const long long ccap = (long long)sms * h->certify_ctas_per_sm;
             const int cgrid = (int)(b < ccap ? b : ccap);
             const double* cws = ws;
             void* cargs[] = {(void*)&r, (void*)&o, (void*)&cws, (void*)&b, (void*)&prm, (void*)&no_tick};
+            LaunchTimer tm(h, 2, st);
             CU(h, cudaLaunchKernel(h->shape->certify_kernel, dim3(cgrid), dim3(CERT_THREADS), cargs,
                                    sizeof(double) * (size_t)h->L.rec_doubles, st));
             h->launches += 1;
@@ -257,6 +274,15 @@ int start_servers(qppvm_handle* h)
     h->launches += 3;
     h->tick_running = true;
     return QPPVM_OK;
+}
+
+LaunchTimer::LaunchTimer(qppvm_handle* h_, int kind, cudaStream_t st_) : h(h_), st(st_)
+{
+    if (!h->timing) return;
+    cudaEvent_t e0 = nullptr;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e1 = nullptr; return; }
+    cudaEventRecord(e0, st);
+    h->tev->push_back(e0); h->tev->push_back(e1); h->tkind->push_back(kind);
 }
 
 }  // namespace
@@ -455,6 +481,7 @@ int qppvm_destroy(qppvm_handle* h)
     cudaFree(h->counters);
     for (int i = 0; i < N_SLOTS; ++i) cudaFree(h->ws[i]);
     if (h->ev_dev) cudaEventDestroy(h->ev_dev);
+    if (h->tev) { for (cudaEvent_t e : *h->tev) cudaEventDestroy(e); delete h->tev; delete h->tkind; }
     delete h;
     return QPPVM_OK;
 }
@@ -767,6 +794,27 @@ int qppvm_solve_states_host_async(qppvm_handle* h, const double* states, void* o
 }
 
 int64_t qppvm_kernel_launches(const qppvm_handle* h) { return h ? h->launches : 0; }
+
+int qppvm_kernel_timing(qppvm_handle* h, int enable, double* ms3, int64_t* launches3)
+{
+    if (!h) return QPPVM_ERR_ARG;
+    ENTER(h);
+    if (!h->tev) { h->tev = new std::vector<cudaEvent_t>(); h->tkind = new std::vector<int>(); }
+    if (ms3 && launches3) {
+        for (int k = 0; k < 3; ++k) { ms3[k] = 0.0; launches3[k] = 0; }
+        for (size_t i = 0; i < h->tkind->size(); ++i) {
+            cudaEvent_t e0 = (*h->tev)[2 * i], e1 = (*h->tev)[2 * i + 1];
+            float ms = 0.f;
+            if (cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) {
+                ms3[(*h->tkind)[i]] += ms; launches3[(*h->tkind)[i]] += 1;
+            }
+        }
+    }
+    for (cudaEvent_t e : *h->tev) cudaEventDestroy(e);
+    h->tev->clear(); h->tkind->clear();
+    h->timing = enable != 0;
+    return QPPVM_OK;
+}
 
 int qppvm_reserve_sms(qppvm_handle* h, int n_sms)
 {
