@@ -64,7 +64,7 @@ constexpr int N_SLOTS = HOST_STREAMS + 2;  // launch slots: host / rollout strea
 // 0.9 - 1.5 GB per pass: it does NOT stay in the 126 MB L2 (ncu: the solve kernel reads it back from DRAM, < 8 % of the
 // HBM bandwidth).  Passes are sized for throughput instead: tens of waves of resident CTAs, so that the idle tail of
 // a pass (the last problems of a dynamic schedule) is a few per cent of it.
-constexpr int64_t WS_CHUNK = 32768;
+constexpr int64_t WS_CHUNK = 65536;
 constexpr int64_t ROLL_LANE = 16384;       // states per lane of the on-device rollout (record scratch <= 4 x 0.3 GB)
 
 }  // namespace
@@ -448,7 +448,9 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
         // on the solve path): the host-path chunks, WS_CHUNK problems for the caller's stream, one problem for the
         // latency slot.  The bulk copies of the solve kernel also move the unused Q1 / RN entries: defined contents.
         for (int i = 0; i < N_SLOTS; ++i) {
-            const int64_t capn = i < HOST_STREAMS ? h->chunk_states : (i == HOST_STREAMS ? WS_CHUNK : 8);
+            int64_t ws_chunk = WS_CHUNK;                       // QPPVM_WS_CHUNK: measurement aid (profiles/README.md: pass-size sweep)
+            if (const char* e = getenv("QPPVM_WS_CHUNK")) { const long c = atol(e); if (c >= 256 && c <= (1 << 20)) ws_chunk = c; }
+            const int64_t capn = i < HOST_STREAMS ? h->chunk_states : (i == HOST_STREAMS ? ws_chunk : 8);
             const size_t bytes = sizeof(double) * (size_t)sh->ws_doubles * capn;
             CUC(cudaMalloc(&h->ws[i], bytes));
             CUC(cudaMemset(h->ws[i], 0, bytes));
