@@ -45,6 +45,17 @@ extern "C" {
 #define QPPVM_FLAG_TORQUE_LIMITS   2  /* tau_min <= M_a qdd + h_a - J^T f <= max  */
 #define QPPVM_FLAG_FULL_WRENCH     4  /* 6 variables per contact (force + torque): "put 6 for full wrench",
                                          ref:src/ForceAcc.cpp:67; the wrench bounds are then six real rows per contact */
+#define QPPVM_FLAG_COM_TASK       32  /* FORCEACC: the centroidal force task the reference constructs (OpenSoT tasks::force::CoM,
+                                         ref:src/ForceAcc.cpp:103) joins level 1: postural + contact Cartesian + CoM.  Its six
+                                         rows act on the contact force / wrench variables, which makes those columns dense in
+                                         the level-1 Hessian (general dense path of the kernels)                          */
+/* TORQUE kind: the tasks / constraints the reference instantiates next to its stack */
+#define QPPVM_FLAG_JOINT_LIMITS    8  /* torque-domain joint limits (OpenSoT constraints::torque::JointLimits,
+                                         ref:include/QPPVM_RT_plugin/QPPVMPlugin.h:70, ref:src/QPPVMPlugin.cpp:169-171):
+                                         simple bounds on tau, intersected with the shifted torque limits            */
+#define QPPVM_FLAG_ELBOW_TASKS    16  /* level 1 = elbow_left + elbow_right (two 3-row Cartesian impedance tasks,
+                                         ref:src/QPPVMPlugin.cpp:154-166) instead of the joint impedance task: the
+                                         alternative stack of ref:src/QPPVMPlugin.cpp:177-178                         */
 
 /* ---- per-problem solver status (reference: bool from solve()) ------------- */
 #define QPPVM_STATUS_OK          0
@@ -68,7 +79,7 @@ typedef struct qppvm_desc {
     int32_t kind;               /* QPPVM_KIND_*                                          */
     int32_t n_a;                /* actuated joints                                       */
     int32_t n_contacts;         /* FORCEACC: contacts c; TORQUE: must be 2 (two hands)   */
-    int32_t flags;              /* QPPVM_FLAG_*  (FORCEACC only)                         */
+    int32_t flags;              /* QPPVM_FLAG_*  (1, 2, 4, 32: FORCEACC; 8, 16: TORQUE)  */
     double  eps_regularisation; /* QPOases_sot ctor arg: 1e4 (ForceAcc.cpp:137) / 1.0    */
     int32_t n_reg_steps;        /* qpOASES numRegularisationSteps (MPC option set: 1)    */
     int32_t max_iter;           /* working-set changes allowed per level (nWSR): 132     */
@@ -95,6 +106,8 @@ typedef struct qppvm_desc {
  *   tau_min, tau_max   2 n_a            only with QPPVM_FLAG_TORQUE_LIMITS
  *   cone     c x (R 3x3 row-major, mu)  only with QPPVM_FLAG_FRICTION_CONES
  *   f_lb,f_ub  c x (lb w, ub w)         force / wrench box                 (ForceAcc.cpp:74-76)
+ *   A_com 6 x (w c) row-major, b_com 6  only with QPPVM_FLAG_COM_TASK: centroidal dynamics on the contact wrenches,
+ *                                       [sum f_i ; sum (p_i - c) x f_i (+ tau_i)] = [m (a_ref - g) ; Ldot_ref]   (ForceAcc.cpp:103)
  *
  * TORQUE  (n_v = n_x = n_a):
  *   J_ee     2 x 6 x n  (right hand first: stack order ee_right + ee_left, QPPVMPlugin.cpp:177)
@@ -103,6 +116,11 @@ typedef struct qppvm_desc {
  *   F_ee     2 x 6      K e + D edot per hand (spring+damper wrench)
  *   tau_j    n          K (q_ref - q) + D (-qdot)                          (QPPVMPlugin.cpp:105-118)
  *   tau_min_const, tau_max_const  2 n  (before the -h shift of QPPVMPlugin.cpp:203-204)
+ *   jl_min, jl_max   2 n    only with QPPVM_FLAG_JOINT_LIMITS: k (q_min - q) - d qdot, k (q_max - q) - d qdot
+ *                           (OpenSoT torque::JointLimits::update; gains setGains(k, d), QPPVMPlugin.cpp:170);
+ *                           NOT shifted by h: they bound the solver's variable directly
+ *   J_elbow  2 x 6 x n      only with QPPVM_FLAG_ELBOW_TASKS (left elbow first: stack order elbow_left + elbow_right,
+ *                           QPPVMPlugin.cpp:178), then F_elbow 2 x 6 (K e + D edot per elbow)
  */
 typedef struct qppvm_layout {
     int32_t n_a, n_v, n_c, n_x;
@@ -118,6 +136,8 @@ typedef struct qppvm_layout {
     int32_t rec_doubles;   /* record stride in doubles (even)                               */
     int32_t out_bytes;     /* output stride: 8 (n_x + n_a) + 32                             */
     int32_t diag_doubles;  /* diagnostic stride: n_x (x0) + 2 n_rows (y0,y1) + QPPVM_M0     */
+    int32_t off_jlim, off_jelbow, off_felbow;        /* TORQUE kind with the flags above, else -1 */
+    int32_t off_com;                                 /* FORCEACC with QPPVM_FLAG_COM_TASK: A_com | b_com, else -1 */
 } qppvm_layout;
 
 /* Output trailer that follows x[n_x], tau[n_a] in every output record (32 B). */

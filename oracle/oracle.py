@@ -28,7 +28,7 @@ class CDesc(C.Structure):
 LAYOUT_FIELDS = ("n_a", "n_v", "n_c", "n_x", "n_rows", "row_dyn", "row_box", "row_cone", "row_tau",
                  "row_opt", "off_jwaist", "off_jc", "off_M", "off_h", "off_jdqd", "off_rhs",
                  "off_taulim", "off_cone", "off_fbox", "off_fee", "off_tauj", "rec_doubles",
-                 "out_bytes", "diag_doubles")
+                 "out_bytes", "diag_doubles", "off_jlim", "off_jelbow", "off_felbow", "off_com")
 
 
 class CLayout(C.Structure):

@@ -49,6 +49,7 @@
 int oracle_layout(const qppvm_desc* d, qppvm_layout* L)
 {
     memset(L, 0, sizeof(*L));
+    L->off_jlim = L->off_jelbow = L->off_felbow = L->off_com = -1;
     if (d->n_a < 1 || d->n_a > 58) return 1;
     int off = 0, row = 0;
     if (d->kind == QPPVM_KIND_FORCEACC) {
@@ -74,9 +75,11 @@ int oracle_layout(const qppvm_desc* d, qppvm_layout* L)
         L->off_taulim = tl ? off : -1; off += tl ? 2 * d->n_a : 0;
         L->off_cone = cones ? off : -1; off += cones ? 10 * c : 0;
         L->off_fbox = off; off += 2 * wd * c;
+        if (d->flags & QPPVM_FLAG_COM_TASK) { L->off_com = off; off += 6 * wd * c + 6; }
+        if (d->flags & ~(QPPVM_FLAG_FRICTION_CONES | QPPVM_FLAG_TORQUE_LIMITS | QPPVM_FLAG_FULL_WRENCH | QPPVM_FLAG_COM_TASK)) return 1;
         L->off_fee = L->off_tauj = -1;
     } else if (d->kind == QPPVM_KIND_TORQUE) {
-        if (d->n_contacts != 2 || d->flags != 0) return 1;
+        if (d->n_contacts != 2 || (d->flags & ~(QPPVM_FLAG_JOINT_LIMITS | QPPVM_FLAG_ELBOW_TASKS))) return 1;
         int n = d->n_a;
         L->n_a = L->n_v = L->n_x = n; L->n_c = 2;
         L->row_dyn = L->row_cone = L->row_tau = -1;
@@ -90,6 +93,8 @@ int oracle_layout(const qppvm_desc* d, qppvm_layout* L)
         L->off_tauj = off; off += n;
         L->off_taulim = off; off += 2 * n;
         L->off_cone = L->off_fbox = -1;
+        if (d->flags & QPPVM_FLAG_JOINT_LIMITS) { L->off_jlim = off; off += 2 * n; }
+        if (d->flags & QPPVM_FLAG_ELBOW_TASKS) { L->off_jelbow = off; off += 12 * n; L->off_felbow = off; off += 12; }
     } else return 1;
     if (row > 128) return 1;
     L->n_rows = row;
@@ -135,7 +140,8 @@ static void assemble_forceacc(const qppvm_desc* d, const qppvm_layout* L, const 
             q->b[r] = sw0 * lam * (rec[L->off_rhs + r] - rec[L->off_jdqd + r]);
         }
     } else {
-        q->m = nv + 6 * c;
+        const int com = (d->flags & QPPVM_FLAG_COM_TASK) != 0;
+        q->m = nv + 6 * c + (com ? 6 : 0);
         memset(q->A, 0, sizeof(double) * q->m * n);
         for (int i = 0; i < nv; ++i) {                      /* Postural: A = [I 0] */
             const double s = (d->postural_actuated_only && i < 6) ? 0.0 : sw1;
@@ -148,6 +154,12 @@ static void assemble_forceacc(const qppvm_desc* d, const qppvm_layout* L, const 
                 const double* J = rec + L->off_jc + (ci * 6 + r) * nv;
                 for (int j = 0; j < nv; ++j) q->A[row * n + j] = sw2 * J[j];
                 q->b[row] = sw2 * lam * (rec[L->off_rhs + 6 * (1 + ci) + r] - rec[L->off_jdqd + 6 * (1 + ci) + r]);
+            }
+        if (com)                                            /* tasks::force::CoM (ref:src/ForceAcc.cpp:103): rows on the wrench variables */
+            for (int r = 0; r < 6; ++r) {
+                int row = nv + 6 * c + r;
+                for (int j = 0; j < wd * c; ++j) q->A[row * n + nv + j] = rec[L->off_com + r * wd * c + j];
+                q->b[row] = lam * rec[L->off_com + 6 * wd * c + r];
             }
     }
     /* global constraints, in stack order */
@@ -253,9 +265,10 @@ static int assemble_torque(const qppvm_desc* d, const qppvm_layout* L, const dou
             Minv[i * n + j] = s;
         }
     /* rows of J Minv for both hands (rows 0..2 are the stacked ones, OpenSoT::Indices::range(0,2)) */
-    if (level == 0) {
+    const int elbows = (d->flags & QPPVM_FLAG_ELBOW_TASKS) != 0;
+    if (level == 0 || elbows) {
         q->m = 6;
-        q->eps = d->eps_regularisation * QPPVM_QPOASES_EPS_REG;   /* HST_SEMIDEF: regularised */
+        q->eps = d->eps_regularisation * QPPVM_QPOASES_EPS_REG;   /* CartesianImpedanceCtrl, HST_SEMIDEF: regularised */
     } else {
         q->m = n;
         q->eps = 0.0;                                             /* HST_POSDEF: not regularised */
@@ -285,7 +298,31 @@ static int assemble_torque(const qppvm_desc* d, const qppvm_layout* L, const dou
         }
     }
     if (level == 0) memcpy(q->A, A0, sizeof(double) * 6 * n);
-    else {
+    else if (elbows) {
+        /* level 1 = elbow_left + elbow_right (ref:src/QPPVMPlugin.cpp:154-166, stack of :177-178): the same task type as
+         * the hands, A = (J M^-1)[0..2], b = A J^T F (App. A.3) */
+        for (int t = 0; t < 2; ++t) {
+            const double* J = rec + L->off_jelbow + t * 6 * n;
+            const double* F = rec + L->off_felbow + 6 * t;
+            double JtF[64];
+            for (int j = 0; j < n; ++j) {
+                double sj = 0;
+                for (int r = 0; r < 6; ++r) sj += J[r * n + j] * F[r];
+                JtF[j] = sj;
+            }
+            for (int r = 0; r < 3; ++r) {
+                double* Ar = q->A + (3 * t + r) * n;
+                double sb = 0;
+                for (int j = 0; j < n; ++j) {
+                    double sj = 0;
+                    for (int k = 0; k < n; ++k) sj += J[r * n + k] * Minv[k * n + j];
+                    Ar[j] = sj;
+                }
+                for (int j = 0; j < n; ++j) sb += Ar[j] * JtF[j];
+                q->b[3 * t + r] = sb;
+            }
+        }
+    } else {
         memcpy(q->A, Minv, sizeof(double) * n * n);                 /* A = M^-1, b = M^-1 tau_j */
         for (int i = 0; i < n; ++i) {
             double s = 0;
@@ -300,6 +337,12 @@ static int assemble_torque(const qppvm_desc* d, const qppvm_layout* L, const dou
         q->C[i * n + i] = 1.0;
         q->lA[i] = rec[L->off_taulim + i] - h[i];
         q->uA[i] = rec[L->off_taulim + n + i] - h[i];
+        if (d->flags & QPPVM_FLAG_JOINT_LIMITS) {
+            /* torque::JointLimits (ref:src/QPPVMPlugin.cpp:169-171): simple bounds on the same variable; AutoStack::getBounds
+             * intersects the simple bounds of all global constraints */
+            q->lA[i] = fmax(q->lA[i], rec[L->off_jlim + i]);
+            q->uA[i] = fmin(q->uA[i], rec[L->off_jlim + n + i]);
+        }
     }
     if (level == 1)
         for (int r = 0; r < 6; ++r) {

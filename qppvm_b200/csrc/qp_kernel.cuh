@@ -45,6 +45,9 @@
 #ifndef QPPVM_SELECTIVE_GS
 #define QPPVM_SELECTIVE_GS 1     // second Gram-Schmidt pass only when the first one cancelled more than half of the norm
 #endif
+#ifndef QPPVM_GS_RATIO
+#define QPPVM_GS_RATIO 0.5       // ... i.e. when |w2|^2 < QPPVM_GS_RATIO |w|^2 after the first pass
+#endif
 namespace qppvm {
 
 // Active-set capacity KMAX (eq + ineq, <= 32 so one warp lane per active row), per problem shape.
@@ -273,8 +276,14 @@ struct ForceAcc {
     // variables per contact: 3 force components, or the full wrench ("put 6 for full wrench", ref:src/ForceAcc.cpp:67)
     static constexpr int WD = (FLAGS & QPPVM_FLAG_FULL_WRENCH) ? 6 : 3;
     static constexpr int NV = NA + 6, N = NV + WD * NC;
-    static constexpr int NB = NV;                            // columns with dense task entries (both levels)
-    static constexpr int MD_MAX = 6 * NC > 6 ? 6 * NC : 6;   // dense task rows per level
+    // QPPVM_FLAG_COM_TASK: the centroidal force task (OpenSoT tasks::force::CoM, ref:src/ForceAcc.cpp:103) joins level 1.
+    // Its rows act on the wrench variables, so those columns are dense in the level Hessian: the whitening covers all N
+    // columns, every inequality row goes through the triangular products (no force-only shortcut), and the shape runs
+    // the general in-kernel path (factorisation, row-by-row equalities, KKT check) the Torque kind uses.
+    static constexpr bool COM = (FLAGS & QPPVM_FLAG_COM_TASK) != 0;
+    static constexpr int NB = COM ? N : NV;                  // columns with dense task entries (both levels)
+    static constexpr int MD1_ = 6 * NC + (COM ? 6 : 0);
+    static constexpr int MD_MAX = MD1_ > 6 ? MD1_ : 6;       // dense task rows per level
     // reference row ids
     static constexpr int ROW_DYN = 0, ROW_BOX = 6, ROW_CONE = ROW_BOX + 6 * NC;
     static constexpr int ROW_TAU = ROW_CONE + (CONES ? 5 * NC : 0);
@@ -283,13 +292,15 @@ struct ForceAcc {
     // inequality slots scanned each iteration
     static constexpr int NI_BOX = WD * NC, NI_CONE = CONES ? 5 * NC : 0, NI_TAU = TLIM ? NA : 0;
     static constexpr int NI = NI_BOX + NI_CONE + NI_TAU;
-    // Slots [0, NI_CHEAP) are rows over the force variables of ONE contact (box, friction pyramid).  The force columns
-    // carry no task entries, so they stay diagonal in the whitening (x_f = jd u_f): such a row is evaluated from u
-    // without the triangular product, and its whitened normal has three entries.  The torque-limit rows are dense.
-    static constexpr int NI_CHEAP = NI_BOX + NI_CONE;
+    // Slots [0, NI_FORCE) are rows over the force variables of ONE contact (box, friction pyramid).  Without a force
+    // task the force columns carry no task entries, so they stay diagonal in the whitening (x_f = jd u_f): such a row is
+    // evaluated from u without the triangular product, and its whitened normal has three entries ("cheap" slots).  The
+    // torque-limit rows are dense.
+    static constexpr int NI_FORCE = NI_BOX + NI_CONE;
+    static constexpr int NI_CHEAP = COM ? 0 : NI_FORCE;
     // The loop over the working-set changes ends with a scan of the dense slots at the final x: their values
     // (M_a qdd - J_a^T f) are kept and reused by the KKT check and the torque recovery.
-    static constexpr bool TAUVAL = TLIM;
+    static constexpr bool TAUVAL = TLIM && !COM;
     static constexpr int NTV = TLIM ? NA + (NA & 1) : 0;
     // record offsets (doubles)
     __host__ __device__ static constexpr int OFF_M_() { return 6 * (NA_ + 6) + NC_ * 6 * (NA_ + 6); }
@@ -297,7 +308,8 @@ struct ForceAcc {
     {
         const int nv = NA_ + 6;
         const int u = OFF_M_() + nv * (nv + 1) / 2 + nv + 6 * (1 + NC_) + 6 * (1 + NC_) + nv
-                      + ((FLAGS_ & QPPVM_FLAG_TORQUE_LIMITS) ? 2 * NA_ : 0) + ((FLAGS_ & QPPVM_FLAG_FRICTION_CONES) ? 10 * NC_ : 0) + 2 * ((FLAGS_ & QPPVM_FLAG_FULL_WRENCH) ? 6 : 3) * NC_;
+                      + ((FLAGS_ & QPPVM_FLAG_TORQUE_LIMITS) ? 2 * NA_ : 0) + ((FLAGS_ & QPPVM_FLAG_FRICTION_CONES) ? 10 * NC_ : 0) + 2 * ((FLAGS_ & QPPVM_FLAG_FULL_WRENCH) ? 6 : 3) * NC_
+                      + ((FLAGS_ & QPPVM_FLAG_COM_TASK) ? 6 * ((FLAGS_ & QPPVM_FLAG_FULL_WRENCH) ? 6 : 3) * NC_ + 6 : 0);
         return u + (u & 1);
     }
     static constexpr int OFF_JW = 0, OFF_JC = OFF_JW + 6 * NV, OFF_M = OFF_JC + NC * 6 * NV;
@@ -305,7 +317,8 @@ struct ForceAcc {
     static constexpr int OFF_RHS = OFF_JDQD + 6 * (1 + NC), OFF_TAULIM = OFF_RHS + 6 * (1 + NC) + NV;
     static constexpr int OFF_CONE = OFF_TAULIM + (TLIM ? 2 * NA : 0);
     static constexpr int OFF_FBOX = OFF_CONE + (CONES ? 10 * NC : 0);
-    static constexpr int REC_UNPADDED = OFF_FBOX + 2 * WD * NC;
+    static constexpr int OFF_COM = OFF_FBOX + 2 * WD * NC;     // A_com 6 x (WD NC) | b_com 6
+    static constexpr int REC_UNPADDED = OFF_COM + (COM ? 6 * WD * NC + 6 : 0);
     static constexpr int REC = REC_UNPADDED + (REC_UNPADDED & 1);
     static_assert(REC == REC_() && OFF_M == OFF_M_(), "layout helpers agree");
 
@@ -313,12 +326,12 @@ struct ForceAcc {
     {
         return i >= j ? rec[OFF_M - SB + i * (i + 1) / 2 + j] : rec[OFF_M - SB + j * (j + 1) / 2 + i];
     }
-    static constexpr int MD0 = 6, MD1 = 6 * NC;                // dense task rows of level 0 / 1
+    static constexpr int MD0 = 6, MD1 = MD1_;                  // dense task rows of level 0 / 1
     static constexpr int EXTRA = 0;                            // policy scratch in the slab (doubles)
     // The two factorisations depend only on the record: for the ForceAcc shapes they run in their own kernel
     // (qp_factor_kernel) and reach the solve through a workspace in global memory (L2-resident), which takes the
     // 25 KB of unrolled factorisation code out of the instruction-fetch-bound solve kernel (profiles/README.md).
-    static constexpr bool SPLIT_FACTOR = QPPVM_SPLIT;
+    static constexpr bool SPLIT_FACTOR = QPPVM_SPLIT && !COM;
     // Staging (see Slab::STAGE): shapes whose inequality scan re-reads M every iteration (torque-limit rows) keep
     // the TAIL of the record [M | h | Jdqd | rhs | tau limits | cones | boxes] (one TMA bulk copy) plus the linear
     // contact-Jacobian rows in shared memory; the task Jacobians (read once per level) stay in global memory.
@@ -327,7 +340,7 @@ struct ForceAcc {
     // J = R^-1 is only needed by the triangular products (full x for the dense slots / the end of a level, whitening
     // of a dense row): a few times per level since the force-only rows bypass them.  The 51-variable shape reads it
     // from the prepare workspace in global memory (L2) and spends the 6 KB on two more resident CTAs per SM.
-    static constexpr bool J_GLOBAL = QPPVM_SPLIT && TLIM && !STAGE_RECORD && QPPVM_J_GLOBAL;
+    static constexpr bool J_GLOBAL = SPLIT_FACTOR && TLIM && !STAGE_RECORD && QPPVM_J_GLOBAL;
     static constexpr bool EXT_IS_GLOBAL = true;                // the `ext` argument carries the global record pointer
     static constexpr int STAGE_FROM = OFF_M_();                // first staged record offset (even => 16-byte aligned)
     static constexpr int SB = STAGE_RECORD ? STAGE_FROM : 0;   // staged offset = record offset - SB
@@ -339,7 +352,8 @@ struct ForceAcc {
     }
     static constexpr int KMAX_RAW = kmax_for(12, WD * NC + (CONES ? 5 * NC : 0) + (TLIM ? NA : 0), N);
     // 31 instead of 32 rows of capacity is what lets a fifth CTA of the 51-variable shape fit on an SM
-    static constexpr int KMAX = (KMAX_RAW == 32 && N > 48) ? 31 : KMAX_RAW;
+    // (dense-force shapes: the helper lanes of the triangular products exchange through KP >= (NB - 1) / 2 slots)
+    static constexpr int KMAX = (KMAX_RAW == 32 && N > 48) ? 31 : ((COM && KMAX_RAW < (N + 1) / 2) ? (N + 1) / 2 : KMAX_RAW);
     template <int TEAM> __device__ static __forceinline__ bool prepare(const double*, double*, int) { return true; }
     __device__ static __forceinline__ int n_eq(int level) { return level == 0 ? 6 : 12; }
     __device__ static __forceinline__ int eq_row(int level, int e) { return e < 6 ? ROW_DYN + e : ROW_OPT + (e - 6); }
@@ -384,12 +398,23 @@ struct ForceAcc {
             const int t = level == 0 ? r : 6 + r;            // task-row index into rhs / Jdqd
             Ad[r * LDA + NB] = sw * prm.lam * (rec[OFF_RHS - SB + t] - rec[OFF_JDQD - SB + t]);
         }
+        if constexpr (COM) {
+            // the Cartesian rows have no entries on the wrench columns; at level 1 the six CoM rows follow them
+            // (zero on the acceleration columns, A_com on the wrench columns, right-hand side lambda b_com)
+            constexpr int NF = WD * NC;
+            for (int e = tid; e < md * NF; e += TEAM) { const int r = e / NF, j = e - r * NF; Ad[r * LDA + NV + j] = 0.0; }
+            if (level == 1) {
+                for (int e = tid; e < 6 * NV; e += TEAM) { const int r = e / NV, j = e - r * NV; Ad[(md + r) * LDA + j] = 0.0; }
+                for (int e = tid; e < 6 * NF; e += TEAM) { const int r = e / NF, j = e - r * NF; Ad[(md + r) * LDA + NV + j] = rec[OFF_COM - SB + e]; }
+                if (tid < 6) Ad[(md + tid) * LDA + NB] = prm.lam * rec[OFF_COM - SB + 6 * NF + tid];
+            }
+        }
         for (int j = tid; j < N; j += TEAM) {
             const bool post = level == 1 && j < NV && !(prm.post_act_only && j < 6);
             dg[j] = post ? prm.sw[1] * prm.sw[1] : 0.0;
             db[j] = post ? prm.lam * rec[OFF_RHS - SB + 6 * (1 + NC) + j] : 0.0;
         }
-        return md;
+        return (COM && level == 1) ? md + 6 : md;
     }
 
     // Coefficients of constraint row `row` as a dense n-vector (smem av) + its two-sided bounds.
@@ -446,14 +471,14 @@ struct ForceAcc {
     // Slot table (shared memory, filled once per problem): per force-only slot its three coefficients on the force
     // variables of its contact and the two bounds.
     static constexpr int CT = 5;
-    static constexpr int NCT = NI_CHEAP * CT + ((NI_CHEAP * CT) & 1);
+    static constexpr int NCT = NI_FORCE * CT + ((NI_FORCE * CT) & 1);
     __device__ static __forceinline__ int slot_row(int q) { return q < NI_BOX ? ROW_BOX + 6 * (q / WD) + q % WD : ROW_CONE + (q - NI_BOX); }
     // first of the three consecutive variables the slot's coefficients refer to (force or torque part of a wrench)
     __device__ static __forceinline__ int slot_col(int q) { return q < NI_BOX ? NV + WD * (q / WD) + 3 * ((q % WD) / 3) : NV + WD * ((q - NI_BOX) / 5); }
     template <int TEAM>
     __device__ static __forceinline__ void fill_slot_table(const double* rec, double* ct, int tid)
     {
-        for (int q = tid; q < NI_CHEAP; q += TEAM) {
+        for (int q = tid; q < NI_FORCE; q += TEAM) {
             double a0, a1, a2, lo, hi;
             if (q < NI_BOX) {                                  // wrench box (GenericConstraint), force rows
                 const int ci = q / WD, k = q % WD;
@@ -478,7 +503,7 @@ struct ForceAcc {
     // Force-only row (box rows with k < 3, pyramid rows): first column and the three coefficients.
     __device__ static __forceinline__ bool sparse_row(const double* ct, int row, int& j0, double& a0, double& a1, double& a2)
     {
-        if (row < ROW_BOX || row >= ROW_TAU) return false;     // (without cones ROW_TAU == ROW_CONE)
+        if (COM || row < ROW_BOX || row >= ROW_TAU) return false;     // (without cones ROW_TAU == ROW_CONE)
         const int q = row < ROW_CONE ? WD * ((row - ROW_BOX) / 6) + (row - ROW_BOX) % 6 : NI_BOX + (row - ROW_CONE);
         j0 = slot_col(q);
         a0 = ct[q * CT]; a1 = ct[q * CT + 1]; a2 = ct[q * CT + 2];
@@ -489,14 +514,14 @@ struct ForceAcc {
     __device__ static void eval_slot(const double* rec, const double* g, const double* ct, int q, const double* x,
                                      int& row, double& val, double& lo, double& hi)
     {
-        if (q < NI_CHEAP) {
+        if (q < NI_FORCE) {
             const double* t = ct + q * CT;
             const double* xf = x + slot_col(q);
             row = slot_row(q);
             val = fma(t[0], xf[0], fma(t[1], xf[1], t[2] * xf[2]));
             lo = t[3]; hi = t[4];
         } else {
-            const int a = q - NI_CHEAP;
+            const int a = q - NI_FORCE;
             row = ROW_TAU + a;
             const int i = 6 + a;
             const double* Mi = rec + OFF_M - SB + i * (i + 1) / 2;
@@ -614,7 +639,7 @@ struct ForceAcc {
     // row id and bounds of a dense slot (q >= NI_CHEAP)
     __device__ static __forceinline__ void dense_slot_bounds(const double* rec, int q, int& row, double& lo, double& hi)
     {
-        const int a = q - NI_CHEAP;
+        const int a = q - NI_FORCE;
         row = ROW_TAU + a;
         const double ha = rec[OFF_H - SB + 6 + a];
         lo = rec[OFF_TAULIM - SB + a] - ha; hi = rec[OFF_TAULIM - SB + NA + a] - ha;
@@ -661,12 +686,17 @@ struct ForceAcc {
 //   output : tau_d = tau_qp + h, and tau_qp = 0 when the solve fails                        (cpp:246-256)
 // Policy scratch (ext): M^-1 (N x LDM, symmetric) | A0 (6 x N, kept for the level-1 optimality rows) | T (N x LDM).
 // ------------------------------------------------------------------------------------------
-template <int NA_>
+//   QPPVM_FLAG_JOINT_LIMITS: torque-domain JointLimits (cpp:169-171) -- simple bounds on the same variable, intersected
+//                            with the shifted torque limits (AutoStack::getBounds)
+//   QPPVM_FLAG_ELBOW_TASKS : level 1 = elbow_left + elbow_right (cpp:154-166; the alternative stack of cpp:177-178),
+//                            A = (J_elbow M^-1)[rows 0..2], b = A J^T F; SEMIDEF like the hands -> regularised
+template <int NA_, int FLAGS_ = 0>
 struct Torque {
     static constexpr int KIND = QPPVM_KIND_TORQUE;
-    static constexpr int NA = NA_, NC = 2, FLAGS = 0;
+    static constexpr int NA = NA_, NC = 2, FLAGS = FLAGS_;
+    static constexpr bool JLIM = (FLAGS & QPPVM_FLAG_JOINT_LIMITS) != 0, ELBOW = (FLAGS & QPPVM_FLAG_ELBOW_TASKS) != 0;
     static constexpr int NV = NA, N = NA, NB = NA;
-    static constexpr int MD0 = 6, MD1 = NA, MD_MAX = NA;
+    static constexpr int MD0 = 6, MD1 = ELBOW ? 6 : NA, MD_MAX = MD1;
     static constexpr int ROW_BOX = 0, ROW_OPT = NA, NROWS = NA + QPPVM_M0;
     static constexpr int WD = 3;
     static constexpr int NI = NA, NI_CHEAP = 0;              // every bound row is a (dense) row of J in whitened coordinates
@@ -677,7 +707,8 @@ struct Torque {
     __device__ static __forceinline__ bool sparse_row(const double*, int, int&, double&, double&, double&) { return false; }
     static constexpr int OFF_J = 0, OFF_M = 12 * NA, OFF_H = OFF_M + NA * (NA + 1) / 2, OFF_FEE = OFF_H + NA;
     static constexpr int OFF_TAUJ = OFF_FEE + 12, OFF_TAULIM = OFF_TAUJ + NA;
-    static constexpr int REC_UNPADDED = OFF_TAULIM + 2 * NA;
+    static constexpr int OFF_JLIM = OFF_TAULIM + 2 * NA, OFF_JEL = OFF_JLIM + (JLIM ? 2 * NA : 0), OFF_FEL = OFF_JEL + 12 * NA;
+    static constexpr int REC_UNPADDED = OFF_JEL + (ELBOW ? 12 * NA + 12 : 0);
     static constexpr int REC = REC_UNPADDED + (REC_UNPADDED & 1);
     static constexpr int LDM = NA | 1;
     static constexpr bool STAGE_RECORD = false;                // see Slab::STAGE
@@ -693,7 +724,14 @@ struct Torque {
     __device__ static __forceinline__ int n_eq(int level) { return level == 0 ? 0 : 6; }
     __device__ static __forceinline__ int eq_row(int, int e) { return ROW_OPT + e; }
     // CartesianImpedanceCtrl: HST_SEMIDEF -> regularised; JointImpedanceCtrl: HST_POSDEF -> not
-    __device__ static __forceinline__ bool regularised(int level) { return level == 0; }
+    __device__ static __forceinline__ bool regularised(int level) { return level == 0 || ELBOW; }
+    // bounds of tau_i: shifted torque limits (cpp:203-205), intersected with the joint-limit bounds when present
+    __device__ static __forceinline__ void bounds(const double* rec, int i, double& lo, double& hi)
+    {
+        const double h = rec[OFF_H + i];
+        lo = rec[OFF_TAULIM + i] - h; hi = rec[OFF_TAULIM + NA + i] - h;
+        if (JLIM) { lo = fmax(lo, rec[OFF_JLIM + i]); hi = fmin(hi, rec[OFF_JLIM + NA + i]); }
+    }
 
     // M^-1 by Cholesky (M = L L^T), T = L^-1, M^-1 = T^T T; then A0 = (J_t M^-1)[0..2] for both hands.
     // Element (i, j) of a square buffer X lives at X[j * LDM + i].
@@ -753,8 +791,31 @@ struct Torque {
             for (int k = 0; k < NA; ++k) sacc = fma(Jr[k], L[j * LDM + k], sacc);
             A0[row * NA + j] = sacc;
         }
+        if (ELBOW) {
+            // A1 row (3 t + r) = J_elbow_t[r] M^-1 over the dead T (the products above no longer read it)
+            for (int t = tid; t < 6 * NA; t += TEAM) {
+                const int row = t / NA, j = t - row * NA;
+                const double* Jr = rec + OFF_JEL + ((row / 3) * 6 + (row % 3)) * NA;
+                double sacc = 0.0;
+#pragma unroll 2
+                for (int k = 0; k < NA; ++k) sacc = fma(Jr[k], L[j * LDM + k], sacc);
+                T[row * NA + j] = sacc;
+            }
+        }
         Team<TEAM>::sync();
         return true;
+    }
+    // b = A (J^T F) for the 3-row Cartesian impedance tasks (full 6-row J and 6-vector F): threads 0 .. 5
+    __device__ static __forceinline__ double cart_rhs(const double* Arow, const double* J, const double* F)
+    {
+        double sacc = 0.0;
+        for (int j = 0; j < NA; ++j) {
+            double jtf = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) jtf = fma(J[r * NA + j], F[r], jtf);
+            sacc = fma(Arow[j], jtf, sacc);
+        }
+        return sacc;
     }
 
     template <int TEAM>
@@ -767,29 +828,24 @@ struct Torque {
         for (int j = tid; j < N; j += TEAM) { dg[j] = 0.0; db[j] = 0.0; }
         if (level == 0) {
             for (int t = tid; t < 6 * NA; t += TEAM) { const int r = t / NA, j = t - r * NA; Ad[r * LDA + j] = A0[t]; }
-            if (tid < 6) {                                   // b = A (J^T F)  (full 6-row J and 6-vector F)
-                const int tsk = tid / 3;
-                const double* J = rec + OFF_J + tsk * 6 * NA;
-                const double* F = rec + OFF_FEE + 6 * tsk;
-                double sacc = 0.0;
-                for (int j = 0; j < NA; ++j) {
-                    double jtf = 0.0;
-#pragma unroll
-                    for (int r = 0; r < 6; ++r) jtf = fma(J[r * NA + j], F[r], jtf);
-                    sacc = fma(A0[tid * NA + j], jtf, sacc);
-                }
-                Ad[tid * LDA + NB] = sacc;
-            }
+            if (tid < 6) Ad[tid * LDA + NB] = cart_rhs(A0 + tid * NA, rec + OFF_J + (tid / 3) * 6 * NA, rec + OFF_FEE + 6 * (tid / 3));
             return 6;
         }
-        for (int t = tid; t < NA * NA; t += TEAM) { const int r = t / NA, j = t - r * NA; Ad[r * LDA + j] = Minv[j * LDM + r]; }
-        for (int r = tid; r < NA; r += TEAM) {               // b = M^-1 tau_j
-            double sacc = 0.0;
+        if constexpr (ELBOW) {
+            const double* A1 = ext + O_T;
+            for (int t = tid; t < 6 * NA; t += TEAM) { const int r = t / NA, j = t - r * NA; Ad[r * LDA + j] = A1[t]; }
+            if (tid < 6) Ad[tid * LDA + NB] = cart_rhs(A1 + tid * NA, rec + OFF_JEL + (tid / 3) * 6 * NA, rec + OFF_FEL + 6 * (tid / 3));
+            return 6;
+        } else {
+            for (int t = tid; t < NA * NA; t += TEAM) { const int r = t / NA, j = t - r * NA; Ad[r * LDA + j] = Minv[j * LDM + r]; }
+            for (int r = tid; r < NA; r += TEAM) {           // b = M^-1 tau_j
+                double sacc = 0.0;
 #pragma unroll 2
-            for (int j = 0; j < NA; ++j) sacc = fma(Minv[j * LDM + r], rec[OFF_TAUJ + j], sacc);
-            Ad[r * LDA + NB] = sacc;
+                for (int j = 0; j < NA; ++j) sacc = fma(Minv[j * LDM + r], rec[OFF_TAUJ + j], sacc);
+                Ad[r * LDA + NB] = sacc;
+            }
+            return NA;
         }
-        return NA;
     }
 
     template <int TEAM>
@@ -798,8 +854,7 @@ struct Torque {
     {
         if (row < ROW_OPT) {                                 // TorqueLimits: simple bound on tau_row
             for (int j = tid; j < N; j += TEAM) av[j] = j == row ? 1.0 : 0.0;
-            const double h = rec[OFF_H + row];
-            lo = rec[OFF_TAULIM + row] - h; hi = rec[OFF_TAULIM + NA + row] - h;
+            bounds(rec, row, lo, hi);
         } else {                                             // optimality rows: A0 x = A0 x0*
             const int r = row - ROW_OPT;
             for (int j = tid; j < N; j += TEAM) av[j] = ext[O_A0 + r * NA + j];
@@ -810,8 +865,7 @@ struct Torque {
                                      int& row, double& val, double& lo, double& hi)
     {
         row = q; val = x[q];
-        const double h = rec[OFF_H + q];
-        lo = rec[OFF_TAULIM + q] - h; hi = rec[OFF_TAULIM + NA + q] - h;
+        bounds(rec, q, lo, hi);
     }
     template <int TEAM>
     __device__ static void task0_value(const double*, const double* ext, const double* x, double* eopt, int tid)
@@ -1364,7 +1418,7 @@ struct Solver {
                 gs_update(w, w2, k);
                 nrm2 = dot(w2, w2);
 #if QPPVM_SELECTIVE_GS
-                if (nrm2 < 0.5 * ww)                          // Daniel-Gragg-Kaufman-Stewart: a second pass only after cancellation
+                if (nrm2 < QPPVM_GS_RATIO * ww)               // Daniel-Gragg-Kaufman-Stewart: a second pass only after cancellation
 #endif
                 {
                     gs_pass(w2, true, k);                     // CGS2: "twice is enough"

@@ -51,7 +51,7 @@ constexpr ShapeEntry entry()
 // The instantiation list is generated from the build-time table shapes.def (one line per robot / constraint set).
 const ShapeEntry g_shapes[] = {
 #define QPPVM_SHAPE_FORCEACC(NA, NC, FLAGS) entry<ForceAcc<NA, NC, (FLAGS)>>(),
-#define QPPVM_SHAPE_TORQUE(NA) entry<Torque<NA>>(),
+#define QPPVM_SHAPE_TORQUE(NA, FLAGS) entry<Torque<NA, (FLAGS)>>(),
 #include "shapes.def"
 #undef QPPVM_SHAPE_FORCEACC
 #undef QPPVM_SHAPE_TORQUE
@@ -293,6 +293,7 @@ int qppvm_get_layout(const qppvm_desc* d, qppvm_layout* L)
 {
     if (!d || !L) return QPPVM_ERR_ARG;
     memset(L, 0, sizeof(*L));
+    L->off_jlim = L->off_jelbow = L->off_felbow = L->off_com = -1;
     if (d->n_a < 1 || d->n_a > 58) return QPPVM_ERR_ARG;
     int off = 0, row = 0;
     if (d->kind == QPPVM_KIND_FORCEACC) {
@@ -317,9 +318,11 @@ int qppvm_get_layout(const qppvm_desc* d, qppvm_layout* L)
         L->off_taulim = tl ? off : -1; if (tl) off += 2 * d->n_a;
         L->off_cone = cones ? off : -1; if (cones) off += 10 * c;
         L->off_fbox = off; off += 2 * wd * c;
+        if (d->flags & QPPVM_FLAG_COM_TASK) { L->off_com = off; off += 6 * wd * c + 6; }
+        if (d->flags & ~(QPPVM_FLAG_FRICTION_CONES | QPPVM_FLAG_TORQUE_LIMITS | QPPVM_FLAG_FULL_WRENCH | QPPVM_FLAG_COM_TASK)) return QPPVM_ERR_ARG;
         L->off_fee = L->off_tauj = -1;
     } else if (d->kind == QPPVM_KIND_TORQUE) {
-        if (d->n_contacts != 2 || d->flags != 0) return QPPVM_ERR_ARG;
+        if (d->n_contacts != 2 || (d->flags & ~(QPPVM_FLAG_JOINT_LIMITS | QPPVM_FLAG_ELBOW_TASKS))) return QPPVM_ERR_ARG;
         const int n = d->n_a;
         L->n_a = L->n_v = L->n_x = n; L->n_c = 2;
         L->row_dyn = L->row_cone = L->row_tau = -1;
@@ -333,6 +336,8 @@ int qppvm_get_layout(const qppvm_desc* d, qppvm_layout* L)
         L->off_tauj = off; off += n;
         L->off_taulim = off; off += 2 * n;
         L->off_cone = L->off_fbox = -1;
+        if (d->flags & QPPVM_FLAG_JOINT_LIMITS) { L->off_jlim = off; off += 2 * n; }
+        if (d->flags & QPPVM_FLAG_ELBOW_TASKS) { L->off_jelbow = off; off += 12 * n; L->off_felbow = off; off += 12; }
     } else return QPPVM_ERR_ARG;
     if (row > 128) return QPPVM_ERR_ARG;
     L->n_rows = row;
@@ -416,7 +421,7 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
     CUC(cudaMalloc(&h->counters, sizeof(unsigned long long) * N_SLOTS));
     // host path: records per pipelined chunk (H2D of chunk i+1 overlaps the solve of chunk i); QPPVM_CHUNK overrides
     if (const char* e = getenv("QPPVM_ROWWISE_EQUALITIES")) h->rowwise = atoi(e) != 0;
-    h->chunk = 1024;
+    h->chunk = 2048;      // (configs[2] end to end: 1024 -> 2.62 M, 2048 -> 2.80 M, 4096 -> 2.78 M solves/s; profiles/README.md)
     if (const char* e = getenv("QPPVM_CHUNK")) { const long c = atol(e); if (c >= 64 && c <= (1 << 20)) h->chunk = c; }
     h->chunk_states = 4 * h->chunk;
     for (int i = 0; i < HOST_STREAMS; ++i) {
@@ -602,7 +607,7 @@ int qppvm_reset_warm(qppvm_handle* h)
 static int state_layout(const qppvm_desc* d, RbdShape* sh)
 {
     qppvm_layout L;
-    if (!d || d->kind != QPPVM_KIND_FORCEACC || (d->flags & QPPVM_FLAG_FULL_WRENCH) || qppvm_get_layout(d, &L)) return -1;
+    if (!d || d->kind != QPPVM_KIND_FORCEACC || (d->flags & (QPPVM_FLAG_FULL_WRENCH | QPPVM_FLAG_COM_TASK)) || qppvm_get_layout(d, &L)) return -1;
     const int na = L.n_a, c = L.n_c;
     int o = 0;
     RbdShape s;
@@ -623,7 +628,7 @@ int qppvm_state_doubles(const qppvm_desc* d) { return state_layout(d, nullptr); 
 int qppvm_set_robot(qppvm_handle* h, const qppvm_robot* r)
 {
     if (!h || !r) return QPPVM_ERR_ARG;
-    if (state_layout(&h->desc, &h->rsh) < 0) return fail(h, QPPVM_ERR_UNSUPPORTED, "the state front end covers the ForceAcc kind only");
+    if (state_layout(&h->desc, &h->rsh) < 0) return fail(h, QPPVM_ERR_UNSUPPORTED, "the state front end covers the ForceAcc kind with 3-D contact forces and without the CoM force task");
     const int na = h->desc.n_a, nb = na + 1, nc = h->desc.n_contacts;
     if (r->n_a != na || nb > RBD_MAXB) return fail(h, QPPVM_ERR_ARG, "robot has %d joints, handle expects %d (max %d bodies)", r->n_a, na, RBD_MAXB);
     std::vector<int> depth(nb, 0);

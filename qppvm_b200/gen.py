@@ -15,7 +15,7 @@ from __future__ import annotations
 import numpy as np
 from scipy.special import ndtri
 
-from .layout import (Desc, Layout, layout, KIND_FORCEACC, KIND_TORQUE, FLAG_FRICTION_CONES, FLAG_FULL_WRENCH,
+from .layout import (Desc, Layout, layout, KIND_FORCEACC, KIND_TORQUE, FLAG_FRICTION_CONES, FLAG_FULL_WRENCH, FLAG_ELBOW_TASKS, FLAG_JOINT_LIMITS, FLAG_COM_TASK,
                      FLAG_TORQUE_LIMITS)
 
 DRAWS = 256            # uniforms reserved per problem (multiple of 4: Philox yields 4 per step)
@@ -340,10 +340,37 @@ def records_from_states(desc: Desc, states: np.ndarray) -> np.ndarray:
             tmax = rob.tau_max[None] * tau_scale
             rec[:, L.off_taulim:L.off_taulim + na] = -tmax
             rec[:, L.off_taulim + na:L.off_taulim + 2 * na] = tmax
+        if desc.flags & FLAG_COM_TASK:
+            # OpenSoT tasks::force::CoM (ref:src/ForceAcc.cpp:103): centroidal dynamics on the contact wrenches,
+            #   sum f_i = m (a_ref + l2 (0 - cdot) + l (c_ref - c)) + m g z,   sum (p_i - c) x f_i (+ tau_i) = -k_L L_c.
+            # Total mass, centre of mass and momentum come out of the joint-space quantities the record already holds:
+            # M[0:3, 0:3] = m I, M[0:3, 3:6] = -m [c - p0]x (mixed velocity convention), momentum = M[0:6] v.
+            wd = 6 if desc.flags & FLAG_FULL_WRENCH else 3
+            Mm = dyn["M"]
+            m = Mm[:, 0, 0]
+            dcom = np.stack([Mm[:, 1, 5], Mm[:, 2, 3], Mm[:, 0, 4]], axis=1) / m[:, None]      # c - p0
+            mom = np.einsum("bij,bj->bi", Mm[:, :6], v)
+            cdot = mom[:, :3] / m[:, None]
+            Lc = mom[:, 3:6] - np.cross(dcom, mom[:, :3])          # angular momentum about the centre of mass
+            A = np.zeros((n, 6, wd * c))
+            for ci, b in enumerate(contact_bodies):
+                r = dyn["links"][b]["p"] - (p0 + dcom)
+                A[:, 0, wd * ci + 0] = A[:, 1, wd * ci + 1] = A[:, 2, wd * ci + 2] = 1.0
+                A[:, 3, wd * ci + 1], A[:, 3, wd * ci + 2] = -r[:, 2], r[:, 1]             # [r]x
+                A[:, 4, wd * ci + 0], A[:, 4, wd * ci + 2] = r[:, 2], -r[:, 0]
+                A[:, 5, wd * ci + 0], A[:, 5, wd * ci + 1] = -r[:, 1], r[:, 0]
+                if wd == 6:
+                    A[:, 3, wd * ci + 3] = A[:, 4, wd * ci + 4] = A[:, 5, wd * ci + 5] = 1.0
+            e_com = np.concatenate([ori_err[:, :2] * 0.4, -0.02 * np.ones((n, 1))], axis=1)    # c_ref - c
+            b_lin = m[:, None] * (lam_p * e_com - lam2_p * cdot) + m[:, None] * np.array([0.0, 0.0, GRAVITY])
+            b_ang = -10.0 * gains[:, 3:4] * Lc
+            rec[:, L.off_com:L.off_com + 6 * wd * c] = A.reshape(n, -1)
+            rec[:, L.off_com + 6 * wd * c:L.off_com + 6 * wd * c + 6] = np.concatenate([b_lin, b_ang], axis=1)
     elif desc.kind == KIND_TORQUE:
         # fixed base: drop the 6 base columns/rows of the floating-base quantities
         Z3 = np.zeros((n, 3))
-        dyn = rob.dynamics(q, qd, np.tile(np.eye(3), (n, 1, 1)), Z3, Z3, Z3, rob.hand[::-1])
+        elbows = [hb - 3 for hb in rob.hand]                   # "arm1_4" / "arm2_4": fourth body of each seven-joint arm chain
+        dyn = rob.dynamics(q, qd, np.tile(np.eye(3), (n, 1, 1)), Z3, Z3, Z3, rob.hand[::-1] + elbows)
         Mj = dyn["M"][:, 6:, 6:]
         rec[:, L.off_M:L.off_M + na * (na + 1) // 2] = pack_lower(Mj)
         rec[:, L.off_h:L.off_h + na] = dyn["h"][:, 6:]
@@ -359,6 +386,24 @@ def records_from_states(desc: Desc, states: np.ndarray) -> np.ndarray:
         tmax = rob.tau_max[None] * tau_scale
         rec[:, L.off_taulim:L.off_taulim + na] = -tmax
         rec[:, L.off_taulim + na:L.off_taulim + 2 * na] = tmax
+        if desc.flags & FLAG_JOINT_LIMITS:
+            # OpenSoT constraints::torque::JointLimits (ref:src/QPPVMPlugin.cpp:169-171): tau in [k (q_min - q) - d qdot,
+            # k (q_max - q) - d qdot] (gains through setGains, :170; k0 / d0 are not defined in the reference: synthetic
+            # k = 50, d = 4 here); joint range q_home +- 0.35 rad shrunk by 10 % on both sides (:119-122), so that some of
+            # the states (q_home + U(-0.3, 0.3)) sit close enough to a limit for the bound to bind
+            qmin, qmax = rob.q_home[None] - 0.35 * 0.8, rob.q_home[None] + 0.35 * 0.8
+            kj, dj = 50.0 * gains[:, 2:3], 4.0 * gains[:, 3:4]
+            rec[:, L.off_jlim:L.off_jlim + na] = kj * (qmin - q) - dj * qd
+            rec[:, L.off_jlim + na:L.off_jlim + 2 * na] = kj * (qmax - q) - dj * qd
+        if desc.flags & FLAG_ELBOW_TASKS:
+            # elbow_left + elbow_right: CartesianImpedanceCtrl on "arm1_4" / "arm2_4" (ref:src/QPPVMPlugin.cpp:154-166),
+            # default gains K = 100 I, D = I (these two tasks never get setStiffnessDamping)
+            for ti, hb in enumerate(rob.hand):                 # left first (:178)
+                Je = dyn["links"][hb - 3]["J"][:, :, 6:]
+                rec[:, L.off_jelbow + ti * 6 * na:L.off_jelbow + (ti + 1) * 6 * na] = Je.reshape(n, -1)
+                e = np.concatenate([ferr[:, 6 * ti + 3:6 * ti + 6] * 20.0, -ori_err * (1 - 2 * ti)], axis=1)
+                Fe = 100.0 * gains[:, 0:1] * e - 1.0 * gains[:, 1:2] * np.einsum("bij,bj->bi", Je, qd)
+                rec[:, L.off_felbow + 6 * ti:L.off_felbow + 6 * ti + 6] = Fe
     return rec
 
 

@@ -17,6 +17,9 @@ KIND_FORCEACC = 1
 FLAG_FRICTION_CONES = 1
 FLAG_TORQUE_LIMITS = 2
 FLAG_FULL_WRENCH = 4      # 6 variables per contact ("put 6 for full wrench", ref:src/ForceAcc.cpp:67)
+FLAG_COM_TASK = 32        # ForceAcc kind: the centroidal force task joins level 1 (ref:src/ForceAcc.cpp:103)
+FLAG_JOINT_LIMITS = 8     # Torque kind: torque-domain JointLimits bounds (ref:src/QPPVMPlugin.cpp:169-171)
+FLAG_ELBOW_TASKS = 16     # Torque kind: level 1 = elbow_left + elbow_right (ref:src/QPPVMPlugin.cpp:154-166, 177-178)
 STATUS_OK, STATUS_MAX_ITER, STATUS_INFEASIBLE, STATUS_NUMERIC = 0, 1, 2, 3
 QPOASES_EPS = 2.221e-16
 QPOASES_EPS_REG = 1.0e3 * QPOASES_EPS
@@ -70,10 +73,14 @@ class Layout:
     rec_doubles: int
     out_bytes: int
     diag_doubles: int
+    off_jlim: int = -1
+    off_jelbow: int = -1
+    off_felbow: int = -1
+    off_com: int = -1
     FIELDS = ("n_a", "n_v", "n_c", "n_x", "n_rows", "row_dyn", "row_box", "row_cone", "row_tau",
               "row_opt", "off_jwaist", "off_jc", "off_M", "off_h", "off_jdqd", "off_rhs",
               "off_taulim", "off_cone", "off_fbox", "off_fee", "off_tauj", "rec_doubles",
-              "out_bytes", "diag_doubles")
+              "out_bytes", "diag_doubles", "off_jlim", "off_jelbow", "off_felbow", "off_com")
 
     @property
     def out_doubles(self) -> int:
@@ -93,6 +100,7 @@ class Layout:
 def layout(desc: Desc) -> Layout:
     if desc.n_a < 1 or desc.n_a > 58:
         raise ValueError("n_a out of range")
+    off_jlim = off_jelbow = off_felbow = off_com = -1
     if desc.kind == KIND_FORCEACC:
         c = desc.n_contacts
         if c < 1 or c > 4:
@@ -120,10 +128,14 @@ def layout(desc: Desc) -> Layout:
         off_taulim = off if tl else -1; off += 2 * n_a if tl else 0
         off_cone = off if cones else -1; off += 10 * c if cones else 0
         off_fbox = off; off += 2 * wd * c
+        if desc.flags & FLAG_COM_TASK:
+            off_com = off; off += 6 * wd * c + 6
+        if desc.flags & ~(FLAG_FRICTION_CONES | FLAG_TORQUE_LIMITS | FLAG_FULL_WRENCH | FLAG_COM_TASK):
+            raise ValueError("ForceAcc kind: unknown flag")
         off_fee = off_tauj = -1
     elif desc.kind == KIND_TORQUE:
-        if desc.n_contacts != 2 or desc.flags != 0:
-            raise ValueError("torque kind: n_contacts must be 2, flags 0")
+        if desc.n_contacts != 2 or desc.flags & ~(FLAG_JOINT_LIMITS | FLAG_ELBOW_TASKS):
+            raise ValueError("torque kind: n_contacts must be 2, flags a subset of JOINT_LIMITS | ELBOW_TASKS")
         c = 2
         n_a = n_v = n_x = desc.n_a
         row_dyn = row_cone = row_tau = -1
@@ -140,6 +152,11 @@ def layout(desc: Desc) -> Layout:
         off_tauj = off; off += n_v
         off_taulim = off; off += 2 * n_v
         off_cone = off_fbox = -1
+        if desc.flags & FLAG_JOINT_LIMITS:
+            off_jlim = off; off += 2 * n_v
+        if desc.flags & FLAG_ELBOW_TASKS:
+            off_jelbow = off; off += 12 * n_v
+            off_felbow = off; off += 12
     else:
         raise ValueError("unknown kind")
     if row > 128:
@@ -151,7 +168,8 @@ def layout(desc: Desc) -> Layout:
                   off_jc=off_jc, off_M=off_M, off_h=off_h, off_jdqd=off_jdqd, off_rhs=off_rhs,
                   off_taulim=off_taulim, off_cone=off_cone, off_fbox=off_fbox, off_fee=off_fee,
                   off_tauj=off_tauj, rec_doubles=rec, out_bytes=8 * (n_x + n_a) + 32,
-                  diag_doubles=n_x + 2 * row + M0, _unpadded=unp)
+                  diag_doubles=n_x + 2 * row + M0, off_jlim=off_jlim, off_jelbow=off_jelbow, off_felbow=off_felbow, off_com=off_com,
+                  _unpadded=unp)
 
 
 # The five BASELINE.json configs (SURVEY.md 8(a) "Per-config QP dimensions").

@@ -6,6 +6,7 @@
 #include "plugin_math.h"
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 
@@ -14,6 +15,8 @@ REGISTER_XBOT_PLUGIN(QPPVMPlugin, demo::QPPVMPlugin)
 using namespace demo;
 static const char* kLeftEE = "arm1_7";      // ref:src/QPPVMPlugin.cpp:132
 static const char* kRightEE = "arm2_7";     // ref:src/QPPVMPlugin.cpp:145
+static const char* kLeftElbow = "arm1_4";   // ref:src/QPPVMPlugin.cpp:157
+static const char* kRightElbow = "arm2_4";  // ref:src/QPPVMPlugin.cpp:164
 
 QPPVMPlugin::QPPVMPlugin() {}
 QPPVMPlugin::~QPPVMPlugin() { if (_solver) qppvm_destroy(_solver); }
@@ -58,7 +61,26 @@ bool QPPVMPlugin::init_control_plugin(XBot::Handle::Ptr handle)
     d.kind = QPPVM_KIND_TORQUE;
     d.n_a = n;
     d.n_contacts = 2;
-    d.flags = 0;
+    if (const char* e = std::getenv("QPPVM_PLUGIN_STACK")) {
+        if (std::strstr(e, "elbows")) _stack_flags |= QPPVM_FLAG_ELBOW_TASKS;        // .../(_elbow_task_left + _elbow_task_right) (:178)
+        if (std::strstr(e, "joint_limits")) _stack_flags |= QPPVM_FLAG_JOINT_LIMITS; // _joint_limits (:169-171)
+    }
+    if (_stack_flags & QPPVM_FLAG_JOINT_LIMITS) {
+        _model->getJointLimits(_q_min, _q_max);                                      // :120-123
+        _k_jl.setZero(n); _d_jl.setZero(n);
+        for (int j = 0; j < n; ++j) {
+            const double q_range = _q_max[j] - _q_min[j];
+            _q_max[j] -= 0.1 * q_range;
+            _q_min[j] += 0.1 * q_range;
+            _k_jl[j] = 10.0 * k0[j];                                                 // setGains(k0*10, d0*20) (:170)
+            _d_jl[j] = 20.0 * d0[j];
+        }
+    }
+    if (_stack_flags & QPPVM_FLAG_ELBOW_TASKS) {                                     // :154-166: reference = pose at construction
+        _model->getPose(kLeftElbow, _ref_elbow_left);
+        _model->getPose(kRightElbow, _ref_elbow_right);
+    }
+    d.flags = _stack_flags;
     d.eps_regularisation = 1.0;
     d.n_reg_steps = 1;
     d.max_iter = 132;
@@ -72,7 +94,7 @@ bool QPPVMPlugin::init_control_plugin(XBot::Handle::Ptr handle)
     return true;
 }
 
-void QPPVMPlugin::impedance_wrench(const std::string& link, const Eigen::Affine3d& ref, const Eigen::MatrixXd& J, double* F) const
+void QPPVMPlugin::impedance_wrench(const std::string& link, const Eigen::Affine3d& ref, const Eigen::MatrixXd& J, double K, double D, double* F) const
 {
     // CartesianImpedanceCtrl: F = K [e_pos; e_ori] + D (xdot_des - J qdot), xdot_des = 0
     Eigen::Affine3d T;
@@ -83,7 +105,7 @@ void QPPVMPlugin::impedance_wrench(const std::string& link, const Eigen::Affine3
     for (int r = 0; r < 6; ++r) {
         double v = 0.0;
         for (int j = 0; j < J.cols(); ++j) v += J(r, j) * _dq[j];
-        F[r] = _Kc * e[r] - _Dc * v;
+        F[r] = K * e[r] - D * v;
     }
 }
 
@@ -105,7 +127,7 @@ void QPPVMPlugin::QPPVMControl(const double time)
         _model->getJacobian(ee[t], _Jtmp);
         for (int r = 0; r < 6; ++r)
             for (int j = 0; j < n; ++j) rec[_L.off_jc + (t * 6 + r) * n + j] = _Jtmp(r, j);
-        impedance_wrench(ee[t], *ref[t], _Jtmp, rec + _L.off_fee + 6 * t);
+        impedance_wrench(ee[t], *ref[t], _Jtmp, _Kc, _Dc, rec + _L.off_fee + 6 * t);
     }
     _model->getInertiaMatrix(_M);
     for (int i = 0; i < n; ++i)
@@ -115,6 +137,21 @@ void QPPVMPlugin::QPPVMControl(const double time)
         rec[_L.off_tauj + j] = _Kj * (_q_ref[j] - _q[j]) - _Dj * _dq[j];
         rec[_L.off_taulim + j] = _tau_min_const[j];
         rec[_L.off_taulim + n + j] = _tau_max_const[j];
+    }
+    if (_stack_flags & QPPVM_FLAG_JOINT_LIMITS)                                      // torque::JointLimits::update
+        for (int j = 0; j < n; ++j) {
+            rec[_L.off_jlim + j] = _k_jl[j] * (_q_min[j] - _q[j]) - _d_jl[j] * _dq[j];
+            rec[_L.off_jlim + n + j] = _k_jl[j] * (_q_max[j] - _q[j]) - _d_jl[j] * _dq[j];
+        }
+    if (_stack_flags & QPPVM_FLAG_ELBOW_TASKS) {
+        const char* el[2] = {kLeftElbow, kRightElbow};                               // stack order elbow_left + elbow_right (:178)
+        const Eigen::Affine3d* eref[2] = {&_ref_elbow_left, &_ref_elbow_right};
+        for (int t = 0; t < 2; ++t) {
+            _model->getJacobian(el[t], _Jtmp);
+            for (int r = 0; r < 6; ++r)
+                for (int j = 0; j < n; ++j) rec[_L.off_jelbow + (t * 6 + r) * n + j] = _Jtmp(r, j);
+            impedance_wrench(el[t], *eref[t], _Jtmp, _Ke, _De, rec + _L.off_felbow + 6 * t);
+        }
     }
     /* _solver->solve(_tau_d) (:246) */
     int rc = qppvm_solve_one(_solver, _record.data(), _out.data());

@@ -81,6 +81,12 @@ public:
     }
     bool getVelocityTwist(const std::string& l, Eigen::Vector6d& v) const override { for (int r = 0; r < 6; ++r) v[r] = s().links[link(l)].twist[r]; return true; }
     bool getEffortLimits(Eigen::VectorXd& t) const override { t.resize(g_nv); for (int i = 0; i < g_nv; ++i) t[i] = s().tmax[i]; return true; }
+    bool getJointLimits(Eigen::VectorXd& lo, Eigen::VectorXd& hi) const override
+    {
+        lo.resize(g_nv); hi.resize(g_nv);
+        for (int i = 0; i < g_nv; ++i) { lo[i] = s().home[i] - 0.35; hi[i] = s().home[i] + 0.35; }
+        return true;
+    }
     bool setFloatingBaseState(const Eigen::Affine3d& T, const Eigen::Vector6d& tw) override { fb_pose = T; fb_twist = tw; ++fb_sets; return true; }
     bool getFloatingBasePose(Eigen::Affine3d& T) const override { T = fb_pose; return true; }
     bool syncFrom(const XBot::RobotInterface&) override { ++syncs; return true; }

@@ -109,6 +109,7 @@ public:
     virtual bool getPointPosition(const std::string& link, const Eigen::Vector3d& p, Eigen::Vector3d& w_p) const = 0;
     virtual bool getVelocityTwist(const std::string& link, Eigen::Vector6d& v) const = 0;
     virtual bool getEffortLimits(Eigen::VectorXd& tmax) const = 0;                            // QPPVMPlugin.cpp:56
+    virtual bool getJointLimits(Eigen::VectorXd& qmin, Eigen::VectorXd& qmax) const = 0;      // QPPVMPlugin.cpp:120
     virtual bool setFloatingBaseState(const Eigen::Affine3d& T, const Eigen::Vector6d& twist) = 0;   // ForceAcc.cpp:274
     virtual bool getFloatingBasePose(Eigen::Affine3d& T) const = 0;                           // ForceAcc.cpp:279
     virtual bool syncFrom(const class RobotInterface& robot) = 0;                             // ForceAcc.cpp:258

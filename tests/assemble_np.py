@@ -5,7 +5,7 @@ from __future__ import annotations
 import numpy as np
 
 from qppvm_b200.gen import unpack_lower
-from qppvm_b200.layout import Desc, KIND_FORCEACC, layout, QPOASES_EPS_REG, INFTY
+from qppvm_b200.layout import Desc, KIND_FORCEACC, FLAG_COM_TASK, FLAG_ELBOW_TASKS, FLAG_JOINT_LIMITS, layout, QPOASES_EPS_REG, INFTY
 
 
 def level_matrices(desc: Desc, rec: np.ndarray, level: int, x0=None):
@@ -34,6 +34,10 @@ def level_matrices(desc: Desc, rec: np.ndarray, level: int, x0=None):
                           [w_cont * np.hstack([Jc[i], Z((6, wd * c))]) for i in range(c)])
             b = np.concatenate([P @ (lam * rhs[6 * (1 + c):])] +
                                [w_cont * lam * (rhs[6 * (1 + i):6 * (2 + i)] - jdqd[6 * (1 + i):6 * (2 + i)]) for i in range(c)])
+            if desc.flags & FLAG_COM_TASK:   # ... + _com_task (constructed at ForceAcc.cpp:103): rows on the wrench variables
+                blk = rec[L.off_com:L.off_com + 6 * wd * c + 6]
+                A = np.vstack([A, np.hstack([Z((6, nv)), blk[:6 * wd * c].reshape(6, wd * c)])])
+                b = np.concatenate([b, lam * blk[6 * wd * c:]])
         rows, lo, hi = [], [], []
         # DynamicFeasibility: (M qdd + h - sum J_i^T [f_i; 0])[0:6] = 0
         D = np.hstack([M[:6]] + [-Jc[i][:wd, :6].T for i in range(c)])
@@ -68,11 +72,22 @@ def level_matrices(desc: Desc, rec: np.ndarray, level: int, x0=None):
         if level == 0:
             A = A0; b = np.concatenate([(J[t] @ Minv)[:3] @ (J[t].T @ F[t]) for t in range(2)])
             eps = desc.eps_regularisation * QPOASES_EPS_REG
+        elif desc.flags & FLAG_ELBOW_TASKS:
+            # (_ee_task_right + _ee_task_left) / (_elbow_task_left + _elbow_task_right)  (QPPVMPlugin.cpp:154-166, 177-178)
+            Je = rec[L.off_jelbow:L.off_jelbow + 12 * nn].reshape(2, 6, nn)
+            Fe = rec[L.off_felbow:L.off_felbow + 12].reshape(2, 6)
+            A = np.vstack([(Je[t] @ Minv)[:3] for t in range(2)])
+            b = np.concatenate([(Je[t] @ Minv)[:3] @ (Je[t].T @ Fe[t]) for t in range(2)])
+            eps = desc.eps_regularisation * QPOASES_EPS_REG
         else:
             A = Minv; b = Minv @ rec[L.off_tauj:L.off_tauj + nn]        # JointImpedanceCtrl
             eps = 0.0
         tl = rec[L.off_taulim:L.off_taulim + 2 * nn]
-        rows, lo, hi = [np.eye(nn)], [tl[:nn] - h], [tl[nn:] - h]      # TorqueLimits (QPPVMPlugin.cpp:203-205)
+        blo, bhi = tl[:nn] - h, tl[nn:] - h                            # TorqueLimits (QPPVMPlugin.cpp:203-205)
+        if desc.flags & FLAG_JOINT_LIMITS:                             # torque::JointLimits: bounds on the same variable
+            jl = rec[L.off_jlim:L.off_jlim + 2 * nn]
+            blo, bhi = np.maximum(blo, jl[:nn]), np.minimum(bhi, jl[nn:])
+        rows, lo, hi = [np.eye(nn)], [blo], [bhi]
         if level == 1:
             rows.append(A0); lo.append(A0 @ x0); hi.append(A0 @ x0)
     return A, b, np.vstack(rows), np.concatenate(lo), np.concatenate(hi), eps

@@ -7,7 +7,8 @@ import re
 import pytest
 
 from qppvm_b200 import api, build
-from qppvm_b200.layout import (CONFIGS, Desc, KIND_TORQUE, layout, FLAG_FRICTION_CONES, FLAG_TORQUE_LIMITS)
+from qppvm_b200.layout import (CONFIGS, Desc, KIND_TORQUE, layout, FLAG_FRICTION_CONES, FLAG_TORQUE_LIMITS, FLAG_ELBOW_TASKS,
+                               FLAG_JOINT_LIMITS, FLAG_COM_TASK)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -22,6 +23,10 @@ DESCS = [c["desc"] for c in CONFIGS.values()] + [
     Desc(n_a=33, n_contacts=4, flags=0), Desc(n_a=39, n_contacts=4, flags=0),
     Desc(n_a=12, n_contacts=1, flags=FLAG_FRICTION_CONES), Desc(n_a=20, n_contacts=3, flags=FLAG_TORQUE_LIMITS),
     Desc(kind=KIND_TORQUE, n_a=39, n_contacts=2, flags=0, eps_regularisation=1.0),
+    Desc(kind=KIND_TORQUE, n_a=29, n_contacts=2, flags=FLAG_JOINT_LIMITS, eps_regularisation=1.0),
+    Desc(kind=KIND_TORQUE, n_a=29, n_contacts=2, flags=FLAG_ELBOW_TASKS, eps_regularisation=1.0),
+    Desc(kind=KIND_TORQUE, n_a=33, n_contacts=2, flags=FLAG_JOINT_LIMITS | FLAG_ELBOW_TASKS, eps_regularisation=1.0),
+    Desc(n_a=29, n_contacts=2, flags=FLAG_COM_TASK), Desc(n_a=33, n_contacts=4, flags=FLAG_COM_TASK | FLAG_FRICTION_CONES | FLAG_TORQUE_LIMITS),
 ]
 
 

@@ -10,12 +10,18 @@ import numpy as np
 import pytest
 
 from qppvm_b200 import gen
-from qppvm_b200.layout import CONFIGS, Desc, KIND_TORQUE, layout
+from qppvm_b200.layout import CONFIGS, Desc, KIND_TORQUE, FLAG_COM_TASK, FLAG_ELBOW_TASKS, FLAG_JOINT_LIMITS, layout
 from tests.assemble_np import level_matrices
 from tests.qp_ref import highs_qp, kkt_numpy
 
 CASES = [(1, CONFIGS[1]["desc"]), (0, CONFIGS[0]["desc"]), (2, CONFIGS[2]["desc"]),
-         (7, Desc(kind=KIND_TORQUE, n_a=29, n_contacts=2, flags=0, eps_regularisation=1.0))]
+         (7, Desc(kind=KIND_TORQUE, n_a=29, n_contacts=2, flags=0, eps_regularisation=1.0)),
+         # task library of SURVEY 8(f) row 4: torque-domain JointLimits, elbow tasks as level 1 (eps factor 1e2: with
+         # the reference's 1.0 the 17 directions no elbow / hand row sees are defined by a 2.2e-13 regulariser alone)
+         (8, Desc(kind=KIND_TORQUE, n_a=29, n_contacts=2, flags=FLAG_JOINT_LIMITS, eps_regularisation=1.0)),
+         (9, Desc(kind=KIND_TORQUE, n_a=29, n_contacts=2, flags=FLAG_JOINT_LIMITS | FLAG_ELBOW_TASKS, eps_regularisation=1.0e2)),
+         # the centroidal force task at level 1 (ref:src/ForceAcc.cpp:103), with cones + torque limits
+         (10, Desc(n_a=29, n_contacts=2, flags=FLAG_COM_TASK | 3))]
 
 
 @pytest.mark.parametrize("ci,desc", CASES)

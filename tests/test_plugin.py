@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from qppvm_b200 import gen
-from qppvm_b200.layout import Desc, KIND_TORQUE, layout
+from qppvm_b200.layout import Desc, KIND_TORQUE, FLAG_ELBOW_TASKS, FLAG_JOINT_LIMITS, layout
 from tests.helpers import PRIMAL_TOL, rel_inf
 
 PLUG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "qppvm_b200", "plugin")
@@ -77,9 +77,9 @@ def _write_states(path, T, nv, per_tick):
                 f.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
 
 
-def _run(built, lib, factory, states, out, T, nv, floating, links):
+def _run(built, lib, factory, states, out, T, nv, floating, links, env=None):
     cmd = [os.path.join(built, "plugin_test"), os.path.join(built, lib), factory, states, out, str(T), str(nv), str(int(floating))] + links
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stderr + r.stdout
     return r.stdout, r.stderr
 
@@ -201,3 +201,58 @@ def test_qppvm_plugin_boundary(built, oracle_mod, tmp_path):
     assert (oo["status"] == 0).all()
     assert rel_inf(out[:-1, :n], oo["x"]).max() <= PRIMAL_TOL
     assert rel_inf(eff[:-1], oo["tau"]).max() <= PRIMAL_TOL         # tau_d = tau_qp + h
+
+
+@pytest.mark.gpu
+def test_qppvm_plugin_elbow_and_joint_limit_stack(built, oracle_mod, tmp_path):
+    """QPPVM_PLUGIN_STACK=elbows,joint_limits: the drop-in stacks what the reference only constructs
+    (ref:src/QPPVMPlugin.cpp:154-171, commented stack :177-178): record packing vs numpy, command vs the oracle."""
+    rob = gen.robot_for(29)
+    n, T = 29, 6
+    desc = Desc(kind=KIND_TORQUE, n_a=29, n_contacts=2, flags=FLAG_ELBOW_TASKS | FLAG_JOINT_LIMITS, eps_regularisation=1.0)
+    L = layout(desc)
+    links = ["arm1_7", "arm2_7", "arm1_4", "arm2_4"]
+    bodies = [rob.hand[0], rob.hand[1], rob.hand[0] - 3, rob.hand[1] - 3]
+    q, qd, rpy, R0, p0, v0, w0 = _states(rob, T, 11, False)
+    dyn = rob.dynamics(q, qd, R0, p0, v0, w0, bodies)
+    M = dyn["M"][:, 6:, 6:].copy(); h = dyn["h"][:, 6:].copy()
+    tmax = rob.tau_max * 0.6
+
+    def tick(t):
+        yield from (q[t], qd[t], rob.q_home, M[t], h[t], tmax, np.zeros(3), np.zeros(3), np.eye(3), np.zeros(3))
+        for b in bodies:
+            lk = dyn["links"][b]
+            yield from (lk["J"][t][:, 6:], lk["Jdqd"][t], lk["R"][t], lk["p"][t], lk["J"][t][:, 6:] @ qd[t])
+    _write_states(tmp_path / "s.bin", T, n, tick)
+    stdout, _ = _run(built, "libQPPVMPlugin.so", "QPPVMPlugin_factory", str(tmp_path / "s.bin"), str(tmp_path / "o.bin"), T, n, False, links,
+                     env={"QPPVM_PLUGIN_STACK": "elbows,joint_limits"})
+    per = 3 + n + L.rec_doubles + L.out_doubles
+    o = np.fromfile(tmp_path / "o.bin").reshape(T, per)
+    eff, rec, out = o[:, 3:3 + n], o[:, 3 + n:3 + n + L.rec_doubles], o[:, 3 + n + L.rec_doubles:]
+    assert (o[:, 0] == 0).all()
+    # joint limits: model limits home -+ 0.35 shrunk by 10 % of the range on both sides (:120-123), gains k0 * 10, d0 * 20 (:170)
+    # with the fake robot's k0 = 1600, d0 = 40; elbows: K = 100, D = 1, reference = pose at construction (tick 0)
+    qmin, qmax = rob.q_home - 0.35 + 0.07, rob.q_home + 0.35 - 0.07
+    for t in range(T):
+        np.testing.assert_allclose(rec[t, L.off_jlim:L.off_jlim + n], 16000.0 * (qmin - q[t]) - 800.0 * qd[t], rtol=1e-12, atol=1e-9)
+        np.testing.assert_allclose(rec[t, L.off_jlim + n:L.off_jlim + 2 * n], 16000.0 * (qmax - q[t]) - 800.0 * qd[t], rtol=1e-12, atol=1e-9)
+        for ti, b in enumerate(bodies[2:]):                     # elbow_left + elbow_right (:178)
+            lk = dyn["links"][b]
+            J = lk["J"][t][:, 6:]
+            e = np.concatenate([lk["p"][0] - lk["p"][t], _ori_err(lk["R"][0], lk["R"][t])])
+            np.testing.assert_allclose(rec[t, L.off_jelbow + ti * 6 * n:L.off_jelbow + (ti + 1) * 6 * n], J.ravel(), rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(rec[t, L.off_felbow + 6 * ti:L.off_felbow + 6 * ti + 6], 100.0 * e - 1.0 * (J @ qd[t]), rtol=1e-12, atol=1e-10)
+    oo = oracle_mod.split_out(desc, oracle_mod.solve_batch(desc, rec)[0])
+    assert (oo["status"] == 0).all()
+    ok = oo["kkt"].max(axis=1) <= 1e-6
+    assert ok.sum() >= T - 1
+    # the directions neither a hand nor an elbow row sees are regulariser-defined (eps = 2.2e-13): the commanded torques
+    # agree where the problem pins them -- the task values of both levels -- and within the conditioning bound elsewhere
+    from tests.assemble_np import level_matrices
+    for t in np.nonzero(ok)[0]:
+        A0 = level_matrices(desc, rec[t], 0)[0]
+        A1 = level_matrices(desc, rec[t], 1, out[t, :n])[0]
+        for A in (A0, A1):
+            np.testing.assert_allclose(A @ out[t, :n], A @ oo["x"][t], rtol=0, atol=1e-6 * max(1.0, np.abs(A @ oo["x"][t]).max()))
+    assert rel_inf(out[ok, :n], oo["x"][ok]).max() <= 0.2          # (KKT residual / eps of order one at eps = 2.2e-13)
+    np.testing.assert_allclose(eff, out[:, :n] + h, rtol=0, atol=1e-12)        # tau_d = tau_qp + h (:256)
