@@ -6,6 +6,7 @@
 #include "ForceAccPlugin.h"
 #include "plugin_math.h"
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 REGISTER_XBOT_PLUGIN_(XBotPlugin::ForceAccExample)
@@ -43,7 +44,8 @@ bool XBotPlugin::ForceAccExample::init_control_plugin(XBot::Handle::Ptr handle)
     d.kind = QPPVM_KIND_FORCEACC;
     d.n_a = _model->getJointNum() - 6;
     d.n_contacts = (int)_contact_links.size();
-    d.flags = 0;
+    if (const char* e = std::getenv("FORCEACC_PLUGIN_STACK")) _stack_com = std::strstr(e, "com") != nullptr;
+    d.flags = _stack_com ? QPPVM_FLAG_COM_TASK : 0;
     d.eps_regularisation = 1e4;
     d.n_reg_steps = 1;
     d.max_iter = 132;
@@ -83,6 +85,46 @@ void XBotPlugin::ForceAccExample::on_start(double time)
         _model->getPose(_contact_links[i], _feet_ref[i].pose);
     _model->getPose(floating_base_name, _waist_ref.pose);                            // :162
     _model->getPointPosition(floating_base_name, Eigen::Vector3d::Zero(), _initial_com);   // :164
+    if (_stack_com) {                                                                // the CoM task's reference: where the CoM is now
+        _model->getInertiaMatrix(_M);
+        Eigen::Affine3d Tb;
+        _model->getPose(floating_base_name, Tb);
+        const double m = _M(0, 0);
+        _com_ref[0] = Tb.translation()[0] + _M(1, 5) / m;
+        _com_ref[1] = Tb.translation()[1] + _M(2, 3) / m;
+        _com_ref[2] = Tb.translation()[2] + _M(0, 4) / m;
+    }
+}
+
+// Centroidal dynamics on the contact forces (OpenSoT tasks::force::CoM, ref:src/ForceAcc.cpp:103):
+//   sum f_i = m (lambda (c_ref - c) - lambda2 cdot) + m g z,     sum (p_i - c) x f_i = -lambda2 L_c.
+// Total mass, centre of mass and centroidal momentum are read from the floating-base block of the joint-space inertia
+// matrix (M[0:3,0:3] = m I, M[0:3,3:6] = -m [c - p_base]x in the world-aligned convention of the model) and M[0:6] qdot.
+void XBotPlugin::ForceAccExample::com_task_rows(double* A, double* b) const
+{
+    const int nv = _L.n_v, c = _L.n_c, nf = 3 * c;
+    Eigen::Affine3d Tb, Tc;
+    _model->getPose(floating_base_name, Tb);
+    const double m = _M(0, 0);
+    const double d[3] = {_M(1, 5) / m, _M(2, 3) / m, _M(0, 4) / m};                  // c - p_base
+    double mom[6];
+    for (int r = 0; r < 6; ++r) { double v = 0.0; for (int j = 0; j < nv; ++j) v += _M(r, j) * _qdot[j]; mom[r] = v; }
+    const double Lc[3] = {mom[3] - (d[1] * mom[2] - d[2] * mom[1]), mom[4] - (d[2] * mom[0] - d[0] * mom[2]), mom[5] - (d[0] * mom[1] - d[1] * mom[0])};
+    for (int e = 0; e < 6 * nf; ++e) A[e] = 0.0;
+    for (int i = 0; i < c; ++i) {
+        _model->getPose(_contact_links[i], Tc);
+        double r[3];
+        for (int k = 0; k < 3; ++k) r[k] = Tc.translation()[k] - (Tb.translation()[k] + d[k]);
+        for (int k = 0; k < 3; ++k) A[k * nf + 3 * i + k] = 1.0;
+        A[3 * nf + 3 * i + 1] = -r[2]; A[3 * nf + 3 * i + 2] = r[1];                 // [r]x
+        A[4 * nf + 3 * i + 0] = r[2];  A[4 * nf + 3 * i + 2] = -r[0];
+        A[5 * nf + 3 * i + 0] = -r[1]; A[5 * nf + 3 * i + 1] = r[0];
+    }
+    for (int k = 0; k < 3; ++k) {
+        const double ck = Tb.translation()[k] + d[k];
+        b[k] = m * (_lambda * (_com_ref[k] - ck) - _lambda2 * mom[k] / m) + (k == 2 ? m * 9.81 : 0.0);
+        b[3 + k] = -_lambda2 * Lc[k];
+    }
 }
 
 void XBotPlugin::ForceAccExample::cartesian_rhs(const std::string& link, const CartesianRef& ref,
@@ -134,6 +176,7 @@ void XBotPlugin::ForceAccExample::build_record()
         for (int j = 0; j <= i; ++j) rec[_L.off_M + i * (i + 1) / 2 + j] = _M(i, j);
     _model->computeNonlinearTerm(_h);
     for (int j = 0; j < nv; ++j) rec[_L.off_h + j] = _h[j];
+    if (_stack_com) com_task_rows(rec + _L.off_com, rec + _L.off_com + 6 * 3 * c);
 }
 
 void XBotPlugin::ForceAccExample::control_loop(double time, double period)

@@ -51,6 +51,12 @@ private:
     CartesianRef _waist_ref;
     Eigen::MatrixXd _Jtmp, _M;
     double _lambda = 100.0, _lambda2 = 20.0;       // OpenSoT acceleration-task defaults
+    // _com_task (OpenSoT tasks::force::CoM, ref:src/ForceAcc.cpp:103; member ref:include/ForceAccPlugin/ForceAcc.h): the
+    // reference constructs it and never stacks it.  FORCEACC_PLUGIN_STACK=com adds it to level 1
+    // (_postural_task + feet_cart_aggr + _com_task); unset = the shipped stack.
+    bool _stack_com = false;
+    Eigen::Vector3d _com_ref;                      // centre of mass at on_start (the task's construction-time reference)
+    void com_task_rows(double* A_com, double* b_com) const;
 
     qppvm_handle* _solver = nullptr;
     qppvm_layout _L;

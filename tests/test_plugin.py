@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from qppvm_b200 import gen
-from qppvm_b200.layout import Desc, KIND_TORQUE, FLAG_ELBOW_TASKS, FLAG_JOINT_LIMITS, layout
+from qppvm_b200.layout import Desc, KIND_TORQUE, FLAG_COM_TASK, FLAG_ELBOW_TASKS, FLAG_JOINT_LIMITS, layout
 from tests.helpers import PRIMAL_TOL, rel_inf
 
 PLUG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "qppvm_b200", "plugin")
@@ -85,11 +85,13 @@ def _run(built, lib, factory, states, out, T, nv, floating, links, env=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n_a", (33, 39))                  # 39: the reference's literal shape, n_v = 45 (ref:src/ForceAcc.cpp:58-70)
-def test_forceacc_plugin_boundary(built, oracle_mod, tmp_path, n_a):
+# 39: the reference's literal shape, n_v = 45 (ref:src/ForceAcc.cpp:58-70); "com": FORCEACC_PLUGIN_STACK=com stacks the
+# _com_task the reference only constructs (ref:src/ForceAcc.cpp:103)
+@pytest.mark.parametrize("n_a,stack", ((33, ""), (39, ""), (39, "com")))
+def test_forceacc_plugin_boundary(built, oracle_mod, tmp_path, n_a, stack):
     rob = gen.robot_for(n_a)
     nv, T = n_a + 6, 10
-    desc = Desc(n_a=n_a, n_contacts=4, flags=0)
+    desc = Desc(n_a=n_a, n_contacts=4, flags=FLAG_COM_TASK if stack == "com" else 0)
     L = layout(desc)
     links = ["pelvis", "foot_fl", "foot_fr", "foot_hr", "foot_hl"]
     bodies = [0] + rob.foot + rob.hand
@@ -107,7 +109,8 @@ def test_forceacc_plugin_boundary(built, oracle_mod, tmp_path, n_a):
             yield from (lk["J"][t], lk["Jdqd"][t], lk["R"][t], lk["p"][t], lk["J"][t] @ vfull[t])
     _write_states(tmp_path / "s.bin", T, nv, tick)
     os.environ["QPPVM_TRACE_DIR"] = str(tmp_path)
-    stdout, stderr = _run(built, "libForceAccPlugin.so", "create_instance", str(tmp_path / "s.bin"), str(tmp_path / "o.bin"), T, nv, True, links)
+    stdout, stderr = _run(built, "libForceAccPlugin.so", "create_instance", str(tmp_path / "s.bin"), str(tmp_path / "o.bin"), T, nv, True, links,
+                          env={"FORCEACC_PLUGIN_STACK": stack})
     per = 3 + nv + L.rec_doubles + L.out_doubles
     o = np.fromfile(tmp_path / "o.bin").reshape(T, per)
     status, moved, nerr = o[:, 0], o[:, 1], o[:, 2]
@@ -138,7 +141,23 @@ def test_forceacc_plugin_boundary(built, oracle_mod, tmp_path, n_a):
                 exp[t, L.off_fbox + 6 * c:L.off_fbox + 6 * c + 6] = [-1000, -1000, 10, 1000, 1000, 1000]
         exp[t, L.off_rhs + 30:L.off_rhs + 30 + nv] = 100.0 * (home - qfull[t]) - 20.0 * vfull[t]
         exp[t, L.off_M:L.off_M + nv * (nv + 1) // 2] = gen.pack_lower(M[t]); exp[t, L.off_h:L.off_h + nv] = h[t]
-    np.testing.assert_allclose(rec[:-1], exp[:-1], rtol=1e-12, atol=1e-12)
+        if stack == "com":
+            # sum f_i = m (100 (c_ref - c) - 20 cdot) + m g z, sum (p_i - c) x f_i = -20 L_c, with m, c, momentum from M
+            def com_of(tt):
+                m = M[tt, 0, 0]
+                return m, np.array([M[tt, 1, 5], M[tt, 2, 3], M[tt, 0, 4]]) / m
+            (m, dcm), (_, dcm0) = com_of(t), com_of(0)
+            cpos, cref = dyn["links"][0]["p"][t] + dcm, dyn["links"][0]["p"][0] + dcm0
+            mom = M[t, :6] @ vfull[t]
+            A = np.zeros((6, 12))
+            for ci, b in enumerate(bodies[1:]):
+                r = dyn["links"][b]["p"][t] - cpos
+                A[:3, 3 * ci:3 * ci + 3] = np.eye(3)
+                A[3:, 3 * ci:3 * ci + 3] = np.array([[0, -r[2], r[1]], [r[2], 0, -r[0]], [-r[1], r[0], 0]])
+            bl = m * (100.0 * (cref - cpos) - 20.0 * mom[:3] / m) + np.array([0, 0, m * 9.81])
+            exp[t, L.off_com:L.off_com + 72] = A.ravel()
+            exp[t, L.off_com + 72:L.off_com + 78] = np.concatenate([bl, -20.0 * (mom[3:] - np.cross(dcm, mom[:3]))])
+    np.testing.assert_allclose(rec[:-1], exp[:-1], rtol=1e-12, atol=1e-9)
     # ---- what was commanded == the oracle's answer for that record
     oo = oracle_mod.split_out(desc, oracle_mod.solve_batch(desc, rec[:-1])[0])
     assert (oo["status"] == 0).all()
