@@ -89,6 +89,7 @@ struct qppvm_handle {
     int64_t chunk_states;                  // states per chunk of the state front end (transfers are 10x smaller)
     double* d_state[HOST_STREAMS];         // host-path staging for the state front end
     RobotTables rob; RbdShape rsh; void* rob_blob; bool has_robot;
+    bool rbd_v1; int rbd_smem, rbd_ctas_per_sm;   // front-end kernel choice and launch geometry (set by qppvm_set_robot)
     double* d_roll; int64_t roll_cap;      // record scratch of the on-device rollout: HOST_STREAMS lanes of roll_cap
     cudaEvent_t ev_fork, ev_join[HOST_STREAMS];
     double* d_one_rec; unsigned char* d_one_out;
@@ -669,6 +670,15 @@ int qppvm_set_robot(qppvm_handle* h, const qppvm_robot* r)
     h->rob.parent = di; h->rob.depth = di + nb; h->rob.contact_body = di + 2 * nb;
     for (int i = 0; i < HOST_STREAMS; ++i)
         if (!h->d_state[i]) CU(h, cudaMalloc(&h->d_state[i], sizeof(double) * h->rsh.state_doubles * h->chunk_states));
+    // launch geometry of the warp-per-state front end: RBD_WARPS states per CTA, per-body data in dynamic shared memory
+    h->rbd_v1 = false;
+    if (const char* e = getenv("QPPVM_RBD_V1")) h->rbd_v1 = atoi(e) != 0;
+    h->rbd_smem = (int)(sizeof(double) * RBD_WARPS * rbd_warp_doubles(h->rsh));
+    CU(h, cudaFuncSetAttribute(rbd_records_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->rbd_smem));
+    CU(h, cudaFuncSetAttribute(rbd_records_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int rocc = 0;
+    CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rocc, rbd_records_warp_kernel, 32 * RBD_WARPS, (size_t)h->rbd_smem));
+    h->rbd_ctas_per_sm = rocc < 1 ? 1 : rocc;
     h->has_robot = true;
     return QPPVM_OK;
 }
@@ -676,8 +686,13 @@ int qppvm_set_robot(qppvm_handle* h, const qppvm_robot* r)
 static int launch_rbd(qppvm_handle* h, const double* states, double* recs, int64_t batch, cudaStream_t st)
 {
     if (batch <= 0) return QPPVM_OK;
-    const int grid = (int)((batch + RBD_TEAM - 1) / RBD_TEAM);          // one thread per state
-    rbd_records_kernel<<<grid, RBD_TEAM, 0, st>>>(h->rob, h->rsh, states, recs, (long long)batch);
+    if (h->rbd_v1) {                                                    // QPPVM_RBD_V1=1: the thread-per-state kernel (A/B measurements)
+        const int grid = (int)((batch + RBD_TEAM - 1) / RBD_TEAM);
+        rbd_records_kernel<<<grid, RBD_TEAM, 0, st>>>(h->rob, h->rsh, states, recs, (long long)batch);
+    } else {                                                            // a warp per state, per-body data in shared memory
+        const long long need = (batch + RBD_WARPS - 1) / RBD_WARPS, cap = (long long)h->sm_count * h->rbd_ctas_per_sm;
+        rbd_records_warp_kernel<<<(int)(need < cap ? need : cap), 32 * RBD_WARPS, h->rbd_smem, st>>>(h->rob, h->rsh, states, recs, (long long)batch);
+    }
     CU(h, cudaGetLastError());
     h->launches += 1;
     return QPPVM_OK;

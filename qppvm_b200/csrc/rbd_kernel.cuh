@@ -176,8 +176,11 @@ rbd_records_kernel(RobotTables rob, RbdShape sh, const double* __restrict__ stat
 #pragma unroll 1
     for (int j = nb - 1; j >= 1; --j) {
         const int pa = tParent[j];
+        double cj[16], cp[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) bC[pa][k] += bC[j][k];
+        for (int k = 0; k < 16; ++k) { cj[k] = bC[j][k]; cp[k] = bC[pa][k]; }       // 32 loads in flight, then 16 stores
+#pragma unroll
+        for (int k = 0; k < 16; ++k) bC[pa][k] = cp[k] + cj[k];
     }
     // ---- 3. per column: twist about the world origin (omega | v_O) and the momentum (n | l) of the subtree it moves;
     // M(a,b) = twist_b . momentum_a for related columns (a >= b, column a the deeper one)
@@ -217,12 +220,15 @@ rbd_records_kernel(RobotTables rob, RbdShape sh, const double* __restrict__ stat
 #pragma unroll
         for (int k = 0; k < 6; ++k) Ta[k] = T[a][6 + k];
         const unsigned long long anc_a = a >= 6 ? tAnc[a - 5] : 0ull;
-#pragma unroll 1
+        // (the twists are loaded unconditionally and four columns at a time: the per-thread arrays live in local memory,
+        // i.e. in L2 / DRAM at this footprint, and the kernel is bound by how many of those loads are in flight --
+        // profiles/README.md, round 2: 94 % of the stall samples were long-scoreboard waits with one column per iteration)
+        double* const Mrow = rec + sh.off_M + a * (a + 1) / 2;
+#pragma unroll 4
         for (int b = 0; b <= a; ++b) {
-            const bool related = b < 6 || a == b || ((anc_a >> (b - 6)) & 1ull);     // joint b on the path to body of a
-            double val = 0.0;
-            if (related) val = T[b][0] * Ta[0] + T[b][1] * Ta[1] + T[b][2] * Ta[2] + T[b][3] * Ta[3] + T[b][4] * Ta[4] + T[b][5] * Ta[5];
-            rec[sh.off_M + a * (a + 1) / 2 + b] = val;
+            const bool related = b < 6 || a == b || ((anc_a >> (b < 6 ? 0 : b - 6)) & 1ull);     // joint b on the path to body of a
+            const double val = T[b][0] * Ta[0] + T[b][1] * Ta[1] + T[b][2] * Ta[2] + T[b][3] * Ta[3] + T[b][4] * Ta[4] + T[b][5] * Ta[5];
+            Mrow[b] = related ? val : 0.0;
         }
     }
     // ---- 4. task links: waist (body 0) then the contact links
@@ -235,23 +241,34 @@ rbd_records_kernel(RobotTables rob, RbdShape sh, const double* __restrict__ stat
         double pt[3] = {bp[body][0], bp[body][1], bp[body][2]}, p0[3] = {bp[0][0], bp[0][1], bp[0][2]};
         double jvel[6] = {0, 0, 0, 0, 0, 0};
         double* Jout = rec + (t == 0 ? sh.off_jwaist : sh.off_jc + (t - 1) * 6 * nv);
-#pragma unroll 1
-        for (int col = 0; col < nv; ++col) {
+#pragma unroll
+        for (int col = 0; col < 6; ++col) {                    // floating-base columns
             double jv[3] = {0, 0, 0}, jw[3] = {0, 0, 0};
             if (col < 3) jv[col] = 1.0;
-            else if (col < 6) { double r[3] = {pt[0] - p0[0], pt[1] - p0[1], pt[2] - p0[2]}; jw[col - 3] = 1.0; cross3(jw, r, jv); }
-            else if ((an >> (col - 6)) & 1ull) {
-                const int b = col - 5;
-                double r[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { jw[k] = bz[b][k]; r[k] = pt[k] - bp[b][k]; }
-                cross3(jw, r, jv);
-            }
-            const double vc = col < 6 ? tw[col] : qd[col - 6];
+            else { double r[3] = {pt[0] - p0[0], pt[1] - p0[1], pt[2] - p0[2]}; jw[col - 3] = 1.0; cross3(jw, r, jv); }
+            const double vc = tw[col];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 Jout[r * nv + col] = jv[r]; Jout[(3 + r) * nv + col] = jw[r];
                 jvel[r] = fma(jv[r], vc, jvel[r]); jvel[3 + r] = fma(jw[r], vc, jvel[3 + r]);
+            }
+        }
+        // joint columns: axis and origin of every joint are fetched whether or not it moves this link (loads of four
+        // columns in flight), the ancestor mask selects afterwards
+#pragma unroll 4
+        for (int col = 6; col < nv; ++col) {
+            const int b = col - 5;
+            const bool on = (an >> (col - 6)) & 1ull;
+            double jv[3], jw[3], r[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { jw[k] = bz[b][k]; r[k] = pt[k] - bp[b][k]; }
+            cross3(jw, r, jv);
+            const double vc = qd[col - 6];
+#pragma unroll
+            for (int r2 = 0; r2 < 3; ++r2) {
+                const double v = on ? jv[r2] : 0.0, w = on ? jw[r2] : 0.0;
+                Jout[r2 * nv + col] = v; Jout[(3 + r2) * nv + col] = w;
+                jvel[r2] = fma(v, vc, jvel[r2]); jvel[3 + r2] = fma(w, vc, jvel[3 + r2]);
             }
         }
 #pragma unroll
@@ -288,6 +305,295 @@ rbd_records_kernel(RobotTables rob, RbdShape sh, const double* __restrict__ stat
         }
     if (sh.rec_doubles & 1 || true) {                         // padding double of the record stride
         for (int k = sh.off_fbox + 6 * nc; k < sh.rec_doubles; ++k) rec[k] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-per-state front end (round 2).  The thread-per-state kernel above keeps 17 KB of per-body data per thread in
+// local memory: at any useful batch that footprint lives in L2 / DRAM (ncu: 5.6 GB of DRAM traffic for 1.2 GB of
+// records, 94 % of the stall samples on local loads, issue slots 4 % busy), and because every state is one serial
+// thread a chunk of a few thousand states takes as long as 65 536 (2.6 ms: one wave).  Here one WARP owns a state and
+// the per-body data sits in shared memory (14.6 KB per state for the 33-DoF robot): lanes take the bodies of one tree
+// level (forward kinematics), bodies (inertias), columns (twists / momenta), packed entries of M, Jacobian columns;
+// every store to the record is a coalesced 256-byte row of lanes.  Same arithmetic as above and as gen.py.
+// Per-state block (doubles): state copy | bodies x RBD_BS [R 9 | p 3 | z 3 | w 3 | al 3 | a 3 | C 16] | columns x RBD_TS
+// [omega 3 | v_O 3 | n 3 | l 3].  Odd strides: a lane per body / column walks conflict-free banks.
+// ------------------------------------------------------------------------------------------
+constexpr int RBD_WARPS = 4;       // states in flight per CTA
+constexpr int RBD_BS = 41, RBD_TS = 13;
+__host__ __device__ inline int rbd_state_pad(const RbdShape& sh) { return (sh.state_doubles + 1) & ~1; }
+__host__ __device__ inline int rbd_warp_doubles(const RbdShape& sh) { return rbd_state_pad(sh) + RBD_BS * (sh.n_a + 1) + RBD_TS * sh.n_v + 1; }
+
+__global__ void __launch_bounds__(32 * RBD_WARPS)
+rbd_records_warp_kernel(RobotTables rob, RbdShape sh, const double* __restrict__ states, double* __restrict__ recs, long long batch)
+{
+    __shared__ double tAxis[RBD_MAXB * 3], tOff[RBD_MAXB * 3], tCom[RBD_MAXB * 3], tIn[RBD_MAXB * 3], tMass[RBD_MAXB];
+    __shared__ double tQh[RBD_MAXB], tTm[RBD_MAXB];
+    __shared__ unsigned long long tAnc[RBD_MAXB];
+    __shared__ int tParent[RBD_MAXB], tContact[4], tOrder[RBD_MAXB], tLevel[RBD_MAXB + 2];
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int nb = rob.n_b, nv = sh.n_v, na = sh.n_a, nc = sh.n_c, maxd = rob.max_depth;
+    const double grav = 9.81;
+    for (int i = tid; i < nb * 3; i += 32 * RBD_WARPS) { tAxis[i] = rob.axis[i]; tOff[i] = rob.offset[i]; tCom[i] = rob.com[i]; tIn[i] = rob.inertia[i]; }
+    for (int i = tid; i < nb; i += 32 * RBD_WARPS) { tMass[i] = rob.mass[i]; tAnc[i] = rob.anc[i]; tParent[i] = rob.parent[i]; }
+    for (int i = tid; i < na; i += 32 * RBD_WARPS) { tQh[i] = rob.q_home[i]; tTm[i] = rob.tau_max[i]; }
+    if (tid < 4) tContact[tid] = rob.contact_body[tid];
+    // bodies sorted by tree depth (stable): tOrder, level d occupies [tLevel[d], tLevel[d + 1])
+    for (int i = tid; i < nb; i += 32 * RBD_WARPS) {
+        const int di = rob.depth[i];
+        int rank = 0;
+        for (int j = 0; j < nb; ++j) { const int dj = rob.depth[j]; rank += (dj < di || (dj == di && j < i)) ? 1 : 0; }
+        tOrder[rank] = i;
+    }
+    for (int d = tid; d <= maxd + 1; d += 32 * RBD_WARPS) {
+        int cnt = 0;
+        for (int j = 0; j < nb; ++j) cnt += rob.depth[j] < d ? 1 : 0;
+        tLevel[d] = cnt;
+    }
+    __syncthreads();
+    const int SDP = rbd_state_pad(sh);
+    double* const S = reinterpret_cast<double*>(g_smem) + (size_t)wp * rbd_warp_doubles(sh);
+    double* const Bd = S + SDP;
+    double* const T = Bd + RBD_BS * nb;
+    const double* const q = S + sh.s_q; const double* const qd = S + sh.s_qd; const double* const tw = S + sh.s_tw;
+#pragma unroll 1
+    for (long long idx = (long long)blockIdx.x * RBD_WARPS + wp; idx < batch; idx += (long long)gridDim.x * RBD_WARPS) {
+        const double* st = states + idx * (size_t)sh.state_doubles;
+        double* rec = recs + idx * (size_t)sh.rec_doubles;
+        __syncwarp();                                         // the previous state's readers are done with S / Bd / T
+        for (int k = lane; k < sh.state_doubles; k += 32) S[k] = st[k];
+        __syncwarp();
+        // body 0: the floating base
+        if (lane < 9) Bd[lane] = S[sh.s_R0 + lane];
+        else if (lane < 12) Bd[lane] = S[sh.s_p0 + lane - 9];
+        else if (lane < 15) Bd[lane] = 0.0;                   // z
+        else if (lane < 18) Bd[lane] = tw[3 + lane - 15];     // w
+        else if (lane < 24) Bd[lane] = 0.0;                   // al, a
+        __syncwarp();
+        // ---- 1. forward kinematics, velocities and bias accelerations: one tree level at a time, a lane per body
+#pragma unroll 1
+        for (int d = 1; d <= maxd; ++d) {
+#pragma unroll 1
+            for (int kk = tLevel[d] + lane; kk < tLevel[d + 1]; kk += 32) {
+                const int i = tOrder[kk], pa = tParent[i];
+                const double* P = Bd + RBD_BS * pa;
+                double* Bi = Bd + RBD_BS * i;
+                double Rp[9], ax[3], of[3], r[3], zz[3];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) Rp[k] = P[k];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { ax[k] = tAxis[3 * i + k]; of[k] = tOff[3 * i + k]; }
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    r[a] = Rp[3 * a] * of[0] + Rp[3 * a + 1] * of[1] + Rp[3 * a + 2] * of[2];
+                    zz[a] = Rp[3 * a] * ax[0] + Rp[3 * a + 1] * ax[1] + Rp[3 * a + 2] * ax[2];
+                    Bi[9 + a] = P[9 + a] + r[a];
+                    Bi[12 + a] = zz[a];
+                }
+                double sn, cs;                              // Rodrigues about the unit joint axis: Rot = I + s K + (1 - c) K^2
+                sincos(q[i - 1], &sn, &cs);
+                const double K[9] = {0, -ax[2], ax[1], ax[2], 0, -ax[0], -ax[1], ax[0], 0};
+                double Rot[9];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        const double kq = K[3 * a] * K[b] + K[3 * a + 1] * K[3 + b] + K[3 * a + 2] * K[6 + b];
+                        Rot[3 * a + b] = (a == b ? 1.0 : 0.0) + sn * K[3 * a + b] + (1.0 - cs) * kq;
+                    }
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b)
+                        Bi[3 * a + b] = Rp[3 * a] * Rot[b] + Rp[3 * a + 1] * Rot[3 + b] + Rp[3 * a + 2] * Rot[6 + b];
+                const double qdi = qd[i - 1];
+                const double zq[3] = {zz[0] * qdi, zz[1] * qdi, zz[2] * qdi};
+                double wpar[3], alp[3], c1[3], c2[3], c3[3], c4[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { wpar[k] = P[15 + k]; alp[k] = P[18 + k]; }
+                cross3(wpar, zq, c1);
+                cross3(alp, r, c2);
+                cross3(wpar, r, c3);
+                cross3(wpar, c3, c4);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    Bi[15 + a] = wpar[a] + zq[a];
+                    Bi[18 + a] = alp[a] + c1[a];
+                    Bi[21 + a] = P[21 + a] + c2[a] + c4[a];
+                }
+            }
+            __syncwarp();
+        }
+        // ---- 2. per body: spatial inertia about the world origin (m | m c | I_O) and bias wrench about the origin
+#pragma unroll 1
+        for (int i = lane; i < nb; i += 32) {
+            double* Bi = Bd + RBD_BS * i;
+            double R[9], w[3], al[3], c[3], Iw[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) R[k] = Bi[k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { w[k] = Bi[15 + k]; al[k] = Bi[18 + k]; }
+            const double cm[3] = {tCom[3 * i], tCom[3 * i + 1], tCom[3 * i + 2]};
+            const double In[3] = {tIn[3 * i], tIn[3 * i + 1], tIn[3 * i + 2]};
+            const double m = tMass[i];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) c[a] = R[3 * a] * cm[0] + R[3 * a + 1] * cm[1] + R[3 * a + 2] * cm[2];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b)
+                    Iw[3 * a + b] = R[3 * a] * In[0] * R[3 * b] + R[3 * a + 1] * In[1] * R[3 * b + 1] + R[3 * a + 2] * In[2] * R[3 * b + 2];
+            double t1[3], t2[3], t3[3], Iw_w[3], Iw_al[3], t4[3], fv[3], fw[3], pc[3], mom[3];
+            cross3(al, c, t1);
+            cross3(w, c, t2);
+            cross3(w, t2, t3);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                Iw_w[a] = Iw[3 * a] * w[0] + Iw[3 * a + 1] * w[1] + Iw[3 * a + 2] * w[2];
+                Iw_al[a] = Iw[3 * a] * al[0] + Iw[3 * a + 1] * al[1] + Iw[3 * a + 2] * al[2];
+            }
+            cross3(w, Iw_w, t4);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                pc[a] = Bi[9 + a] + c[a];                         // COM position in the world
+                fv[a] = m * (Bi[21 + a] + t1[a] + t3[a] + (a == 2 ? grav : 0.0));
+                fw[a] = Iw_al[a] + t4[a];
+            }
+            cross3(pc, fv, mom);
+            const double cc = pc[0] * pc[0] + pc[1] * pc[1] + pc[2] * pc[2];
+            double* C = Bi + 24;
+            C[0] = m; C[1] = m * pc[0]; C[2] = m * pc[1]; C[3] = m * pc[2];
+            C[4] = Iw[0] + m * (cc - pc[0] * pc[0]); C[5] = Iw[1] - m * pc[0] * pc[1]; C[6] = Iw[2] - m * pc[0] * pc[2];
+            C[7] = Iw[4] + m * (cc - pc[1] * pc[1]); C[8] = Iw[5] - m * pc[1] * pc[2]; C[9] = Iw[8] + m * (cc - pc[2] * pc[2]);
+            C[10] = fv[0]; C[11] = fv[1]; C[12] = fv[2];
+            C[13] = fw[0] + mom[0]; C[14] = fw[1] + mom[1]; C[15] = fw[2] + mom[2];
+        }
+        __syncwarp();
+        // composites: every body folded into its parent, children in descending index order (fixed order: no atomics);
+        // lane k owns entry k of every body's block, so the sweep needs no synchronisation
+        if (lane < 16) {
+#pragma unroll 1
+            for (int j = nb - 1; j >= 1; --j) Bd[RBD_BS * tParent[j] + 24 + lane] += Bd[RBD_BS * j + 24 + lane];
+        }
+        __syncwarp();
+        // ---- 3. per column: twist about the world origin and the momentum of the subtree it moves; h
+#pragma unroll 1
+        for (int col = lane; col < nv; col += 32) {
+            double om[3] = {0, 0, 0}, vo[3] = {0, 0, 0};
+            const double p0[3] = {Bd[9], Bd[10], Bd[11]};
+            int body = 0;
+            if (col < 3) { vo[0] = col == 0 ? 1.0 : 0.0; vo[1] = col == 1 ? 1.0 : 0.0; vo[2] = col == 2 ? 1.0 : 0.0; }
+            else if (col < 6) { om[0] = col == 3 ? 1.0 : 0.0; om[1] = col == 4 ? 1.0 : 0.0; om[2] = col == 5 ? 1.0 : 0.0; cross3(p0, om, vo); }
+            else {
+                body = col - 5;
+                double pb[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { om[k] = Bd[RBD_BS * body + 12 + k]; pb[k] = Bd[RBD_BS * body + 9 + k]; }
+                cross3(pb, om, vo);
+            }
+            double C[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) C[k] = Bd[RBD_BS * body + 24 + k];
+            const double mc[3] = {C[1], C[2], C[3]};
+            double l[3], n[3], t[3];
+            cross3(om, mc, t);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) l[a] = C[0] * vo[a] + t[a];
+            cross3(mc, vo, t);
+            n[0] = t[0] + C[4] * om[0] + C[5] * om[1] + C[6] * om[2];
+            n[1] = t[1] + C[5] * om[0] + C[7] * om[1] + C[8] * om[2];
+            n[2] = t[2] + C[6] * om[0] + C[8] * om[1] + C[9] * om[2];
+            double* Tc = T + RBD_TS * col;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { Tc[a] = om[a]; Tc[3 + a] = vo[a]; Tc[6 + a] = n[a]; Tc[9 + a] = l[a]; }
+            rec[sh.off_h + col] = om[0] * C[13] + om[1] * C[14] + om[2] * C[15] + vo[0] * C[10] + vo[1] * C[11] + vo[2] * C[12];
+        }
+        __syncwarp();
+        // M(a, b) = twist_b . momentum_a for related columns (a >= b): a lane per packed entry
+        {
+            const int nm = nv * (nv + 1) / 2;
+#pragma unroll 1
+            for (int e = lane; e < nm; e += 32) {
+                int a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);        // row of packed entry e (fixed up below)
+                while (a * (a + 1) / 2 > e) --a;
+                while ((a + 1) * (a + 2) / 2 <= e) ++a;
+                const int b = e - a * (a + 1) / 2;
+                const unsigned long long anc_a = a >= 6 ? tAnc[a - 5] : 0ull;
+                const bool related = b < 6 || a == b || ((anc_a >> (b < 6 ? 0 : b - 6)) & 1ull);
+                const double* Tb = T + RBD_TS * b; const double* Ta = T + RBD_TS * a + 6;
+                const double val = Tb[0] * Ta[0] + Tb[1] * Ta[1] + Tb[2] * Ta[2] + Tb[3] * Ta[3] + Tb[4] * Ta[4] + Tb[5] * Ta[5];
+                rec[sh.off_M + e] = related ? val : 0.0;
+            }
+        }
+        // ---- 4. task links: waist (body 0) then the contact links; a lane per Jacobian column
+        const double* gains = S + sh.s_gains;
+        const double lam_w = 100.0 * gains[0], lam2_w = 20.0 * gains[1], lam_p = 100.0 * gains[2], lam2_p = 20.0 * gains[3];
+#pragma unroll 1
+        for (int t = 0; t <= nc; ++t) {
+            const int body = t == 0 ? 0 : tContact[t - 1];
+            const unsigned long long an = tAnc[body];
+            const double pt[3] = {Bd[RBD_BS * body + 9], Bd[RBD_BS * body + 10], Bd[RBD_BS * body + 11]}, p0[3] = {Bd[9], Bd[10], Bd[11]};
+            double jvel[6] = {0, 0, 0, 0, 0, 0};
+            double* Jout = rec + (t == 0 ? sh.off_jwaist : sh.off_jc + (t - 1) * 6 * nv);
+#pragma unroll 1
+            for (int col = lane; col < nv; col += 32) {
+                double jv[3] = {0, 0, 0}, jw[3] = {0, 0, 0};
+                if (col < 3) { jv[0] = col == 0 ? 1.0 : 0.0; jv[1] = col == 1 ? 1.0 : 0.0; jv[2] = col == 2 ? 1.0 : 0.0; }
+                else if (col < 6) {
+                    const double r[3] = {pt[0] - p0[0], pt[1] - p0[1], pt[2] - p0[2]};
+                    jw[0] = col == 3 ? 1.0 : 0.0; jw[1] = col == 4 ? 1.0 : 0.0; jw[2] = col == 5 ? 1.0 : 0.0;
+                    cross3(jw, r, jv);
+                }
+                else if ((an >> (col - 6)) & 1ull) {
+                    const int b = col - 5;
+                    double r[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { jw[k] = Bd[RBD_BS * b + 12 + k]; r[k] = pt[k] - Bd[RBD_BS * b + 9 + k]; }
+                    cross3(jw, r, jv);
+                }
+                const double vc = col < 6 ? tw[col] : qd[col - 6];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    Jout[r * nv + col] = jv[r]; Jout[(3 + r) * nv + col] = jw[r];
+                    jvel[r] = fma(jv[r], vc, jvel[r]); jvel[3 + r] = fma(jw[r], vc, jvel[3 + r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) jvel[r] += __shfl_xor_sync(0xffffffffu, jvel[r], o);
+            if (lane < 6) {
+                const int r = lane;
+                double jvr = jvel[0];
+#pragma unroll
+                for (int k = 1; k < 6; ++k) jvr = r == k ? jvel[k] : jvr;
+                rec[sh.off_jdqd + 6 * t + r] = r < 3 ? Bd[RBD_BS * body + 21 + r] : Bd[RBD_BS * body + 18 + r - 3];
+                double e;
+                if (t == 0) e = r < 3 ? S[sh.s_wpos + r] : S[sh.s_ori + r - 3];   // reference = initial - 0.1 z (ref:src/ForceAcc.cpp:181)
+                else e = S[sh.s_foot + 6 * (t - 1) + r];
+                rec[sh.off_rhs + 6 * t + r] = (t == 0 ? lam_w : lam_p) * e - (t == 0 ? lam2_w : lam2_p) * jvr;
+            }
+            if (t > 0) {
+                if (sh.flags & QPPVM_FLAG_FRICTION_CONES) {
+                    if (lane < 9) rec[sh.off_cone + 10 * (t - 1) + lane] = Bd[RBD_BS * body + lane];
+                    else if (lane == 9) rec[sh.off_cone + 10 * (t - 1) + 9] = S[sh.s_mu + t - 1];
+                }
+                if (lane < 6) rec[sh.off_fbox + 6 * (t - 1) + lane] = lane < 2 ? -1000.0 : (lane == 2 ? 10.0 : 1000.0);   // ref:src/ForceAcc.cpp:75-76
+            }
+        }
+        // postural right-hand side, torque limits, padding
+        for (int j = lane; j < nv; j += 32) {
+            const double e = j < 6 ? 0.0 : tQh[j - 6] - q[j - 6];
+            const double vc = j < 6 ? tw[j] : qd[j - 6];
+            rec[sh.off_rhs + 6 * (1 + nc) + j] = lam_p * e - lam2_p * vc;
+        }
+        if (sh.flags & QPPVM_FLAG_TORQUE_LIMITS)
+            for (int a = lane; a < na; a += 32) {
+                const double tm = tTm[a] * S[sh.s_tscale + a];
+                rec[sh.off_taulim + a] = -tm;
+                rec[sh.off_taulim + na + a] = tm;
+            }
+        for (int k = sh.off_fbox + 6 * nc + lane; k < sh.rec_doubles; k += 32) rec[k] = 0.0;
     }
 }
 

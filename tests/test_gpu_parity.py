@@ -222,6 +222,21 @@ def test_parity_com_force_task(torch_mod, oracle_mod, flags):
     assert np.abs(gb["x"][:, L.n_v:] - g["x"][:, L.n_v:]).max() > 50.0
 
 
+def test_infeasible_state_of_the_sharded_workload(torch_mod, oracle_mod):
+    """State 696 838 of configs[3] is infeasible (LP-certified in tests/test_oracle_crosscheck.py): kernel and oracle
+    both say so, neighbours in the same launch are unaffected, nothing is commanded for it (ref:src/ForceAcc.cpp:189-193)."""
+    desc = CONFIGS[3]["desc"]
+    L = layout(desc)
+    recs = gen.generate(desc, 5, gen.config_seed(3), start=696836)
+    o = oracle_mod.split_out(desc, oracle_mod.solve_batch(desc, recs)[0])
+    g, _ = _solve_gpu(torch_mod, desc, recs, diag=False)
+    np.testing.assert_array_equal(g["status"], o["status"])
+    assert g["status"].tolist() == [0, 0, 2, 0, 0]
+    assert (g["x"][2] == 0).all() and (g["tau"][2] == 0).all() and not np.isfinite(g["kkt"][2]).any()
+    ok = g["status"] == 0
+    assert rel_inf(g["x"][ok], o["x"][ok]).max() <= PRIMAL_TOL and g["kkt"][ok].max() <= KKT_TOL
+
+
 def test_empty_single_and_ragged_batches(torch_mod, oracle_mod):
     from qppvm_b200 import api
     torch = torch_mod

@@ -138,3 +138,21 @@ def test_hot_started_sequence_matches_cold_solves(oracle_mod):
     rel = np.abs(hot["x"] - cold["x"]).max(axis=1) / np.maximum(1.0, np.abs(cold["x"]).max(axis=1))
     assert rel.max() <= 1e-9 and np.array_equal(hot["active"], cold["active"])
     assert (hot["iters0"] + hot["iters1"]).sum() < (cold["iters0"] + cold["iters1"]).sum()
+
+
+def test_infeasible_state_is_reported_as_such(oracle_mod):
+    """State 696 838 of configs[3] (found by the 2^20-state bench run: 2 of 1 048 576 solves do not converge) has torque
+    limits, friction pyramids and the floating-base dynamics in conflict: HiGHS' LP phase proves the constraint set empty,
+    and the oracle reports INFEASIBLE at level 0 (the kernel does the same: tests/test_gpu_parity.py)."""
+    from scipy.optimize import linprog
+    desc = CONFIGS[3]["desc"]
+    L = layout(desc)
+    rec = gen.generate(desc, 1, gen.config_seed(3), start=696838)
+    o = oracle_mod.split_out(desc, oracle_mod.solve_batch(desc, rec)[0])
+    assert o["status"][0] == 2 and (o["x"] == 0).all() and (o["tau"] == 0).all()      # nothing is commanded (ForceAcc.cpp:189-193)
+    _, _, C, lA, uA, _ = level_matrices(desc, rec[0], 0)
+    eq = lA == uA
+    Aub = np.vstack([C[~eq], -C[~eq]]); bub = np.concatenate([uA[~eq], -lA[~eq]])
+    fin = np.abs(bub) < 1e19
+    r = linprog(np.zeros(L.n_x), A_ub=Aub[fin], b_ub=bub[fin], A_eq=C[eq], b_eq=lA[eq], bounds=[(None, None)] * L.n_x, method="highs")
+    assert r.status == 2

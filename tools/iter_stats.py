@@ -9,6 +9,7 @@ sys.path.insert(0, ".")
 from qppvm_b200 import api, gen, layout  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
+START = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 d = layout.CONFIGS[3]["desc"]
 L = layout.layout(d)
 s = api.Solver(d)
@@ -17,7 +18,7 @@ s.set_robot(rob, (rob.foot + rob.hand)[:d.n_contacts])
 bad_recs, bad_idx = [], []
 it0, it1, nact = [], [], []
 CH = 32768
-for c0 in range(0, B, CH):
+for c0 in range(START, START + B, CH):
     states = torch.from_numpy(gen.generate_states(d, CH, gen.config_seed(3), c0)).cuda()
     recs = s.records_from_states(states)
     out, _ = s.solve_batch(recs)
