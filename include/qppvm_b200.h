@@ -234,7 +234,8 @@ int qppvm_solve_states_host_async(qppvm_handle* h, const double* states_host, vo
  * (ref:src/ForceAcc.cpp:225-226).  A state whose solve failed is left as it is (ref:src/ForceAcc.cpp:189-193).
  * qppvm_rollout_states: `ticks` control periods of front end -> 2-level solve -> integrate, all on `stream`, nothing
  * crossing PCIe; `out` holds the last tick's solutions.  The task references are those the states were created with: the
- * stored errors shrink as the robot moves towards them. */
+ * stored errors shrink as the robot moves towards them.  Each tick of a state starts from the working sets of its previous
+ * tick (the persistent QPOases_sot of the reference hot-starts the same way, ref:src/ForceAcc.cpp:135-137,189). */
 int qppvm_integrate_states(qppvm_handle* h, double* states_dev, const void* out_dev, double dt, int64_t batch, void* stream);
 /* The same plus the tick's records: the task errors stored in the states follow the motion (e <- e - dt v_link -
  * dt^2/2 a_link per task link), which is what keeps multi-tick rollouts closed-loop in the task references;

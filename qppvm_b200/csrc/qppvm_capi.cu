@@ -90,7 +90,8 @@ struct qppvm_handle {
     double* d_state[HOST_STREAMS];         // host-path staging for the state front end
     RobotTables rob; RbdShape rsh; void* rob_blob; bool has_robot;
     bool rbd_v1; int rbd_smem, rbd_ctas_per_sm;   // front-end kernel choice and launch geometry (set by qppvm_set_robot)
-    double* d_roll; int64_t roll_cap;      // record scratch of the on-device rollout: HOST_STREAMS lanes of roll_cap
+    double* d_roll; int64_t roll_cap;
+    uint32_t* d_roll_warm; int64_t roll_warm_cap;   // working sets carried from tick to tick of a rollout (QPPVM_WARM_WORDS per state)      // record scratch of the on-device rollout: HOST_STREAMS lanes of roll_cap
     cudaEvent_t ev_fork, ev_join[HOST_STREAMS];
     double* d_one_rec; unsigned char* d_one_out;
     double* h_one_rec; unsigned char* h_one_out;   // pinned staging for latency mode
@@ -425,6 +426,7 @@ int qppvm_create(const qppvm_desc* d, qppvm_handle** out)
     h->chunk = 2048;      // (configs[2] end to end: 1024 -> 2.62 M, 2048 -> 2.80 M, 4096 -> 2.78 M solves/s; profiles/README.md)
     if (const char* e = getenv("QPPVM_CHUNK")) { const long c = atol(e); if (c >= 64 && c <= (1 << 20)) h->chunk = c; }
     h->chunk_states = 4 * h->chunk;
+    if (const char* e = getenv("QPPVM_CHUNK_STATES")) { const long c = atol(e); if (c >= h->chunk && c <= (1 << 20)) h->chunk_states = c; }
     for (int i = 0; i < HOST_STREAMS; ++i) {
         CUC(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
         CUC(cudaMalloc(&h->d_rec[i], sizeof(double) * L.rec_doubles * h->chunk_states));
@@ -482,7 +484,7 @@ int qppvm_destroy(qppvm_handle* h)
     }
     if (h->one_stream) cudaStreamDestroy(h->one_stream);
     for (int i = 0; i < HOST_STREAMS; ++i) cudaFree(h->d_state[i]);
-    cudaFree(h->rob_blob); cudaFree(h->d_roll);
+    cudaFree(h->rob_blob); cudaFree(h->d_roll); cudaFree(h->d_roll_warm);
     if (h->ev_fork) { cudaEventDestroy(h->ev_fork); for (int i = 0; i < HOST_STREAMS; ++i) cudaEventDestroy(h->ev_join[i]); }
     cudaFree(h->d_one_rec); cudaFree(h->d_one_out);
     cudaFreeHost(h->h_one_rec); cudaFreeHost(h->h_one_out);
@@ -757,6 +759,15 @@ int qppvm_rollout_states(qppvm_handle* h, double* states, void* out, int ticks, 
         CU(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         for (int i = 0; i < HOST_STREAMS; ++i) CU(h, cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
     }
+    // Every tick of a state starts from the working sets its previous tick ended with, which is what the reference gets
+    // from keeping one QPOases_sot alive across control_loop calls (ref:src/ForceAcc.cpp:135-137,189); the first tick is cold.
+    if (batch > h->roll_warm_cap) {
+        CU(h, cudaDeviceSynchronize());
+        cudaFree(h->d_roll_warm); h->d_roll_warm = nullptr; h->roll_warm_cap = 0;
+        CU(h, cudaMalloc(&h->d_roll_warm, sizeof(uint32_t) * QPPVM_WARM_WORDS * (size_t)batch));
+        h->roll_warm_cap = batch;
+    }
+    CU(h, cudaMemsetAsync(h->d_roll_warm, 0, sizeof(uint32_t) * QPPVM_WARM_WORDS * (size_t)batch, st));
     const size_t sd = h->rsh.state_doubles, ob = (size_t)h->L.out_bytes;
     CU(h, cudaEventRecord(h->ev_fork, st));
     int used = 0, w = 0;
@@ -770,7 +781,7 @@ int qppvm_rollout_states(qppvm_handle* h, double* states, void* out, int ticks, 
         for (int t = 0; t < ticks; ++t) {
             int rc = launch_rbd(h, s, rec, n, ws);
             if (rc) return rc;
-            rc = launch(h, rec, o, nullptr, n, ws, w);
+            rc = launch(h, rec, o, nullptr, n, ws, w, true, h->d_roll_warm + c0 * QPPVM_WARM_WORDS);
             if (rc) return rc;
             rc = launch_integrate(h, s, o, rec, dt, n, ws);
             if (rc) return rc;

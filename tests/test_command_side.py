@@ -167,7 +167,14 @@ def test_rollout_matches_cpu_closed_loop(oracle_mod):
         out3, _ = s.solve_batch(r3)
         s.integrate_states(d3, out3, DT, records=r3)
     torch.cuda.synchronize()
-    assert torch.equal(d2, d) and torch.equal(out2, out) and torch.equal(d3, d) and torch.equal(out3, out)
+    # the two cold-started forms agree to the bit; the T-tick rollout starts every tick but the first from the working
+    # sets of the previous one (the hot start of the reference's persistent solver): same minimiser, another pivot
+    # order -- equal within the solver's accuracy, same active set, fewer working-set changes
+    assert torch.equal(d3, d2) and torch.equal(out3, out2)
+    g2 = api.split_out(L, out2.cpu().numpy())
+    assert rel_inf(g["x"], g2["x"]).max() <= 1e-8 and np.array_equal(g["active"], g2["active"])
+    np.testing.assert_allclose(d.cpu().numpy(), d2.cpu().numpy(), rtol=0, atol=1e-10)
+    assert (g["iters0"] + g["iters1"]).mean() < (g2["iters0"] + g2["iters1"]).mean()
 
 
 @pytest.mark.gpu
