@@ -4,7 +4,7 @@ solver stack is not installable here: SURVEY.md 4, 8(c)) -- these fixtures pin t
 regressions and travel to the GPU box; they are not reference outputs.  Every stored solution was
 verified with the independent numpy KKT certificate (tests/qp_ref.py) when it was generated.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [name ...]      (no name: every case)
 """
 import os
 import sys
@@ -14,7 +14,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from qppvm_b200 import gen  # noqa: E402
-from qppvm_b200.layout import CONFIGS, Desc, KIND_TORQUE, layout  # noqa: E402
+from qppvm_b200.layout import CONFIGS, Desc, KIND_TORQUE, FLAG_COM_TASK, FLAG_JOINT_LIMITS, layout  # noqa: E402
 from oracle import oracle  # noqa: E402
 from tests.assemble_np import level_matrices  # noqa: E402
 from tests.qp_ref import kkt_numpy  # noqa: E402
@@ -24,12 +24,17 @@ CASES = {
     "cfg0_qppvm_29dof_2c_cones_taulim": (CONFIGS[0]["desc"], gen.config_seed(0)),
     "cfg2_qppvm_33dof_4c_cones_taulim": (CONFIGS[2]["desc"], gen.config_seed(2)),
     "torque_29dof_fixed_base": (Desc(kind=KIND_TORQUE, n_a=29, n_contacts=2, flags=0, eps_regularisation=1.0), 777),
+    # task library: CoM force task at level 1 with cones + torque limits; torque-domain joint limits
+    "forceacc_29dof_2c_com_cones_taulim": (Desc(n_a=29, n_contacts=2, flags=FLAG_COM_TASK | 3), 781),
+    "torque_29dof_joint_limits": (Desc(kind=KIND_TORQUE, n_a=29, n_contacts=2, flags=FLAG_JOINT_LIMITS, eps_regularisation=1.0), 779),
 }
 N = 12
 
 if __name__ == "__main__":
     here = os.path.dirname(os.path.abspath(__file__))
     for name, (desc, seed) in CASES.items():
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         L = layout(desc)
         recs = gen.generate(desc, N, seed)
         out, dg = oracle.solve_batch(desc, recs, mode=oracle.FACTOR_QR, diag=True)
