@@ -166,7 +166,11 @@ struct Team {
     {
         if (TEAM == 32) __syncwarp(); else __syncthreads();
     }
-    // cross-warp exchange (TEAM > 32 only): red = 2 x WARPS doubles
+    // cross-warp exchange (TEAM > 32 only): red = 2 x WARPS doubles.
+    // sum / argmin end WITHOUT a barrier after the read of `red`: the caller guarantees that every thread passes at
+    // least one team barrier before the next reduction writes the exchange slots again (audited per call site: in the
+    // active-set loop each reduction is followed by a phase that ends with a barrier of its own).  The one barrier
+    // inside also publishes whatever the threads wrote to shared memory before the call.
     __device__ static __forceinline__ double sum(double v, double* red)
     {
         v = warp_sum(v);
@@ -177,7 +181,6 @@ struct Team {
             v = red[0];
 #pragma unroll
             for (int w = 1; w < WARPS; ++w) v += red[w];
-            __syncthreads();
         }
         return v;
     }
@@ -208,7 +211,6 @@ struct Team {
                 const double ov = red[w]; const int oi = (int)red[WARPS + w];
                 if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
             }
-            __syncthreads();
         }
     }
     __device__ static __forceinline__ bool any(bool p)
@@ -1298,6 +1300,25 @@ struct Solver {
         }
         tm::sync();
     }
+    // gs_update plus |dst|^2: the barrier of the team sum is the one that publishes dst (one barrier and one pass over
+    // the vector less than gs_update followed by dot)
+    __device__ static __noinline__ double gs_update_norm(const double* src, double* dst, int k)
+    {
+        QP_BIND
+        double sq = 0.0;
+        for (int i = tid; i < N; i += TEAM) {
+            double s0 = src[i], s1 = 0.0;
+            const double* q = Q1 + i * LDQ;
+            int c = 0;
+#pragma unroll 2
+            for (; c + 1 < k; c += 2) { s0 = fma(-q[c], rr[c], s0); s1 = fma(-q[c + 1], rr[c + 1], s1); }
+            if (c < k) s0 = fma(-q[c], rr[c], s0);
+            const double v = s0 + s1;
+            dst[i] = v;
+            sq = fma(v, v, sq);
+        }
+        return tm::sum(sq, red);
+    }
     __device__ static __forceinline__ void gs_pass(double* v, bool accumulate, int k)
     {
         gs_dots(v, accumulate, k);
@@ -1415,14 +1436,13 @@ struct Solver {
             double nrm2 = ww;
             if (k > 0) {
                 if (sj0 >= 0) gs_dots_sparse(w, sj0, k); else gs_dots(w, false, k);
-                gs_update(w, w2, k);
-                nrm2 = dot(w2, w2);
+                nrm2 = gs_update_norm(w, w2, k);
 #if QPPVM_SELECTIVE_GS
                 if (nrm2 < QPPVM_GS_RATIO * ww)               // Daniel-Gragg-Kaufman-Stewart: a second pass only after cancellation
 #endif
                 {
-                    gs_pass(w2, true, k);                     // CGS2: "twice is enough"
-                    nrm2 = dot(w2, w2);
+                    gs_dots(w2, true, k);                     // CGS2: "twice is enough"
+                    nrm2 = gs_update_norm(w2, w2, k);
                 }
             } else {
                 for (int i = tid; i < N; i += TEAM) w2[i] = w[i];
@@ -1461,9 +1481,8 @@ struct Solver {
                 for (int i = tid; i < N; i += TEAM) u[i] = fma(t, w2[i], u[i]);
                 sp = fma(t, nrm2, sp);
             }
-            tm::sync();
             ++iters;
-            if (t == t2) {                                    // full step: row becomes active
+            if (t == t2) {                                    // full step: row becomes active (every thread writes its own entries)
                 const double inv = rsqrt(nrm2), nr = nrm2 * inv;
                 for (int i = tid; i < N; i += TEAM) Q1[i * LDQ + k] = w2[i] * inv;
                 if (tid < k) { RN[tri(k) + tid] = d1[tid]; RI[tri(k) + tid] = -rr[tid] * inv; }
@@ -1475,6 +1494,7 @@ struct Solver {
                 tm::sync();
                 return QPPVM_STATUS_OK;
             }
+            tm::sync();                                       // lam and u of every thread are final before the sweep reads them
             drop(l, k);                                       // partial step: blocking constraint leaves
             --k; --nai;
         }
@@ -1511,9 +1531,7 @@ struct Solver {
             if (tid < 32 && widx == idx && wkey == v && idx != 0x7fffffff) { red[8] = worst; red[9] = (double)wsgn; red[10] = wb; red[11] = (double)idx; }
             if (tid == 0 && idx == 0x7fffffff) red[11] = -1.0;
             tm::sync();
-            const int r = (int)red[11];
-            tm::sync();
-            return r;
+            return (int)red[11];                               // (red[8 .. 11] are next written by the next scan: barriers in between)
         }
         tm::argmin(v, idx, red);
         if (idx == 0x7fffffff) return -1;
@@ -1536,7 +1554,8 @@ struct Solver {
             whiten(av, 1.0, w);
             const double s = dot(w, u) - lo;
             const int sgn = s > 0.0 ? -1 : 1;
-            if (sgn < 0) { for (int i = tid; i < N; i += TEAM) w[i] = -w[i]; tm::sync(); }
+            if (sgn < 0) for (int i = tid; i < N; i += TEAM) w[i] = -w[i];
+            tm::sync();                                        // (also separates the two reductions: Team::sum)
             const double ww = dot(w, w);
             status = add_constraint(row, sgn, true, -fabs(s), fabs(lo), max_iter, ww, -1);
         }
