@@ -409,8 +409,7 @@ def main():
                 "steps": e2e_steps, "api": "qppvm_solve_batch_host_async + qppvm_host_sync (steps overlap)"}
 
     # ---- end to end from compact STATES: rigid-body front end + solve on the device; the host
-    # ships 1 KB states instead of 11-18 KB records.  Extra leg, not the headline `e2e` (whose inputs are records,
-    # i.e. what the reference's plugin hands to OpenSoT after model->update()).
+    # ships 1 KB states instead of 11-18 KB records.  This is the headline `e2e` at every N (see the end of main).
     e2e_states = None
     if desc.kind == 1:
         h_states = torch.from_numpy(h_states_all).pin_memory()
@@ -535,9 +534,13 @@ def main():
     e2e_records = {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": hb * L.rec_doubles * 8,
                    "d2h_bytes_per_step": hb * L.out_bytes, "steps": e2e_steps, "records_per_step_per_gpu": hb,
                    "api": "qppvm_solve_batch_host (records in pinned host buffers in, outputs out)"}
-    # headline e2e: the sharded 2^20-state workload ships compact states (records from a single root are
-    # egress / PCIe bound); the single-GPU workload ships the records the reference's plugin hands to OpenSoT
-    if strong and e2e_states:
+    # headline e2e, the same call at every N: compact states in, torques out (qppvm_solve_states_host) -- what one
+    # control_loop tick does between sense() and move() (ref:src/ForceAcc.cpp:167-253: model update, stack update, solve,
+    # torque recovery), batched.  The reference arm only times the QP part of that tick, from records: the comparison is
+    # conservative.  The record path (the boundary after model->update(), 11-18 KB per problem over PCIe; host-DRAM
+    # bound with 8 processes on one box) is reported beside it as `e2e_records`.  Shapes without a rigid-body front
+    # end (Torque kind) ship records.
+    if e2e_states:
         e2e_head = {k: e2e_states[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "steps", "api")}
     else:
         e2e_head = e2e_records

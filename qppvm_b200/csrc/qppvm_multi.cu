@@ -21,6 +21,9 @@
 #include <new>
 #include "../../include/qppvm_b200.h"
 
+#ifndef QPPVM_MULTI_ROOT_SHARE_DEFAULT
+#define QPPVM_MULTI_ROOT_SHARE_DEFAULT 1.0      // tuned on 8 GPUs: see profiles/README.md
+#endif
 namespace {
 
 constexpr int MAX_DEV = 16;
@@ -54,6 +57,7 @@ struct qppvm_multi {
     unsigned char* out[MAX_DEV][NBUF];
     cudaEvent_t ev_recv[MAX_DEV][NBUF], ev_solved[MAX_DEV][NBUF], ev_sent[MAX_DEV][NBUF], ev_root;
     int64_t chunk;                                  // records per pipeline chunk and GPU
+    double root_share;                              // device-root form: the root's block relative to an equal share (QPPVM_MULTI_ROOT_SHARE)
     int64_t nccl_calls;
     char err[512];
 };
@@ -111,6 +115,20 @@ inline void block_of(int64_t batch, int n, int r, int64_t* lo, int64_t* hi)
     *lo = batch * r / n;
     *hi = batch * (r + 1) / n;
 }
+// The same with the root's block scaled by `share` (device-root form: the root GPU also feeds every other GPU, its copy
+// kernels and HBM reads compete with its own solves, so an equal split makes it the straggler); the other GPUs split the
+// rest evenly.  Problems are independent: the split does not change a single output bit.
+inline void block_of_root(int64_t batch, int n, int r, double share, int64_t* lo, int64_t* hi)
+{
+    if (n == 1 || share == 1.0) { block_of(batch, n, r, lo, hi); return; }
+    int64_t b0 = (int64_t)(share * (double)(batch / n));
+    if (b0 < 0) b0 = 0;
+    if (b0 > batch) b0 = batch;
+    const int64_t rest = batch - b0;
+    if (r == 0) { *lo = 0; *hi = b0; return; }
+    *lo = b0 + rest * (r - 1) / (n - 1);
+    *hi = b0 + rest * r / (n - 1);
+}
 
 }  // namespace
 
@@ -158,8 +176,14 @@ int qppvm_multi_create(const qppvm_desc* desc, const int32_t* devices, int n_dev
             if (m->dev[q] == m->dev[r]) { mfail(nullptr, QPPVM_ERR_ARG, "device %d listed twice", m->dev[r]); qppvm_multi_destroy(m); return QPPVM_ERR_ARG; }
     }
     if (qppvm_get_layout(desc, &m->L)) { mfail(nullptr, QPPVM_ERR_ARG, "invalid problem description"); qppvm_multi_destroy(m); return QPPVM_ERR_ARG; }
-    m->chunk = 32768;                               // = one prepare-workspace pass of the per-GPU handles
+    // records per pipeline chunk: large chunks make efficient solve launches (pass-size sweep in profiles/README.md), small
+    // ones shorten the fill and drain of the scatter pipeline.  Measured on 8 GPUs, where the root's NVLink egress is the
+    // bound (~330 GB/s through grouped ncclSend, 18.6 GB per 2^20-record batch): 16 384 -> 51-54 ms, 32 768 -> 54-57 ms,
+    // 65 536 -> 62 ms per batch; on 2 GPUs (solve-bound) 32 768 wins.
+    m->chunk = n_devices >= 8 ? 16384 : 32768;
     if (const char* e = getenv("QPPVM_MULTI_CHUNK")) { const long c = atol(e); if (c >= 256 && c <= (1 << 20)) m->chunk = c; }
+    m->root_share = QPPVM_MULTI_ROOT_SHARE_DEFAULT;
+    if (const char* e = getenv("QPPVM_MULTI_ROOT_SHARE")) { const double v = atof(e); if (v >= 0.0 && v <= 1.0) m->root_share = v; }
 #define MCC(call)                                                                                       \
     do {                                                                                                \
         cudaError_t e_ = (call);                                                                        \
@@ -249,14 +273,14 @@ int qppvm_multi_solve_batch(qppvm_multi* m, const double* rec_root, void* out_ro
     MCU(m, cudaStreamWaitEvent(m->s_solve[0], m->ev_root, 0));
     MCU(m, cudaStreamWaitEvent(m->s_gather[0], m->ev_root, 0));
     int64_t lo0, hi0;
-    block_of(batch, n, 0, &lo0, &hi0);
+    block_of_root(batch, n, 0, m->root_share, &lo0, &hi0);
     if (n == 1) {
         const int rc = qppvm_solve_batch(m->h[0], rec_root, out_root, batch, m->s_solve[0]);
         if (rc) return mfail(m, rc, "device %d: %s", m->dev[0], qppvm_last_error(m->h[0]));
     }
     if (n > 1) {
         int64_t maxblk = hi0 - lo0;
-        for (int r = 1; r < n; ++r) { int64_t lo, hi; block_of(batch, n, r, &lo, &hi); if (hi - lo > maxblk) maxblk = hi - lo; }
+        for (int r = 1; r < n; ++r) { int64_t lo, hi; block_of_root(batch, n, r, m->root_share, &lo, &hi); if (hi - lo > maxblk) maxblk = hi - lo; }
         const int64_t nchunks = (maxblk + m->chunk - 1) / m->chunk;
         // software pipeline over chunk index c: scatter(c), solve(c), gather(c) are enqueued in that order, each on its own
         // stream per GPU; the hardware overlaps scatter(c + 1) and gather(c - 1) with solve(c)
@@ -266,7 +290,7 @@ int qppvm_multi_solve_batch(qppvm_multi* m, const double* rec_root, void* out_ro
             MNC(m, m->nccl.GroupStart());
             for (int r = 1; r < n; ++r) {
                 int64_t lo, hi;
-                block_of(batch, n, r, &lo, &hi);
+                block_of_root(batch, n, r, m->root_share, &lo, &hi);
                 const int64_t c0 = lo + c * m->chunk;
                 if (c0 >= hi) continue;
                 const int64_t cn = hi - c0 < m->chunk ? hi - c0 : m->chunk;
@@ -297,7 +321,7 @@ int qppvm_multi_solve_batch(qppvm_multi* m, const double* rec_root, void* out_ro
             }
             for (int r = 1; r < n; ++r) {
                 int64_t lo, hi;
-                block_of(batch, n, r, &lo, &hi);
+                block_of_root(batch, n, r, m->root_share, &lo, &hi);
                 const int64_t c0 = lo + c * m->chunk;
                 if (c0 >= hi) continue;
                 const int64_t cn = hi - c0 < m->chunk ? hi - c0 : m->chunk;
@@ -317,7 +341,7 @@ int qppvm_multi_solve_batch(qppvm_multi* m, const double* rec_root, void* out_ro
             MNC(m, m->nccl.GroupStart());
             for (int r = 1; r < n; ++r) {
                 int64_t lo, hi;
-                block_of(batch, n, r, &lo, &hi);
+                block_of_root(batch, n, r, m->root_share, &lo, &hi);
                 const int64_t c0 = lo + c * m->chunk;
                 if (c0 >= hi) continue;
                 const int64_t cn = hi - c0 < m->chunk ? hi - c0 : m->chunk;
@@ -330,7 +354,7 @@ int qppvm_multi_solve_batch(qppvm_multi* m, const double* rec_root, void* out_ro
             MNC(m, m->nccl.GroupEnd());
             for (int r = 1; r < n; ++r) {
                 int64_t lo, hi;
-                block_of(batch, n, r, &lo, &hi);
+                block_of_root(batch, n, r, m->root_share, &lo, &hi);
                 if (lo + c * m->chunk >= hi) continue;
                 MCU(m, cudaSetDevice(m->dev[r]));
                 MCU(m, cudaEventRecord(m->ev_sent[r][b], m->s_gather[r]));
