@@ -221,6 +221,18 @@ def run_multi(args):
         o = api.split_out(L, out[:65536].cpu().numpy())
         good = float(((o["status"] == 0) & (o["kkt"].max(axis=1) <= 1e-6)).mean())
         entry = {"root_resident_solves_per_s": B * good / dt, "ms_per_step": dt * 1e3, "nccl_calls_per_step": m.nccl_calls // (steps + 2)}
+        # the same with the compact states on the root GPU: the states travel, every GPU runs the front end on its chunks
+        dst = torch.from_numpy(st).cuda()
+        for _ in range(2):
+            m.solve_states(dst, out=out)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            m.solve_states(dst, out=out)
+        dts = (time.perf_counter() - t0) / steps
+        o = api.split_out(L, out[:65536].cpu().numpy())
+        good_s = float(((o["status"] == 0) & (o["kkt"].max(axis=1) <= 1e-6)).mean())
+        entry["root_states_solves_per_s"] = B * good_s / dts
+        del dst
         hst = torch.from_numpy(st).pin_memory()
         hout = torch.empty((B, L.out_doubles), dtype=torch.float64).pin_memory()
         m.solve_states_host_ptr(hst.data_ptr(), hout.data_ptr(), B)
@@ -238,13 +250,14 @@ def run_multi(args):
             del hrec
         res["gpus_%d" % g] = entry
         m.close()
-    line = {"leg": "multi_gpu_single_process", "api": "qppvm_multi_solve_batch / _solve_states_host / _solve_batch_host",
+    line = {"leg": "multi_gpu_single_process", "api": "qppvm_multi_solve_batch / _solve_states / _solve_states_host / _solve_batch_host",
             "workload": "configs[3]: %d states, 33-DoF, 4 contacts, cones + tau limits" % B, "gpus": G, "steps": steps,
             "results": res}
     if G > 1:
         a, b = res["gpus_1"], res["gpus_%d" % G]
         line["scatter_gather_efficiency_vs_1gpu"] = b["root_resident_solves_per_s"] / (G * a["root_resident_solves_per_s"])
         line["host_states_efficiency_vs_1gpu"] = b["host_states_solves_per_s"] / (G * a["host_states_solves_per_s"])
+        line["root_states_efficiency_vs_1gpu"] = b["root_states_solves_per_s"] / (G * a["root_states_solves_per_s"])
     print(json.dumps(line), flush=True)
 
 

@@ -250,7 +250,9 @@ int qppvm_rollout_states(qppvm_handle* h, double* states_dev, void* out_dev, int
  * (NULL: 0 .. n - 1), devices[0] is the root.  qppvm_multi_solve_batch: records and outputs on the ROOT GPU; the other
  * GPUs' blocks travel by grouped ncclSend / ncclRecv (ncclCommInitAll, NVLink / NVSwitch), in chunks, so that the scatter of
  * chunk i + 1 and the gather of chunk i - 1 overlap the solve of chunk i; outputs land directly in their place in
- * `out_root_dev`.  Synchronous.  The *_host forms take host (pinned) buffers: every GPU moves its own block over its own
+ * `out_root_dev`.  Synchronous.  qppvm_multi_solve_states: the same with compact STATES on the root GPU (after
+ * qppvm_multi_set_robot): the states travel (1 KB instead of 11-18 KB per problem, so the root's NVLink egress is no longer
+ * the bound) and every GPU runs the rigid-body front end on its chunk before the solve.  The *_host forms take host (pinned) buffers: every GPU moves its own block over its own
  * PCIe link, no GPU-to-GPU traffic.  Results are bitwise those of one GPU. */
 typedef struct qppvm_multi qppvm_multi;
 int qppvm_multi_create(const qppvm_desc* desc, const int32_t* devices, int n_devices, qppvm_multi** out);
@@ -259,6 +261,7 @@ const char* qppvm_multi_last_error(const qppvm_multi* m);
 int qppvm_multi_devices(const qppvm_multi* m);
 int qppvm_multi_set_robot(qppvm_multi* m, const qppvm_robot* robot);
 int qppvm_multi_solve_batch(qppvm_multi* m, const double* records_root_dev, void* out_root_dev, int64_t batch);
+int qppvm_multi_solve_states(qppvm_multi* m, const double* states_root_dev, void* out_root_dev, int64_t batch);
 int qppvm_multi_solve_batch_host(qppvm_multi* m, const double* records_host, void* out_host, int64_t batch);
 int qppvm_multi_solve_states_host(qppvm_multi* m, const double* states_host, void* out_host, int64_t batch);
 int64_t qppvm_multi_kernel_launches(const qppvm_multi* m);

@@ -42,7 +42,7 @@ EXPORTS = ("qppvm_get_layout", "qppvm_create", "qppvm_destroy", "qppvm_last_erro
            "qppvm_records_from_states", "qppvm_solve_states_host", "qppvm_solve_batch_host_async", "qppvm_host_sync",
            "qppvm_solve_states_host_async", "qppvm_integrate_states", "qppvm_rollout_states", "qppvm_solve_batch_warm", "qppvm_reset_warm", "qppvm_tick_stamps",
            "qppvm_reserve_sms", "qppvm_kernel_timing", "qppvm_integrate_states_tracking", "qppvm_multi_create", "qppvm_multi_destroy", "qppvm_multi_last_error", "qppvm_multi_devices",
-           "qppvm_multi_set_robot", "qppvm_multi_solve_batch", "qppvm_multi_solve_batch_host",
+           "qppvm_multi_set_robot", "qppvm_multi_solve_batch", "qppvm_multi_solve_states", "qppvm_multi_solve_batch_host",
            "qppvm_multi_solve_states_host", "qppvm_multi_kernel_launches", "qppvm_multi_nccl_calls")
 
 _lib = None
@@ -78,6 +78,7 @@ def load_library():
         lib.qppvm_multi_set_robot.argtypes = [P, C.POINTER(CRobot)]
         lib.qppvm_multi_solve_batch.argtypes = [P, P, P, C.c_int64]
         lib.qppvm_multi_solve_batch_host.argtypes = [P, P, P, C.c_int64]
+        lib.qppvm_multi_solve_states.argtypes = [P, P, P, C.c_int64]
         lib.qppvm_multi_solve_states_host.argtypes = [P, P, P, C.c_int64]
         lib.qppvm_multi_kernel_launches.argtypes = [P]
         lib.qppvm_multi_kernel_launches.restype = C.c_int64
@@ -370,6 +371,18 @@ class MultiSolver:
             out = torch.empty((records.shape[0], L.out_doubles), dtype=torch.float64, device=records.device)
         torch.cuda.current_stream(records.device).synchronize()
         self._check(self._lib.qppvm_multi_solve_batch(self._m, records.data_ptr(), out.data_ptr(), records.shape[0]))
+        return out
+
+    def solve_states(self, states, out=None):
+        """states: float64 CUDA tensor (batch, state_doubles) on the ROOT device; the states are what NCCL scatters,
+        every GPU runs the rigid-body front end on its chunks (after set_robot); synchronous."""
+        import torch
+        L = self.layout
+        assert states.is_cuda and states.device.index == self.devices[0] and states.dtype == torch.float64 and states.is_contiguous()
+        if out is None:
+            out = torch.empty((states.shape[0], L.out_doubles), dtype=torch.float64, device=states.device)
+        torch.cuda.current_stream(states.device).synchronize()
+        self._check(self._lib.qppvm_multi_solve_states(self._m, states.data_ptr(), out.data_ptr(), states.shape[0]))
         return out
 
     def solve_batch_host_ptr(self, rec_ptr: int, out_ptr: int, batch: int):

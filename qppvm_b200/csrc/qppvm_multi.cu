@@ -54,6 +54,10 @@ struct qppvm_multi {
     bool have_comms;
     cudaStream_t s_scatter[MAX_DEV], s_solve[MAX_DEV], s_gather[MAX_DEV];
     double* rec[MAX_DEV][NBUF];                     // staging on the non-root GPUs, NBUF chunks deep
+    double* st[MAX_DEV][NBUF];                      // states form: the scattered compact states (allocated by set_robot)
+    double* rec0;                                   // states form: the root's records of one chunk
+    int state_doubles;                              // 0 until qppvm_multi_set_robot
+    qppvm_desc desc;
     unsigned char* out[MAX_DEV][NBUF];
     cudaEvent_t ev_recv[MAX_DEV][NBUF], ev_solved[MAX_DEV][NBUF], ev_sent[MAX_DEV][NBUF], ev_root;
     int64_t chunk;                                  // records per pipeline chunk and GPU
@@ -145,7 +149,7 @@ int qppvm_multi_destroy(qppvm_multi* m)
         if (m->s_scatter[r]) { cudaStreamSynchronize(m->s_scatter[r]); cudaStreamSynchronize(m->s_solve[r]); cudaStreamSynchronize(m->s_gather[r]); }
         if (m->have_comms) { m->nccl.CommDestroy(m->scatter[r]); m->nccl.CommDestroy(m->gather[r]); }
         for (int b = 0; b < NBUF; ++b) {
-            cudaFree(m->rec[r][b]); cudaFree(m->out[r][b]);
+            cudaFree(m->rec[r][b]); cudaFree(m->out[r][b]); cudaFree(m->st[r][b]);
             if (m->ev_recv[r][b]) cudaEventDestroy(m->ev_recv[r][b]);
             if (m->ev_solved[r][b]) cudaEventDestroy(m->ev_solved[r][b]);
             if (m->ev_sent[r][b]) cudaEventDestroy(m->ev_sent[r][b]);
@@ -154,6 +158,7 @@ int qppvm_multi_destroy(qppvm_multi* m)
         if (m->h[r]) qppvm_destroy(m->h[r]);
     }
     if (m->ev_root) { cudaSetDevice(m->dev[0]); cudaEventDestroy(m->ev_root); }
+    if (m->rec0) { cudaSetDevice(m->dev[0]); cudaFree(m->rec0); }
     delete m;
     return QPPVM_OK;
 }
@@ -168,6 +173,7 @@ int qppvm_multi_create(const qppvm_desc* desc, const int32_t* devices, int n_dev
     if (!m) return mfail(nullptr, QPPVM_ERR_ARG, "out of memory");
     memset(m, 0, sizeof(*m));
     m->n = n_devices;
+    m->desc = *desc;
     DevGuard guard;
     for (int r = 0; r < n_devices; ++r) {
         m->dev[r] = devices ? devices[r] : r;
@@ -254,17 +260,36 @@ int qppvm_multi_set_robot(qppvm_multi* m, const qppvm_robot* robot)
         const int rc = qppvm_set_robot(m->h[r], robot);
         if (rc) return mfail(m, rc, "device %d: %s", m->dev[r], qppvm_last_error(m->h[r]));
     }
+    // staging of the device-root states form (qppvm_multi_solve_states): the scattered states on every other GPU, the
+    // root's records of one chunk -- allocated here, once, so that nothing is allocated on the solve path
+    if (!m->state_doubles) {
+        const int sd = qppvm_state_doubles(&m->desc);
+        if (sd <= 0) return mfail(m, QPPVM_ERR_UNSUPPORTED, "the state front end covers the ForceAcc kind only");
+        DevGuard guard;
+        for (int r = 1; r < m->n; ++r) {
+            MCU(m, cudaSetDevice(m->dev[r]));
+            for (int b = 0; b < NBUF; ++b) MCU(m, cudaMalloc(&m->st[r][b], sizeof(double) * (size_t)sd * m->chunk));
+        }
+        MCU(m, cudaSetDevice(m->dev[0]));
+        MCU(m, cudaMalloc(&m->rec0, sizeof(double) * (size_t)m->L.rec_doubles * m->chunk));
+        m->state_doubles = sd;
+    }
     return QPPVM_OK;
 }
 
-// Records and outputs live on the root GPU (devices[0]); synchronous: returns when `out_root` is complete.
-int qppvm_multi_solve_batch(qppvm_multi* m, const double* rec_root, void* out_root, int64_t batch)
+// Inputs and outputs live on the root GPU (devices[0]); synchronous: returns when `out_root` is complete.
+// states == false: `in_root` holds records.  states == true: compact states (qppvm_state_doubles each); they are what
+// travels (1 KB instead of 11-18 KB per problem: the root's NVLink egress stops being the bound), and
+// every GPU runs the rigid-body front end on its own chunk before the solve.
+static int multi_root(qppvm_multi* m, const double* in_root, void* out_root, int64_t batch, bool states)
 {
     if (!m) return QPPVM_ERR_ARG;
-    if (batch < 0 || (batch > 0 && (!rec_root || !out_root))) return mfail(m, QPPVM_ERR_ARG, "bad batch arguments");
+    if (batch < 0 || (batch > 0 && (!in_root || !out_root))) return mfail(m, QPPVM_ERR_ARG, "bad batch arguments");
+    if (states && !m->state_doubles) return mfail(m, QPPVM_ERR_ARG, "qppvm_multi_set_robot has not been called");
     if (batch == 0) return QPPVM_OK;
     DevGuard guard;
-    const size_t rd = (size_t)m->L.rec_doubles, ob = (size_t)m->L.out_bytes;
+    const size_t rd = states ? (size_t)m->state_doubles : (size_t)m->L.rec_doubles, ob = (size_t)m->L.out_bytes;
+    const double* const rec_root = in_root;
     const int n = m->n;
     // the caller's work on the root device (default stream) comes first
     MCU(m, cudaSetDevice(m->dev[0]));
@@ -274,9 +299,20 @@ int qppvm_multi_solve_batch(qppvm_multi* m, const double* rec_root, void* out_ro
     MCU(m, cudaStreamWaitEvent(m->s_gather[0], m->ev_root, 0));
     int64_t lo0, hi0;
     block_of_root(batch, n, 0, m->root_share, &lo0, &hi0);
+    // one chunk on one GPU: [front end ->] solve, in stream order
+    auto solve_chunk = [&](int r, const double* in, double* recs, void* out, int64_t cn) -> int {
+        if (states) {
+            const int rc = qppvm_records_from_states(m->h[r], in, recs, cn, m->s_solve[r]);
+            if (rc) return rc;
+        }
+        return qppvm_solve_batch(m->h[r], states ? recs : in, out, cn, m->s_solve[r]);
+    };
     if (n == 1) {
-        const int rc = qppvm_solve_batch(m->h[0], rec_root, out_root, batch, m->s_solve[0]);
-        if (rc) return mfail(m, rc, "device %d: %s", m->dev[0], qppvm_last_error(m->h[0]));
+        for (int64_t c0 = 0; c0 < batch; c0 += states ? m->chunk : batch) {
+            const int64_t cn = states ? (batch - c0 < m->chunk ? batch - c0 : m->chunk) : batch;
+            const int rc = solve_chunk(0, rec_root + c0 * rd, m->rec0, (unsigned char*)out_root + c0 * ob, cn);
+            if (rc) return mfail(m, rc, "device %d: %s", m->dev[0], qppvm_last_error(m->h[0]));
+        }
     }
     if (n > 1) {
         int64_t maxblk = hi0 - lo0;
@@ -303,7 +339,7 @@ int qppvm_multi_solve_batch(qppvm_multi* m, const double* rec_root, void* out_ro
                     MCU(m, cudaStreamWaitEvent(m->s_scatter[0], m->ev_solved[r][b], 0));
                     MCU(m, cudaSetDevice(m->dev[r]));
                 }
-                MNC(m, m->nccl.Recv(m->rec[r][b], (size_t)cn * rd, ncclDouble, 0, m->scatter[r], m->s_scatter[r]));
+                MNC(m, m->nccl.Recv(states ? m->st[r][b] : m->rec[r][b], (size_t)cn * rd, ncclDouble, 0, m->scatter[r], m->s_scatter[r]));
                 MCU(m, cudaSetDevice(m->dev[0]));
                 MNC(m, m->nccl.Send(rec_root + c0 * rd, (size_t)cn * rd, ncclDouble, r, m->scatter[0], m->s_scatter[0]));
                 m->nccl_calls += 2;
@@ -315,7 +351,7 @@ int qppvm_multi_solve_batch(qppvm_multi* m, const double* rec_root, void* out_ro
                 const int64_t c0 = lo0 + c * m->chunk;
                 if (c0 < hi0) {
                     const int64_t cn = hi0 - c0 < m->chunk ? hi0 - c0 : m->chunk;
-                    const int rc = qppvm_solve_batch(m->h[0], rec_root + c0 * rd, (unsigned char*)out_root + c0 * ob, cn, m->s_solve[0]);
+                    const int rc = solve_chunk(0, rec_root + c0 * rd, m->rec0, (unsigned char*)out_root + c0 * ob, cn);
                     if (rc) return mfail(m, rc, "device %d: %s", m->dev[0], qppvm_last_error(m->h[0]));
                 }
             }
@@ -329,7 +365,7 @@ int qppvm_multi_solve_batch(qppvm_multi* m, const double* rec_root, void* out_ro
                 MCU(m, cudaEventRecord(m->ev_recv[r][b], m->s_scatter[r]));
                 MCU(m, cudaStreamWaitEvent(m->s_solve[r], m->ev_recv[r][b], 0));
                 if (c >= NBUF) MCU(m, cudaStreamWaitEvent(m->s_solve[r], m->ev_sent[r][b], 0));       // output buffer b has been gathered
-                const int rc = qppvm_solve_batch(m->h[r], m->rec[r][b], m->out[r][b], cn, m->s_solve[r]);
+                const int rc = solve_chunk(r, states ? m->st[r][b] : m->rec[r][b], m->rec[r][b], m->out[r][b], cn);
                 if (rc) return mfail(m, rc, "device %d: %s", m->dev[r], qppvm_last_error(m->h[r]));
                 MCU(m, cudaEventRecord(m->ev_solved[r][b], m->s_solve[r]));
                 MCU(m, cudaStreamWaitEvent(m->s_gather[r], m->ev_solved[r][b], 0));
@@ -368,6 +404,16 @@ int qppvm_multi_solve_batch(qppvm_multi* m, const double* rec_root, void* out_ro
         MCU(m, cudaStreamSynchronize(m->s_gather[r]));
     }
     return QPPVM_OK;
+}
+
+int qppvm_multi_solve_batch(qppvm_multi* m, const double* rec_root, void* out_root, int64_t batch)
+{
+    return multi_root(m, rec_root, out_root, batch, false);
+}
+
+int qppvm_multi_solve_states(qppvm_multi* m, const double* states_root, void* out_root, int64_t batch)
+{
+    return multi_root(m, states_root, out_root, batch, true);
 }
 
 // Host buffers (pinned for full speed): every GPU moves its own block over its own PCIe link; no GPU-to-GPU traffic.

@@ -59,6 +59,12 @@ def test_sharded_solve_is_bitwise_the_single_gpu_solve(torch_mod, monkeypatch, b
         hst = torch.from_numpy(st).pin_memory()
         m.solve_states_host_ptr(hst.data_ptr(), hout.data_ptr(), batch)
         assert torch.equal(hout, ref.cpu())
+        # states on the root GPU: they are what NCCL scatters, every GPU runs the front end on its chunks
+        nc0 = m.nccl_calls
+        out_s = m.solve_states(torch.from_numpy(st).cuda())
+        assert torch.equal(out_s, ref), "states form, devices %s" % devices
+        if len(devices) > 1:
+            assert m.nccl_calls > nc0
         m.close()
 
 
@@ -67,5 +73,9 @@ def test_multi_rejects_bad_arguments(torch_mod):
     desc = CONFIGS[1]["desc"]
     with pytest.raises(api.QPError):
         api.MultiSolver(desc, [0, 0])
+    m = api.MultiSolver(CONFIGS[2]["desc"], [0])
+    with pytest.raises(api.QPError):                       # the states form needs the robot tables
+        m.solve_states(torch_mod.zeros((4, 128), dtype=torch_mod.float64, device="cuda:0"))
+    m.close()
     with pytest.raises(api.QPError):
         api.MultiSolver(desc, [torch_mod.cuda.device_count() + 3])

@@ -28,4 +28,11 @@ for share, chunk in settings:
     dt = (time.perf_counter() - t0) / 4
     if ref is None: ref = out.clone()
     print(os.environ.get("TUNE_TAG", ""), "G=%d share=%s chunk=%s  %.2f ms/step  %.2f M solves/s  bitwise_equal_to_first=%s" % (G, share, chunk, dt * 1e3, B / dt / 1e6, bool(torch.equal(out, ref))), flush=True)
+    dst = torch.from_numpy(st).cuda()
+    for _ in range(2): m.solve_states(dst, out=out)
+    t0 = time.perf_counter()
+    for _ in range(4): m.solve_states(dst, out=out)
+    dts = (time.perf_counter() - t0) / 4
+    print("      states on the root: %.2f ms/step  %.2f M solves/s  bitwise_equal=%s" % (dts * 1e3, B / dts / 1e6, bool(torch.equal(out, ref))), flush=True)
+    del dst
     m.close()
