@@ -48,6 +48,9 @@
 #ifndef QPPVM_GS_RATIO
 #define QPPVM_GS_RATIO 0.5       // ... i.e. when |w2|^2 < QPPVM_GS_RATIO |w|^2 after the first pass
 #endif
+#ifndef QPPVM_PREP_INPLACE
+#define QPPVM_PREP_INPLACE 1     // prepare kernel: the whitened equality normals overwrite the equality rows (4.9 KB less per pair: a 4th CTA per SM for the 51-variable shapes)
+#endif
 namespace qppvm {
 
 // Active-set capacity KMAX (eq + ineq, <= 32 so one warp lane per active row), per problem shape.
@@ -1020,8 +1023,8 @@ __device__ __noinline__ void factor_qr(int j, double* Jm, const double* Ad, cons
             for (int r = 0; r + 1 < MD; r += 2) { sg0 = fma(col[r], col[r], sg0); sg1 = fma(col[r + 1], col[r + 1], sg1); }
             if (MD & 1) sg0 = fma(col[MD - 1], col[MD - 1], sg0);
             const double sigma = sg0 + sg1;
-            const double alpha = sqrt(dg[kc] + eps);
             double v1 = 0.0, tau = 0.0;
+            const double alpha = sqrt(dg[kc] + eps);
             if (sigma != 0.0) {
                 const double nrm = sqrt(fma(alpha, alpha, sigma));
                 v1 = -sigma / (alpha + nrm);               // alpha - nrm, cancellation-free (alpha >= 0)
@@ -2115,16 +2118,26 @@ struct FactorShape {
     // (Ad | dg | db are reused for the NEQ x N equality rows: wide shapes with few task rows pad Ad)
     static constexpr int SZ_AD_RAW = MD * LDA > NEQ * N - 2 * VEC ? MD * LDA : NEQ * N - 2 * VEC;
     static constexpr int O_AD = SZ_J, O_DG = O_AD + SZ_AD_RAW + (SZ_AD_RAW & 1), O_DB = O_DG + VEC, O_U0 = O_DB + VEC;
+#if QPPVM_PREP_INPLACE
+    // the whitened normals overwrite the equality rows in place (every lane keeps its column of all rows in registers
+    // across one barrier): no separate NEQ x N block
+    static constexpr int O_JD = O_U0 + VEC, O_BC = O_JD + VEC, O_WQ = O_AD;
+    static constexpr int O_RN = O_BC + 2 * (MD + 4), O_RDI = O_RN + NEQ * NEQ, BLOCK = O_RDI + NEQ;
+#else
     static constexpr int O_JD = O_U0 + VEC, O_BC = O_JD + VEC, O_WQ = O_BC + 2 * (MD + 4);
     static constexpr int O_RN = O_WQ + NEQ * N + ((NEQ * N) & 1), O_RDI = O_RN + NEQ * NEQ, BLOCK = O_RDI + NEQ;
+#endif
     static_assert(O_U0 - O_AD >= NEQ * N, "equality rows fit over Ad | dg | db");
     static_assert(2 * (MD + 4) >= NEQ, "right-hand sides fit in the broadcast slots");
     static_assert(FPC <= THREADS / 32, "one warp per pair in the orthogonalisation phase");
     static constexpr int BYTES = FPC * BLOCK * 8;
+    // resident CTAs per SM the shared memory allows (the register budget follows through __launch_bounds__), at most 4
+    static constexpr int CTAS_RAW = 233472 / (BYTES + 1024);
+    static constexpr int CTAS = QPPVM_PREP_INPLACE ? (CTAS_RAW > 4 ? 4 : (CTAS_RAW < 1 ? 1 : CTAS_RAW)) : 1;
 };
 
 template <class P>
-__global__ void __launch_bounds__(FactorShape<P>::THREADS)
+__global__ void __launch_bounds__(FactorShape<P>::THREADS, FactorShape<P>::CTAS)
 qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long long batch, Params prm,
                  unsigned long long* __restrict__ counter, Tick tk)
 {
@@ -2215,11 +2228,11 @@ qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long 
         }
         __syncthreads();
         // whitened normals w_e = J^T a_e, all rows at once (lane j: column j of J against every row)
-        if (live) {
-            if (lane < P::NB) {
-                double acc[F::NEQ];
+        {
+            double acc[F::NEQ];
 #pragma unroll
-                for (int e = 0; e < F::NEQ; ++e) acc[e] = 0.0;
+            for (int e = 0; e < F::NEQ; ++e) acc[e] = 0.0;
+            if (live && lane < P::NB) {
                 const double* col = Jm + lane * (lane + 1) / 2;
 #pragma unroll 1
                 for (int i = 0; i <= lane; ++i) {
@@ -2227,13 +2240,18 @@ qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long 
 #pragma unroll
                     for (int e = 0; e < F::NEQ; ++e) acc[e] = fma(jv, Aeq[e * N + i], acc[e]);
                 }
-#pragma unroll
-                for (int e = 0; e < F::NEQ; ++e) WQ[e * N + lane] = acc[e];
             }
-            for (int jj = P::NB + lane; jj < N; jj += F::GS) {
-                const double dj = jd[jj];
+            if (F::O_WQ == F::O_AD) __syncthreads();           // in place: every lane has read the rows it needs
+            if (live) {
+                if (lane < P::NB) {
 #pragma unroll
-                for (int e = 0; e < F::NEQ; ++e) WQ[e * N + jj] = dj * Aeq[e * N + jj];
+                    for (int e = 0; e < F::NEQ; ++e) WQ[e * N + lane] = acc[e];
+                }
+                for (int jj = P::NB + lane; jj < N; jj += F::GS) {
+                    const double dj = jd[jj];
+#pragma unroll
+                    for (int e = 0; e < F::NEQ; ++e) WQ[e * N + jj] = dj * Aeq[e * N + jj];
+                }
             }
         }
         __syncthreads();
