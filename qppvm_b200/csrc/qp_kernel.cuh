@@ -48,6 +48,10 @@
 #ifndef QPPVM_GS_RATIO
 #define QPPVM_GS_RATIO 0.5       // ... i.e. when |w2|^2 < QPPVM_GS_RATIO |w|^2 after the first pass
 #endif
+#ifndef QPPVM_WS_COMPACT_Q
+#define QPPVM_WS_COMPACT_Q 2     // the prepare workspace carries the n_eq filled columns of Q1 only (N x n_eq, contiguous), not the whole N x LDQ block;
+                                 // 1: the solve kernel fetches them with plain loads, 2: with one bulk copy into the tail of the Q1 region + a scatter in shared memory
+#endif
 #ifndef QPPVM_PREP_INPLACE
 #define QPPVM_PREP_INPLACE 1     // prepare kernel: the whitened equality normals overwrite the equality rows (4.9 KB less per pair: a 4th CTA per SM for the 51-variable shapes)
 #endif
@@ -360,7 +364,7 @@ struct ForceAcc {
     // (dense-force shapes: the helper lanes of the triangular products exchange through KP >= (NB - 1) / 2 slots)
     static constexpr int KMAX = (KMAX_RAW == 32 && N > 48) ? 31 : ((COM && KMAX_RAW < (N + 1) / 2) ? (N + 1) / 2 : KMAX_RAW);
     template <int TEAM> __device__ static __forceinline__ bool prepare(const double*, double*, int) { return true; }
-    __device__ static __forceinline__ int n_eq(int level) { return level == 0 ? 6 : 12; }
+    __host__ __device__ static constexpr int n_eq(int level) { return level == 0 ? 6 : 12; }
     __device__ static __forceinline__ int eq_row(int level, int e) { return e < 6 ? ROW_DYN + e : ROW_OPT + (e - 6); }
     __device__ static __forceinline__ bool regularised(int) { return true; }   // Cartesian/postural: HST_SEMIDEF
     // Coefficient jc of equality row e as (record offset, sign), -1: zero.  Same rows as build_row (dyn-feas base
@@ -941,7 +945,16 @@ struct Slab {
     // filled) | RN columns [c][LDR] | 1/diag + fallback flag | point after the equalities with a known rhs
     static constexpr int NEQ_MAX = 12;
     static constexpr int WS_U0 = SZ_J, WS_JD = WS_U0 + VEC, WS_Q = WS_JD + VEC;
+    // (staged fetch of the compact Q1: it lands in the last WSZ_Q doubles of the Q1 region)
+    static constexpr int Q_STAGE = SZ_Q - (N * NEQ_MAX + ((N * NEQ_MAX) & 1));
+    static_assert(!P::SPLIT_FACTOR || (Q_STAGE >= 0 && ((O_Q + Q_STAGE) % 2) == 0), "staging block inside the Q1 region, 16-byte aligned");
+#if QPPVM_WS_COMPACT_Q
+    // Q1 of the equality rows, compact: (i, c) at i n_eq + c -- 2.4 / 4.9 KB per level instead of the 12.6 KB block of the
+    // shared-memory layout (whose columns >= n_eq the prepare kernel never wrote, but the bulk copy fetched)
+    static constexpr int WSZ_Q = N * NEQ_MAX + ((N * NEQ_MAX) & 1), WS_RN = WS_Q + WSZ_Q;
+#else
     static constexpr int WSZ_Q = N * LDQ + ((N * LDQ) & 1), WS_RN = WS_Q + WSZ_Q;
+#endif
     static constexpr int WSZ_RN = NEQ_MAX * (NEQ_MAX + 1) / 2 + ((NEQ_MAX * (NEQ_MAX + 1) / 2) & 1), WS_RDI = WS_RN + WSZ_RN;
     static constexpr int WSZ_RDI = NEQ_MAX + 2, WS_FLAG = WS_RDI + NEQ_MAX, WS_U = WS_RDI + WSZ_RDI;
     static constexpr int WS_RI = WS_U + VEC;          // inverse of the equality block of RN, packed like RN
@@ -1668,23 +1681,61 @@ struct Solver {
             md = level == 0 ? P::MD0 : P::MD1;
             if (tid == 0) {
                 const double* wsl = ws_() + level * S::WS_LEVEL;
-                constexpr uint32_t B_J = S::SZ_J * 8, B_V = S::VEC * 8, B_Q = S::WSZ_Q * 8, B_RN = S::WSZ_RN * 8, B_RDI = S::WSZ_RDI * 8;
-                bulk_expect(mbar_ws_(), (P::J_GLOBAL ? 0 : B_J) + 3 * B_V + B_Q + 2 * B_RN + B_RDI);
+                constexpr uint32_t B_J = S::SZ_J * 8, B_V = S::VEC * 8, B_Q = QPPVM_WS_COMPACT_Q ? 0 : S::WSZ_Q * 8, B_RN = S::WSZ_RN * 8, B_RDI = S::WSZ_RDI * 8;
+                // (compact Q1, staged: the N x n_eq block lands in the tail of the Q1 region, see below)
+                const uint32_t B_QS = QPPVM_WS_COMPACT_Q == 2 ? (uint32_t)(((N * P::n_eq(level) + 1) & ~1) * 8) : 0u;
+                bulk_expect(mbar_ws_(), (P::J_GLOBAL ? 0 : B_J) + 3 * B_V + B_Q + B_QS + 2 * B_RN + B_RDI);
+                if (QPPVM_WS_COMPACT_Q == 2) bulk_copy(Q1 + S::Q_STAGE, wsl + S::WS_Q, B_QS, mbar_ws_());
                 if (P::J_GLOBAL) jptr_() = const_cast<double*>(wsl);
                 else bulk_copy(Jm, wsl, B_J, mbar_ws_());
                 bulk_copy(u0, wsl + S::WS_U0, B_V, mbar_ws_());
                 bulk_copy(jd, wsl + S::WS_JD, B_V, mbar_ws_());
-                bulk_copy(Q1, wsl + S::WS_Q, B_Q, mbar_ws_());
+                if (!QPPVM_WS_COMPACT_Q) bulk_copy(Q1, wsl + S::WS_Q, B_Q, mbar_ws_());
                 bulk_copy(RN, wsl + S::WS_RN, B_RN, mbar_ws_());
                 bulk_copy(rdi, wsl + S::WS_RDI, B_RDI, mbar_ws_());
                 bulk_copy(u, wsl + S::WS_U, B_V, mbar_ws_());
                 bulk_copy(RI, wsl + S::WS_RI, B_RN, mbar_ws_());
             }
+#if QPPVM_WS_COMPACT_Q == 1
+            {   // the n_eq equality columns of Q1 (compact in the workspace) into their strided home, coalesced loads
+                const double* const qws = ws_() + level * S::WS_LEVEL + S::WS_Q;
+                static_assert(P::n_eq(1) <= S::NEQ_MAX, "equality columns fit the workspace block");
+                if (level == 0) {
+                    constexpr int NE = P::n_eq(0);
+                    for (int t = tid; t < N * NE; t += TEAM) { const int i = t / NE; Q1[i * LDQ + (t - i * NE)] = qws[t]; }
+                } else {
+                    constexpr int NE = P::n_eq(1);
+                    for (int t = tid; t < N * NE; t += TEAM) { const int i = t / NE; Q1[i * LDQ + (t - i * NE)] = qws[t]; }
+                }
+            }
+#endif
             init_cstate(level, wmask);
             mbar_wait(mbar_ws_(), (uint32_t)st[3]);
             tm::sync();
+#if QPPVM_WS_COMPACT_Q == 2
+            // compact Q1 (i, c) -> its strided home i LDQ + c.  Source (tail of the Q1 region) and targets overlap: every
+            // thread takes its elements into registers, the barrier below separates the reads from the writes
+            constexpr int QPT = (N * S::NEQ_MAX + TEAM - 1) / TEAM;
+            double qv[QPT];
+            {
+                const int ne = P::n_eq(level);
+#pragma unroll
+                for (int m = 0; m < QPT; ++m) { const int t = tid + m * TEAM; qv[m] = t < N * ne ? Q1[S::Q_STAGE + t] : 0.0; }
+            }
+#endif
             const bool prepared = rdi[S::NEQ_MAX] == 0.0;
             tm::sync();
+#if QPPVM_WS_COMPACT_Q == 2
+            if (level == 0) {
+                constexpr int NE = P::n_eq(0);
+#pragma unroll
+                for (int m = 0; m < QPT; ++m) { const int t = tid + m * TEAM, i = t / NE; if (t < N * NE) Q1[i * LDQ + (t - i * NE)] = qv[m]; }
+            } else {
+                constexpr int NE = P::n_eq(1);
+#pragma unroll
+                for (int m = 0; m < QPT; ++m) { const int t = tid + m * TEAM, i = t / NE; if (t < N * NE) Q1[i * LDQ + (t - i * NE)] = qv[m]; }
+            }
+#endif
             if (tid == 0) { st[3] ^= 1; st[0] = 0; st[1] = 0; }
             if (prepared && P::n_eq(level) > max_iter) status = QPPVM_STATUS_MAX_ITER;   // as the row-by-row path would
             else if (prepared) adopt_equalities(level);
@@ -2313,9 +2364,9 @@ qp_factor_kernel(const double* __restrict__ recs, double* __restrict__ ws, long 
                     }
                     __syncwarp();
                 }
-                for (int t2 = l; t2 < wneq * N; t2 += 32) {      // Q1's row-major home: (i, c) -> i LDQ + c
+                for (int t2 = l; t2 < wneq * N; t2 += 32) {      // Q1 row-major: (i, c) -> i n_eq + c (compact) or its shared-memory home i LDQ + c
                     const int i = t2 / wneq, c = t2 - i * wneq;
-                    wso[S::WS_Q + i * S::LDQ + c] = Wq[c * N + i];
+                    wso[S::WS_Q + (QPPVM_WS_COMPACT_Q ? t2 : i * S::LDQ + c)] = Wq[c * N + i];
                 }
                 for (int t2 = l; t2 < wneq * F::NEQ; t2 += 32) {
                     const int c = t2 / F::NEQ, r = t2 - c * F::NEQ;
